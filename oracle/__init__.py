@@ -1,0 +1,198 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes front-end of the CPU oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product package
+``edge_based_visual_odometry_b200`` never imports it.
+
+Two libraries:
+
+* ``oracle/libebvo_oracle.so``  - our restatement (``toed_oracle.c`` + ``stereo_oracle.cpp``)
+* ``oracle/_ref/libtoed_ref.so`` - the UNMODIFIED reference TOED source compiled in place from
+  ``/root/reference/src/toed/cpu_toed.cpp`` (built here, shipped to the GPU box as a binary)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+STAGES = ["epi", "disp", "orient", "sift", "ncc", "bnb_ncc", "bnb_sift", "shift", "gn", "cluster", "ncc2", "best"]
+
+
+def build(force: bool = False) -> None:
+    """Compile the restatement and, when /root/reference exists, oracle/_ref."""
+    need = force or not os.path.exists(os.path.join(_DIR, "libebvo_oracle.so"))
+    if not need:
+        so = os.path.getmtime(os.path.join(_DIR, "libebvo_oracle.so"))
+        need = any(os.path.getmtime(os.path.join(_DIR, f)) > so for f in ("toed_oracle.c", "stereo_oracle.cpp"))
+    if need:
+        subprocess.check_call(["make", "-C", _DIR, "libebvo_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/src/toed/cpu_toed.cpp") and (
+            force or not os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))):
+        subprocess.check_call(["make", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_DIR, "libebvo_oracle.so"))
+        L.toed_oracle.restype = C.c_int
+        L.so_run.restype = C.c_void_p
+        L.so_patch_similarity.restype = C.c_double
+        L.so_num_mates.restype = C.c_int
+        L.so_stage_total.restype = C.c_int
+        L.so_cluster.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))
+
+
+def ref():
+    global _REF
+    if _REF is None:
+        build()
+        R = C.CDLL(os.path.join(_DIR, "_ref", "libtoed_ref.so"))
+        R.toed_ref_run.restype = C.c_int
+        R.toed_ref_create.restype = C.c_void_p
+        R.toed_ref_detect.restype = C.c_int
+        R.toed_ref_fetch.restype = C.c_int
+        R.toed_ref_num_procs.restype = C.c_int
+        _REF = R
+    return _REF
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def toed_reference(img: np.ndarray, threads: int = 0):
+    """Run the compiled reference detector.  Returns (edges[n,3], n_total, time_conv, time_nms)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    cap = 4 * H * W
+    out = np.zeros((cap, 3))
+    nt, tc, tn = C.c_int(), C.c_double(), C.c_double()
+    n = ref().toed_ref_run(_p(img), H, W, W, _p(out), cap, C.byref(nt), None, 0, C.byref(tc), C.byref(tn), threads)
+    return out[:n].copy(), nt.value, tc.value, tn.value
+
+
+def toed(img: np.ndarray, want_maps: bool = False):
+    """Run the restatement.  Returns (edges[n,3], n_total[, maps[7,2H,2W]])."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    cap = 4 * H * W
+    out = np.zeros((cap, 3))
+    nt = C.c_int()
+    maps = np.zeros((7, 2 * H, 2 * W)) if want_maps else None
+    n = lib().toed_oracle(_p(img), H, W, W, _p(out), cap, C.byref(nt), _p(maps), None, 0)
+    if want_maps:
+        return out[:n].copy(), nt.value, maps
+    return out[:n].copy(), nt.value
+
+
+def fundamental(Kl, Kr, R21, T21):
+    a = [np.ascontiguousarray(m, dtype=np.float64) for m in (Kl, Kr, R21, T21)]
+    F21, F12 = np.zeros((3, 3)), np.zeros((3, 3))
+    lib().so_fundamental(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(F21), _p(F12))
+    return F21, F12
+
+
+def sobel(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    gx, gy = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+    lib().so_sobel(_p(img), H, W, _p(gx), _p(gy))
+    return gx, gy
+
+
+def edge_patches(img, x, y, th):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    p, m = np.zeros(49, np.float32), np.zeros(49, np.float32)
+    lib().so_edge_patches(_p(img), H, W, C.c_double(x), C.c_double(y), C.c_double(th), _p(p), _p(m))
+    return p.reshape(7, 7), m.reshape(7, 7)
+
+
+def patch_similarity(a, b) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+    b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+    return lib().so_patch_similarity(_p(a), _p(b))
+
+
+def cluster(xyt, by_orientation=True):
+    xyt = np.ascontiguousarray(xyt, dtype=np.float64).reshape(-1, 3)
+    n = len(xyt)
+    cen, lab = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.int32)
+    k = lib().so_cluster(_p(xyt), n, int(by_orientation), _p(cen), _p(lab))
+    return cen[:k].copy(), lab[:n].copy()
+
+
+def shift_to_line(line, x, y, th):
+    line = np.ascontiguousarray(line, dtype=np.float64)
+    out = np.zeros(3)
+    lib().so_shift_to_line(_p(line), C.c_double(x), C.c_double(y), C.c_double(th), _p(out))
+    return out
+
+
+class StereoResult:
+    """Stage dumps + final mates of one oracle run."""
+
+    def __init__(self, h, nL, want_dumps):
+        L = lib()
+        n = L.so_num_mates(C.c_void_p(h))
+        self.mate_left = np.zeros(n, np.int32)
+        self.mate_right = np.zeros((n, 3))
+        rx, ry, rth = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.mate_score = np.zeros(n)
+        L.so_get_mates(C.c_void_p(h), _p(self.mate_left), _p(rx), _p(ry), _p(rth), _p(self.mate_score))
+        self.mate_right[:, 0], self.mate_right[:, 1], self.mate_right[:, 2] = rx, ry, rth
+        self.lines = np.zeros((nL, 3))
+        L.so_get_lines(C.c_void_p(h), _p(self.lines))
+        t = np.zeros(len(STAGES))
+        cnt = (C.c_long * 5)()
+        L.so_get_stats(C.c_void_p(h), _p(t), cnt)
+        self.stage_seconds = dict(zip(STAGES, t.tolist()))
+        self.counts = dict(zip(["s1_total", "ncc_pairs1", "ncc_pairs2", "gn_pairs", "gn_iters"], list(cnt)))
+        self.stages = {}
+        if want_dumps:
+            for k, name in enumerate(STAGES):
+                tot = L.so_stage_total(C.c_void_p(h), k)
+                if tot < 0:
+                    continue
+                off = np.zeros(nL + 1, np.int32)
+                ridx = np.zeros(tot, np.int32)
+                x, y, th, sc = (np.zeros(tot) for _ in range(4))
+                L.so_get_stage(C.c_void_p(h), k, _p(off), _p(ridx), _p(x), _p(y), _p(th), _p(sc))
+                self.stages[name] = dict(off=off, ridx=ridx, x=x, y=y, th=th, score=sc)
+        L.so_free(C.c_void_p(h))
+
+
+def stereo(Lraw, Rraw, Ledges, Redges, F21, Lund=None, Rund=None, descL=None, descR=None,
+           want_dumps=True, threads=0) -> StereoResult:
+    """Run the stereo restatement on one pair (no-GT branch)."""
+    Lraw = np.ascontiguousarray(Lraw, dtype=np.uint8)
+    Rraw = np.ascontiguousarray(Rraw, dtype=np.uint8)
+    Lund = Lraw if Lund is None else np.ascontiguousarray(Lund, dtype=np.uint8)
+    Rund = Rraw if Rund is None else np.ascontiguousarray(Rund, dtype=np.uint8)
+    H, W = Lraw.shape
+    Le = np.ascontiguousarray(Ledges, dtype=np.float64).reshape(-1, 3)
+    Re = np.ascontiguousarray(Redges, dtype=np.float64).reshape(-1, 3)
+    F = np.ascontiguousarray(F21, dtype=np.float64)
+    mode = 0
+    if descL is not None:
+        mode = 1
+        descL = np.ascontiguousarray(descL, dtype=np.float32)
+        descR = np.ascontiguousarray(descR, dtype=np.float32)
+    h = lib().so_run(_p(Lraw), _p(Rraw), _p(Lund), _p(Rund), H, W, _p(Le), len(Le), _p(Re), len(Re), _p(F),
+                     mode, _p(descL), _p(descR), int(want_dumps), threads)
+    return StereoResult(h, len(Le), want_dumps)
