@@ -1,0 +1,715 @@
+// C ABI of libebvo_b200.so (see include/ebvo_b200.h).  Host-side context, buffers, copies and launch order.
+#include "ebvo_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+namespace ebvo {
+
+int Prof::index_of(const char* name)
+{
+    for (size_t k = 0; k < names.size(); ++k) if (names[k] == name) return (int)k;
+    names.push_back(name); ms.push_back(0.f); launches.push_back(0);
+    return (int)names.size() - 1;
+}
+void Prof::begin(const char* name, cudaStream_t st)
+{
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    pending.push_back({a, b});
+    pendingIdx.push_back(index_of(name));
+}
+void Prof::end(cudaStream_t st) { cudaEventRecord(pending.back().second, st); }
+void Prof::collect()
+{
+    for (size_t k = 0; k < pending.size(); ++k) {
+        float t = 0.f;
+        cudaEventSynchronize(pending[k].second);
+        cudaEventElapsedTime(&t, pending[k].first, pending[k].second);
+        ms[pendingIdx[k]] += t; launches[pendingIdx[k]] += 1;
+        cudaEventDestroy(pending[k].first); cudaEventDestroy(pending[k].second);
+    }
+    pending.clear(); pendingIdx.clear();
+    cnames.clear();
+    for (auto& s : names) cnames.push_back(s.c_str());
+}
+void Prof::reset()
+{
+    for (auto& e : pending) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    pending.clear(); pendingIdx.clear();
+    std::fill(ms.begin(), ms.end(), 0.f); std::fill(launches.begin(), launches.end(), 0);
+}
+
+struct StageData {
+    bool valid = false;
+    std::vector<int> off, ridx;
+    std::vector<double> x, y, th, score;
+};
+
+}  // namespace ebvo
+
+using namespace ebvo;
+
+struct ebvo_ctx {
+    int device = 0, maxW = 0, maxH = 0, maxB = 0, E = 0, P = 0;
+    ebvo_params params;
+    DevParams dp;
+    cudaStream_t st = nullptr;
+    std::string err;
+    DevBatch b;
+    uint8_t* d_raw = nullptr; uint8_t* d_und = nullptr;   // d_und: 2 images, only for ebvo_stereo_match with distinct undistorted inputs
+    size_t imgStrideMax = 0;
+    ebvo_mate* d_out = nullptr;   // [maxB][E] compacted mates
+    float *d_descL = nullptr, *d_descR = nullptr; size_t descCap = 0;
+    std::vector<void*> allocs;
+    Prof prof;
+    bool dumpsEnabled = false;
+    bool dumpAllocated = false;
+    StageData stages[EBVO_STAGE_COUNT];
+    int stageNL = 0;
+    int curFrames = 0;
+    std::vector<int> h_counts;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf[512];                                                                         \
+            snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = buf;                                                                        \
+            return EBVO_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(ebvo_ctx* ctx, T** p, size_t n)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
+    if (e == cudaSuccess) { ctx->allocs.push_back(q); *p = (T*)q; }
+    return e;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void set_devparams(ebvo_ctx* ctx)
+{
+    const ebvo_params& q = ctx->params;
+    DevParams& d = ctx->dp;
+    d.epi = q.epipolar_line_dist_thresh; d.maxdisp = q.max_disparity; d.orient_deg = q.orientation_thresh_deg;
+    d.shift_mag = q.orthogonal_shift_mag; d.ncc_thresh = q.ncc_thresh; d.bnb_ncc = q.bnb_ncc; d.bnb_sift = q.bnb_sift;
+    d.sift_thresh = q.sift_threshold; d.loc_pert = q.location_perturbation; d.tang_displ = q.epip_tangency_displ_thresh;
+    d.orient_pert = q.orient_perturbation; d.clus_dist = q.cluster_dist_thresh;
+    d.clus_orient_rad = q.cluster_orient_thresh_deg * (M_PI / 180.0);   // deg_to_rad, include/utility.h:293-297
+    d.clus_sigma = q.cluster_orient_gauss_sigma; d.clus_max = q.max_cluster_size; d.gn_max_iter = q.gn_max_iter;
+    d.gn_tol = q.gn_tol; d.gn_huber = q.gn_huber_delta; d.toed_mag_thresh = (float)q.toed_mag_thresh; d.toed_border = q.toed_border;
+}
+
+// geometry-dependent fields of the device view
+int configure(ebvo_ctx* ctx, int w, int h, int nFrames)
+{
+    if (w <= 0 || h <= 0 || w > ctx->maxW || h > ctx->maxH || w >= 32768 || h >= 32768) { ctx->err = "image size exceeds the context's max_w/max_h"; return EBVO_ERR_INVALID; }
+    if (nFrames < 1 || nFrames > ctx->maxB) { ctx->err = "n_frames exceeds the context's max_batch"; return EBVO_ERR_INVALID; }
+    DevBatch& b = ctx->b;
+    b.W = w; b.H = h; b.pitch = (int)align_up(w, 16);
+    b.W2 = 2 * w; b.H2 = 2 * h;
+    b.tilesX = (w + TW - 1) / TW; b.tilesY = (h + TH - 1) / TH;
+    b.maskPitch = 2 * b.tilesX; b.maskRows = 2 * TH * b.tilesY;
+    b.nFrames = nFrames; b.nImages = 2 * nFrames;
+    b.raw = ctx->d_raw; b.und = ctx->d_raw;
+    b.descL = nullptr; b.descR = nullptr;
+    b.dumps = 0;
+    ctx->curFrames = nFrames;
+    return EBVO_OK;
+}
+
+int upload_image(ebvo_ctx* ctx, uint8_t* base, int slot, const uint8_t* src, int stride)
+{
+    const DevBatch& b = ctx->b;
+    CK(cudaMemcpy2DAsync(base + (size_t)slot * b.imgStride, b.pitch, src, stride, b.W, b.H, cudaMemcpyHostToDevice, ctx->st));
+    return EBVO_OK;
+}
+
+int check_err_flag(ebvo_ctx* ctx)
+{
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->b.errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (flag) {
+        int zero = 0;
+        cudaMemcpyAsync(ctx->b.errFlag, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->st);
+        static const char* what[] = {"", "edge capacity (max_edges) exceeded", "candidate pool exhausted", "more than 128 NCC survivors for one left edge",
+                                     "more than 128 candidates entering the clusterer for one left edge"};
+        ctx->err = std::string("capacity: ") + what[flag < 5 ? flag : 0];
+        return EBVO_ERR_CAPACITY;
+    }
+    return EBVO_OK;
+}
+
+int ensure_dump_buffers(ebvo_ctx* ctx)
+{
+    if (ctx->dumpAllocated) return EBVO_OK;
+    for (int k = 0; k < DUMP_COUNT; ++k) {
+        DumpBuf& d = ctx->b.dump[k];
+        CK(dalloc(ctx, &d.n, (size_t)ctx->E)); CK(dalloc(ctx, &d.ridx, (size_t)ctx->P));
+        CK(dalloc(ctx, &d.x, (size_t)ctx->P)); CK(dalloc(ctx, &d.y, (size_t)ctx->P));
+        CK(dalloc(ctx, &d.th, (size_t)ctx->P)); CK(dalloc(ctx, &d.score, (size_t)ctx->P));
+    }
+    ctx->dumpAllocated = true;
+    return EBVO_OK;
+}
+
+// host exclusive scan of per-left-edge counts -> offsets on host and device
+int scan_counts(ebvo_ctx* ctx, const int* d_counts, int nL, std::vector<int>& off, int** d_off)
+{
+    std::vector<int> cnt(nL);
+    if (nL) CK(cudaMemcpyAsync(cnt.data(), d_counts, sizeof(int) * nL, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    off.assign(nL + 1, 0);
+    for (int i = 0; i < nL; ++i) off[i + 1] = off[i] + cnt[i];
+    CK(cudaMalloc(d_off, sizeof(int) * (nL + 1)));
+    CK(cudaMemcpyAsync(*d_off, off.data(), sizeof(int) * (nL + 1), cudaMemcpyHostToDevice, ctx->st));
+    return EBVO_OK;
+}
+
+int snapshot_stage(ebvo_ctx* ctx, int stage, int src, int nL)
+{
+    StageData& S = ctx->stages[stage];
+    const int* d_counts = src < 0 ? ctx->b.ccount : ctx->b.dump[src].n;
+    int* d_off = nullptr;
+    int rc = scan_counts(ctx, d_counts, nL, S.off, &d_off);
+    if (rc) return rc;
+    const size_t tot = S.off[nL];
+    S.ridx.assign(tot, -1); S.x.assign(tot, 0); S.y.assign(tot, 0); S.th.assign(tot, 0); S.score.assign(tot, 0);
+    if (tot) {
+        int* d_r; double *d_x, *d_y, *d_t, *d_s;
+        CK(cudaMalloc(&d_r, tot * 4)); CK(cudaMalloc(&d_x, tot * 8)); CK(cudaMalloc(&d_y, tot * 8)); CK(cudaMalloc(&d_t, tot * 8)); CK(cudaMalloc(&d_s, tot * 8));
+        launch_snapshot(ctx->b, src, d_off, d_r, d_x, d_y, d_t, d_s, ctx->st);
+        CK(cudaMemcpyAsync(S.ridx.data(), d_r, tot * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(S.x.data(), d_x, tot * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(S.y.data(), d_y, tot * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(S.th.data(), d_t, tot * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(S.score.data(), d_s, tot * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        cudaFree(d_r); cudaFree(d_x); cudaFree(d_y); cudaFree(d_t); cudaFree(d_s);
+    }
+    cudaFree(d_off);
+    S.valid = true;
+    return EBVO_OK;
+}
+
+int gate_stage(ebvo_ctx* ctx, int stage, int mode, const double* F21, int nL, const std::vector<double>& rx, const std::vector<double>& ry,
+               const std::vector<double>& rth)
+{
+    StageData& S = ctx->stages[stage];
+    int* d_counts = nullptr;
+    CK(cudaMalloc(&d_counts, sizeof(int) * (nL + 1)));
+    launch_gate_count(ctx->b, ctx->dp, F21, mode, d_counts, ctx->st);
+    int* d_off = nullptr;
+    int rc = scan_counts(ctx, d_counts, nL, S.off, &d_off);
+    if (rc) return rc;
+    const size_t tot = S.off[nL];
+    S.ridx.assign(tot, -1);
+    if (tot) {
+        int* d_r;
+        CK(cudaMalloc(&d_r, tot * 4));
+        launch_gate_fill(ctx->b, ctx->dp, F21, mode, d_off, d_r, ctx->st);
+        CK(cudaMemcpyAsync(S.ridx.data(), d_r, tot * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        cudaFree(d_r);
+    }
+    cudaFree(d_off); cudaFree(d_counts);
+    S.x.resize(tot); S.y.resize(tot); S.th.resize(tot);
+    S.score.assign(tot, std::numeric_limits<double>::quiet_NaN());
+    for (size_t k = 0; k < tot; ++k) { int r = S.ridx[k]; S.x[k] = rx[r]; S.y[k] = ry[r]; S.th[k] = rth[r]; }
+    S.valid = true;
+    return EBVO_OK;
+}
+
+int upload_edges(ebvo_ctx* ctx, int img, const ebvo_edge* e, int n, std::vector<double>* keepx = nullptr, std::vector<double>* keepy = nullptr,
+                 std::vector<double>* keept = nullptr)
+{
+    if (n > ctx->E) { ctx->err = "edge list longer than max_edges"; return EBVO_ERR_CAPACITY; }
+    std::vector<double> x(n), y(n), t(n);
+    for (int k = 0; k < n; ++k) { x[k] = e[k].x; y[k] = e[k].y; t[k] = e[k].theta; }
+    const DevBatch& b = ctx->b;
+    if (n) {
+        CK(cudaMemcpyAsync(b.ex + (size_t)img * b.E, x.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.ey + (size_t)img * b.E, y.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.eth + (size_t)img * b.E, t.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    }
+    CK(cudaMemcpyAsync(b.nE + img, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (keepx) { *keepx = x; *keepy = y; *keept = t; }
+    return EBVO_OK;
+}
+
+int download_edges(ebvo_ctx* ctx, int img, ebvo_edge* out, int cap, int* n_edges, int* n_total)
+{
+    const DevBatch& b = ctx->b;
+    int n = 0, nt = 0;
+    CK(cudaMemcpyAsync(&n, b.nE + img, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(&nt, b.nTot + img, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (n_edges) *n_edges = n;
+    if (n_total) *n_total = nt;
+    if (!out) return EBVO_OK;
+    const int m = std::min(n, cap);
+    std::vector<double> x(m), y(m), t(m);
+    if (m) {
+        CK(cudaMemcpyAsync(x.data(), b.ex + (size_t)img * b.E, 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(y.data(), b.ey + (size_t)img * b.E, 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaMemcpyAsync(t.data(), b.eth + (size_t)img * b.E, 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    for (int k = 0; k < m; ++k) { out[k].x = x[k]; out[k].y = y[k]; out[k].theta = t[k]; out[k].index = k; out[k].frame_source = -1; }
+    if (n > cap) { ctx->err = "output edge buffer too small"; return EBVO_ERR_CAPACITY; }
+    return EBVO_OK;
+}
+
+int download_mates(ebvo_ctx* ctx, int nFrames, ebvo_mate* out, int cap, int* n_mates)
+{
+    const DevBatch& b = ctx->b;
+    ctx->h_counts.resize(nFrames);
+    CK(cudaMemcpyAsync(ctx->h_counts.data(), b.nMates, sizeof(int) * nFrames, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    int rc = EBVO_OK;
+    for (int f = 0; f < nFrames; ++f) {
+        int n = ctx->h_counts[f];
+        if (n_mates) n_mates[f] = n;
+        int m = std::min(n, cap);
+        if (n > cap) { ctx->err = "output mate buffer too small"; rc = EBVO_ERR_CAPACITY; }
+        if (out && m) CK(cudaMemcpyAsync(out + (size_t)f * cap, ctx->d_out + (size_t)f * b.E, sizeof(ebvo_mate) * (size_t)m, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ebvo_params_default(ebvo_params* p)
+{
+    if (!p) return EBVO_ERR_INVALID;
+    p->epipolar_line_dist_thresh = 0.5; p->max_disparity = 25.0; p->orientation_thresh_deg = 10.0; p->orthogonal_shift_mag = 5.0;
+    p->ncc_thresh = 0.6; p->bnb_ncc = 0.9; p->bnb_sift = 0.4; p->sift_threshold = 500.0; p->location_perturbation = 0.4;
+    p->epip_tangency_displ_thresh = 3.0; p->orient_perturbation = 0.174533; p->cluster_dist_thresh = 1.0;
+    p->cluster_orient_thresh_deg = 20.0; p->cluster_orient_gauss_sigma = 2.0; p->max_cluster_size = 10; p->gn_max_iter = 20;
+    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->reserved = 0;
+    return EBVO_OK;
+}
+
+int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch, int max_edges, const ebvo_params* params)
+{
+    if (!out || max_w <= 0 || max_h <= 0 || max_batch <= 0 || max_edges <= 0) return EBVO_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return EBVO_ERR_NO_DEVICE;
+    ebvo_ctx* ctx = new ebvo_ctx;
+    ctx->device = device; ctx->maxW = max_w; ctx->maxH = max_h; ctx->maxB = max_batch;
+    ctx->E = (int)align_up(max_edges, 1024);
+    ctx->P = ctx->E * 8;
+    if (params) ctx->params = *params; else ebvo_params_default(&ctx->params);
+    set_devparams(ctx);
+    *out = ctx;   // returned even on failure so that ebvo_last_error() can be read; caller destroys it
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    upload_toed_tables();
+    DevBatch& b = ctx->b;
+    memset(&b, 0, sizeof b);
+    const int B = max_batch, nImg = 2 * B;
+    b.E = ctx->E; b.P = ctx->P; b.NB = ctx->E / 32;
+    const int tilesX = (max_w + TW - 1) / TW, tilesY = (max_h + TH - 1) / TH;
+    b.imgStride = align_up((size_t)align_up(max_w, 16) * max_h, 256);
+    b.maskStride = (size_t)(2 * tilesX) * (2 * TH * tilesY);
+    b.spStride = (size_t)(2 * max_w) * (2 * max_h);
+    b.rowStride = align_up((size_t)2 * max_h + 2, 32);
+    b.gStride = align_up((size_t)max_w * max_h, 64);
+    CK(dalloc(ctx, &ctx->d_raw, b.imgStride * nImg));
+    CK(dalloc(ctx, &ctx->d_und, b.imgStride * 2));
+    CK(dalloc(ctx, &b.mask, b.maskStride * nImg));
+    CK(dalloc(ctx, &b.sp, b.spStride * nImg));
+    CK(dalloc(ctx, &b.rowcnt, b.rowStride * nImg));
+    CK(dalloc(ctx, &b.rowoff, b.rowStride * nImg));
+    CK(dalloc(ctx, &b.coords, (size_t)b.E * nImg));
+    CK(dalloc(ctx, &b.ex, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.ey, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.eth, (size_t)b.E * nImg));
+    CK(dalloc(ctx, &b.nE, (size_t)nImg)); CK(dalloc(ctx, &b.nTot, (size_t)nImg));
+    CK(dalloc(ctx, &b.gx, b.gStride * B)); CK(dalloc(ctx, &b.gy, b.gStride * B));
+    CK(dalloc(ctx, &b.blk, (size_t)b.NB * B)); CK(dalloc(ctx, &b.pmax, (size_t)b.NB * B)); CK(dalloc(ctx, &b.smin, (size_t)b.NB * B));
+    CK(dalloc(ctx, &b.lines, (size_t)b.E * 3 * B));
+    CK(dalloc(ctx, &b.cstart, (size_t)b.E * B)); CK(dalloc(ctx, &b.ccount, (size_t)b.E * B));
+    CK(dalloc(ctx, &b.poolUsed, (size_t)B));
+    CK(dalloc(ctx, &b.c_ridx, (size_t)b.P * B));
+    CK(dalloc(ctx, &b.c_x, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_y, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_th, (size_t)b.P * B));
+    CK(dalloc(ctx, &b.c_score, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_conf, (size_t)b.P * B));
+    CK(dalloc(ctx, &b.mates, (size_t)b.E * B)); CK(dalloc(ctx, &b.nMates, (size_t)B)); CK(dalloc(ctx, &b.mateFlag, (size_t)b.E * B));
+    CK(dalloc(ctx, &b.errFlag, (size_t)4)); CK(dalloc(ctx, &b.counters, (size_t)8 * B));
+    CK(dalloc(ctx, &ctx->d_out, (size_t)b.E * B));
+    CK(dalloc(ctx, &b.dF, (size_t)16));
+    CK(cudaMemsetAsync(b.errFlag, 0, 16, ctx->st));
+    CK(cudaMemsetAsync(b.nE, 0, sizeof(int) * nImg, ctx->st));
+    CK(cudaMemsetAsync(b.nMates, 0, sizeof(int) * B, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return EBVO_OK;
+}
+
+void ebvo_destroy(ebvo_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    ctx->prof.reset();
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->d_descL) cudaFree(ctx->d_descL);
+    if (ctx->d_descR) cudaFree(ctx->d_descR);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+const char* ebvo_last_error(const ebvo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ebvo_fundamental(const ebvo_calib* c, double F21[9], double F12[9])
+{
+    if (!c || !F21) return EBVO_ERR_INVALID;
+    auto inv3 = [](const double* m, double* o) {
+        double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        o[0] = (m[4] * m[8] - m[5] * m[7]) / det; o[1] = (m[2] * m[7] - m[1] * m[8]) / det; o[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+        o[3] = (m[5] * m[6] - m[3] * m[8]) / det; o[4] = (m[0] * m[8] - m[2] * m[6]) / det; o[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+        o[6] = (m[3] * m[7] - m[4] * m[6]) / det; o[7] = (m[1] * m[6] - m[0] * m[7]) / det; o[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+    };
+    auto mul = [](const double* a, const double* b, double* o) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += a[i * 3 + k] * b[k * 3 + j]; o[i * 3 + j] = s; }
+    };
+    auto tr = [](const double* a, double* o) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[i * 3 + j] = a[j * 3 + i]; };
+    auto skew = [](const double* t, double* o) { o[0] = 0; o[1] = -t[2]; o[2] = t[1]; o[3] = t[2]; o[4] = 0; o[5] = -t[0]; o[6] = -t[1]; o[7] = t[0]; o[8] = 0; };
+    double Kli[9], Kri[9], KriT[9], KliT[9], S[9], SR[9], tmp[9];
+    inv3(c->Kl, Kli); inv3(c->Kr, Kri); tr(Kri, KriT); tr(Kli, KliT);
+    skew(c->T21, S); mul(S, c->R21, SR); mul(KriT, SR, tmp); mul(tmp, Kli, F21);   // Dataset.cpp:105
+    if (F12) {
+        double R12[9], T12[3];
+        tr(c->R21, R12);                                                           // Dataset.cpp:107-108
+        for (int i = 0; i < 3; ++i) T12[i] = -(R12[i * 3] * c->T21[0] + R12[i * 3 + 1] * c->T21[1] + R12[i * 3 + 2] * c->T21[2]);
+        skew(T12, S); mul(S, R12, SR); mul(KliT, SR, tmp); mul(tmp, Kri, F12);     // Dataset.cpp:111
+    }
+    return EBVO_OK;
+}
+
+int ebvo_toed(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, ebvo_edge* out, int cap, int* n_edges, int* n_total)
+{
+    if (!ctx || !img) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    ctx->prof.reset();
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, img, stride))) return rc;
+    launch_toed(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+    CK(cudaGetLastError());
+    if ((rc = check_err_flag(ctx))) return rc;
+    ctx->prof.collect();
+    return download_edges(ctx, 0, out, cap, n_edges, n_total);
+}
+
+static int run_match_with_dumps(ebvo_ctx* ctx, const double* F21, bool sift, int nL, const std::vector<double>& rx, const std::vector<double>& ry,
+                                const std::vector<double>& rth)
+{
+    int rc = ensure_dump_buffers(ctx);
+    if (rc) return rc;
+    ctx->b.dumps = 1;
+    for (auto& s : ctx->stages) s.valid = false;
+    ctx->stageNL = nL;
+    match_prologue(ctx->b, ctx->dp, F21, 1, ctx->st, &ctx->prof);
+    if ((rc = gate_stage(ctx, EBVO_STAGE_EPI, 0, F21, nL, rx, ry, rth))) return rc;
+    if ((rc = gate_stage(ctx, EBVO_STAGE_DISP, 1, F21, nL, rx, ry, rth))) return rc;
+    if ((rc = gate_stage(ctx, EBVO_STAGE_ORIENT, 2, F21, nL, rx, ry, rth))) return rc;
+    match_gate(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+    if (sift) {
+        match_sift(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+        // positions are not materialised before the NCC kernel: take them from the right-edge list
+        if ((rc = snapshot_stage(ctx, EBVO_STAGE_SIFT, -1, nL))) return rc;
+        StageData& S = ctx->stages[EBVO_STAGE_SIFT];
+        for (size_t k = 0; k < S.ridx.size(); ++k) { int r = S.ridx[k]; S.x[k] = rx[r]; S.y[k] = ry[r]; S.th[k] = rth[r]; S.score[k] = std::numeric_limits<double>::quiet_NaN(); }
+    } else ctx->stages[EBVO_STAGE_SIFT] = ctx->stages[EBVO_STAGE_ORIENT];
+    match_ncc(ctx->b, ctx->dp, 1, sift, ctx->st, &ctx->prof);
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_NCC, DUMP_S6, nL))) return rc;
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_BNB_NCC, DUMP_S7, nL))) return rc;
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_BNB_SIFT, -1, nL))) return rc;
+    match_gn(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_SHIFT, DUMP_S8, nL))) return rc;
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_GN, -1, nL))) return rc;
+    match_cluster(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_CLUSTER, DUMP_S10, nL))) return rc;
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_NCC2, DUMP_S11, nL))) return rc;
+    if ((rc = snapshot_stage(ctx, EBVO_STAGE_BEST, -1, nL))) return rc;
+    ctx->b.dumps = 0;
+    return EBVO_OK;
+}
+
+int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
+                      const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL, const ebvo_edge* R, int nR,
+                      const float* descL, const float* descR, ebvo_mate* out, int cap, int* n_mates)
+{
+    if (!ctx || !calib || !L_raw || !R_raw || (nL && !L) || (nR && !R) || nL < 0 || nR < 0) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    ctx->prof.reset();
+    if (!L_und) L_und = L_raw;
+    if (!R_und) R_und = R_raw;
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, L_raw, stride))) return rc;
+    if ((rc = upload_image(ctx, ctx->d_raw, 1, R_raw, stride))) return rc;
+    if (L_und != L_raw || R_und != R_raw) {
+        if ((rc = upload_image(ctx, ctx->d_und, 0, L_und, stride))) return rc;
+        if ((rc = upload_image(ctx, ctx->d_und, 1, R_und, stride))) return rc;
+        ctx->b.und = ctx->d_und;
+    }
+    std::vector<double> rx, ry, rth;
+    if ((rc = upload_edges(ctx, 0, L, nL))) return rc;
+    if ((rc = upload_edges(ctx, 1, R, nR, &rx, &ry, &rth))) return rc;
+    const bool sift = descL && descR;
+    if (sift) {
+        size_t need = (size_t)std::max(nL, nR) * 256;
+        if (need > ctx->descCap) {
+            if (ctx->d_descL) cudaFree(ctx->d_descL);
+            if (ctx->d_descR) cudaFree(ctx->d_descR);
+            CK(cudaMalloc(&ctx->d_descL, need * 4 + 256)); CK(cudaMalloc(&ctx->d_descR, need * 4 + 256));
+            ctx->descCap = need;
+        }
+        if (nL) CK(cudaMemcpyAsync(ctx->d_descL, descL, (size_t)nL * 256 * 4, cudaMemcpyHostToDevice, ctx->st));
+        if (nR) CK(cudaMemcpyAsync(ctx->d_descR, descR, (size_t)nR * 256 * 4, cudaMemcpyHostToDevice, ctx->st));
+        ctx->b.descL = ctx->d_descL; ctx->b.descR = ctx->d_descR;
+    }
+    double F21[9];
+    ebvo_fundamental(calib, F21, nullptr);
+    if (ctx->dumpsEnabled) {
+        if ((rc = run_match_with_dumps(ctx, F21, sift, nL, rx, ry, rth))) return rc;
+    } else launch_match(ctx->b, ctx->dp, F21, 1, sift, ctx->st, &ctx->prof);
+    launch_compact(ctx->b, 1, ctx->d_out, ctx->b.E, ctx->st, &ctx->prof);
+    CK(cudaGetLastError());
+    if ((rc = check_err_flag(ctx))) return rc;
+    ctx->prof.collect();
+    return download_mates(ctx, 1, out, cap, n_mates);
+}
+
+static int run_frames(ebvo_ctx* ctx, const ebvo_calib* calib, int nFrames, int do_match)
+{
+    launch_toed(ctx->b, ctx->dp, 2 * nFrames, ctx->st, &ctx->prof);
+    if (do_match) {
+        double F21[9];
+        ebvo_fundamental(calib, F21, nullptr);
+        launch_match(ctx->b, ctx->dp, F21, nFrames, false, ctx->st, &ctx->prof);
+        launch_compact(ctx->b, nFrames, ctx->d_out, ctx->b.E, ctx->st, &ctx->prof);
+    }
+    CK(cudaGetLastError());
+    return EBVO_OK;
+}
+
+int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_img, const uint8_t* R_img, int w, int h, int stride,
+                      ebvo_mate* out, int cap, int* n_mates, ebvo_edge* L_edges, int* nL, ebvo_edge* R_edges, int* nR, int edge_cap)
+{
+    if (!ctx || !calib || !L_img || !R_img) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    ctx->prof.reset();
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, L_img, stride))) return rc;
+    if ((rc = upload_image(ctx, ctx->d_raw, 1, R_img, stride))) return rc;
+    if ((rc = run_frames(ctx, calib, 1, 1))) return rc;
+    if ((rc = check_err_flag(ctx))) return rc;
+    ctx->prof.collect();
+    if ((rc = download_mates(ctx, 1, out, cap, n_mates))) return rc;
+    if (L_edges || nL) if ((rc = download_edges(ctx, 0, L_edges, edge_cap, nL, nullptr))) return rc;
+    if (R_edges || nR) if ((rc = download_edges(ctx, 1, R_edges, edge_cap, nR, nullptr))) return rc;
+    return EBVO_OK;
+}
+
+int ebvo_batch_upload(ebvo_ctx* ctx, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w, int h, int stride)
+{
+    if (!ctx || !L_imgs || !R_imgs) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, n_frames);
+    if (rc) return rc;
+    for (int f = 0; f < n_frames; ++f) {
+        if ((rc = upload_image(ctx, ctx->d_raw, 2 * f, L_imgs[f], stride))) return rc;
+        if ((rc = upload_image(ctx, ctx->d_raw, 2 * f + 1, R_imgs[f], stride))) return rc;
+    }
+    return EBVO_OK;
+}
+
+int ebvo_batch_run(ebvo_ctx* ctx, const ebvo_calib* calib, int do_match)
+{
+    if (!ctx || !calib || ctx->curFrames < 1) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return run_frames(ctx, calib, ctx->curFrames, do_match);
+}
+
+int ebvo_batch_sync(ebvo_ctx* ctx)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->st));
+    int rc = check_err_flag(ctx);
+    ctx->prof.collect();
+    return rc;
+}
+
+int ebvo_batch_download(ebvo_ctx* ctx, ebvo_mate* out, int cap, int* n_mates)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    return download_mates(ctx, ctx->curFrames, out, cap, n_mates);
+}
+
+int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* stage_counts)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    const int F = ctx->curFrames;
+    std::vector<int> nE(2 * F), nM(F);
+    CK(cudaMemcpyAsync(nE.data(), ctx->b.nE, sizeof(int) * 2 * F, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(nM.data(), ctx->b.nMates, sizeof(int) * F, cudaMemcpyDeviceToHost, ctx->st));
+    if (stage_counts) CK(cudaMemcpyAsync(stage_counts, ctx->b.counters, sizeof(long long) * 8 * F, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int f = 0; f < F; ++f) { if (nL) nL[f] = nE[2 * f]; if (nR) nR[f] = nE[2 * f + 1]; if (n_mates) n_mates[f] = nM[f]; }
+    return EBVO_OK;
+}
+
+int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
+                      int h, int stride, ebvo_mate* out, int cap, int* n_mates)
+{
+    if (!ctx || !calib) return EBVO_ERR_INVALID;
+    ctx->prof.reset();
+    int rc = ebvo_batch_upload(ctx, n_frames, L_imgs, R_imgs, w, h, stride);
+    if (rc) return rc;
+    if ((rc = run_frames(ctx, calib, n_frames, 1))) return rc;
+    if ((rc = check_err_flag(ctx))) return rc;
+    ctx->prof.collect();
+    return download_mates(ctx, n_frames, out, cap, n_mates);
+}
+
+int ebvo_edge_patches(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* plus49, float* minus49)
+{
+    if (!ctx || !img || !edges || n < 0) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, img, stride))) return rc;
+    if ((rc = upload_edges(ctx, 0, edges, n))) return rc;
+    if (n == 0) return EBVO_OK;
+    float *dp, *dm;
+    CK(cudaMalloc(&dp, (size_t)n * 49 * 4)); CK(cudaMalloc(&dm, (size_t)n * 49 * 4));
+    launch_edge_patches(ctx->d_raw, w, h, ctx->b.pitch, ctx->b.ex, ctx->b.ey, ctx->b.eth, n, ctx->dp.shift_mag, dp, dm, ctx->st);
+    CK(cudaMemcpyAsync(plus49, dp, (size_t)n * 49 * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(minus49, dm, (size_t)n * 49 * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(dp); cudaFree(dm);
+    return EBVO_OK;
+}
+
+int ebvo_ncc_patch_pair(ebvo_ctx* ctx, const float* p1, const float* p2, int n_pairs, double* out)
+{
+    if (!ctx || !p1 || !p2 || !out || n_pairs < 0) return EBVO_ERR_INVALID;
+    if (n_pairs == 0) return EBVO_OK;
+    CK(cudaSetDevice(ctx->device));
+    float *d1, *d2; double* dout;
+    const size_t nb = (size_t)n_pairs * 49 * 4;
+    CK(cudaMalloc(&d1, nb)); CK(cudaMalloc(&d2, nb)); CK(cudaMalloc(&dout, (size_t)n_pairs * 8));
+    CK(cudaMemcpyAsync(d1, p1, nb, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d2, p2, nb, cudaMemcpyHostToDevice, ctx->st));
+    launch_ncc_pairs(d1, d2, n_pairs, dout, ctx->st);
+    CK(cudaMemcpyAsync(out, dout, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(d1); cudaFree(d2); cudaFree(dout);
+    return EBVO_OK;
+}
+
+int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientation, ebvo_edge* centers, int* labels, int* n_clusters)
+{
+    if (!ctx || !edges || n < 0 || !centers || !labels || !n_clusters) return EBVO_ERR_INVALID;
+    if (n > 128) { ctx->err = "ebvo_cluster handles at most 128 edges per set"; return EBVO_ERR_CAPACITY; }
+    *n_clusters = 0;
+    if (n == 0) return EBVO_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> h(6 * (size_t)n);
+    for (int k = 0; k < n; ++k) { h[k] = edges[k].x; h[n + k] = edges[k].y; h[2 * n + k] = edges[k].theta; }
+    double* d; int* dl;
+    CK(cudaMalloc(&d, 6 * (size_t)n * 8)); CK(cudaMalloc(&dl, ((size_t)n + 1) * 4));
+    CK(cudaMemcpyAsync(d, h.data(), 3 * (size_t)n * 8, cudaMemcpyHostToDevice, ctx->st));
+    launch_cluster_one(d, d + n, d + 2 * n, n, by_orientation, ctx->dp, d + 3 * n, d + 4 * n, d + 5 * n, dl, dl + n, ctx->st);
+    std::vector<int> hl(n + 1);
+    CK(cudaMemcpyAsync(h.data(), d, 6 * (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(hl.data(), dl, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(d); cudaFree(dl);
+    const int nc = hl[n];
+    for (int k = 0; k < nc; ++k) { centers[k].x = h[3 * n + k]; centers[k].y = h[4 * n + k]; centers[k].theta = h[5 * n + k]; centers[k].index = k; centers[k].frame_source = 0; }
+    for (int k = 0; k < n; ++k) labels[k] = hl[k];
+    *n_clusters = nc;
+    return EBVO_OK;
+}
+
+int ebvo_sobel(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* gx, float* gy)
+{
+    if (!ctx || !img || !gx || !gy) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    if ((rc = upload_image(ctx, ctx->d_raw, 1, img, stride))) return rc;   // slot 1 = right view of frame 0
+    launch_sobel(ctx->b, 1, ctx->st, nullptr);
+    CK(cudaMemcpyAsync(gx, ctx->b.gx, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(gy, ctx->b.gy, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return EBVO_OK;
+}
+
+int ebvo_set_stage_dumps(ebvo_ctx* ctx, int enable)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    ctx->dumpsEnabled = enable != 0;
+    return EBVO_OK;
+}
+int ebvo_stage_size(ebvo_ctx* ctx, int stage, int* n_left, int* total)
+{
+    if (!ctx || stage < 0 || stage >= EBVO_STAGE_COUNT || !ctx->stages[stage].valid) return EBVO_ERR_INVALID;
+    if (n_left) *n_left = ctx->stageNL;
+    if (total) *total = ctx->stages[stage].off.back();
+    return EBVO_OK;
+}
+int ebvo_stage_fetch(ebvo_ctx* ctx, int stage, int* offsets, int* ridx, double* x, double* y, double* theta, double* score)
+{
+    if (!ctx || stage < 0 || stage >= EBVO_STAGE_COUNT || !ctx->stages[stage].valid) return EBVO_ERR_INVALID;
+    const StageData& S = ctx->stages[stage];
+    const size_t n = S.ridx.size();
+    if (offsets) memcpy(offsets, S.off.data(), S.off.size() * 4);
+    if (ridx && n) memcpy(ridx, S.ridx.data(), n * 4);
+    if (x && n) memcpy(x, S.x.data(), n * 8);
+    if (y && n) memcpy(y, S.y.data(), n * 8);
+    if (theta && n) memcpy(theta, S.th.data(), n * 8);
+    if (score && n) memcpy(score, S.score.data(), n * 8);
+    return EBVO_OK;
+}
+
+int ebvo_set_profiling(ebvo_ctx* ctx, int enable)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    ctx->prof.enabled = enable != 0;
+    ctx->prof.reset();
+    return EBVO_OK;
+}
+int ebvo_get_kernel_times(ebvo_ctx* ctx, const char*** names, const float** ms, const int** launches, int* n)
+{
+    if (!ctx || !n) return EBVO_ERR_INVALID;
+    ctx->prof.cnames.clear();
+    for (auto& s : ctx->prof.names) ctx->prof.cnames.push_back(s.c_str());
+    if (names) *names = ctx->prof.cnames.data();
+    if (ms) *ms = ctx->prof.ms.data();
+    if (launches) *launches = ctx->prof.launches.data();
+    *n = (int)ctx->prof.names.size();
+    return EBVO_OK;
+}
+void* ebvo_stream(ebvo_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+
+}  // extern "C"

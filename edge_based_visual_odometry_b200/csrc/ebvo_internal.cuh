@@ -1,0 +1,122 @@
+// Internal declarations shared by the translation units of libebvo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/ebvo_b200.h"
+
+namespace ebvo {
+
+// ---- TOED tiling (K_A) ---------------------------------------------------------------------------------
+constexpr int TW = 32;             // input pixels per tile, x
+constexpr int TH = 32;             // input pixels per tile, y
+constexpr int HALO = 10;           // 9 taps + 1 pixel for the NMS ring
+constexpr int IN_W = TW + 2 * HALO;  // 52
+constexpr int IN_H = TH + 2 * HALO;  // 52
+constexpr int OW = TW + 2;         // conv output columns kept per tile (x0-1 .. x0+TW)
+constexpr int OH = TH + 2;
+constexpr int IW = 2 * OW;         // interp samples per tile incl. ring: 68
+constexpr int IH = 2 * OH;
+constexpr int TOED_THREADS = 256;
+
+// Debug stage dumps (frame 0 only): in-kernel snapshots of lists that do not survive the fused kernels.
+// Every buffer is addressed with the left edge's pool segment offset (cstart[i]); n[i] = entries of edge i.
+struct DumpBuf { int* n; int* ridx; double *x, *y, *th, *score; };
+enum { DUMP_S6 = 0, DUMP_S7, DUMP_S8, DUMP_S10, DUMP_S11, DUMP_COUNT };
+
+// Device view of one batch: base pointers + per-image / per-frame strides (elements of the pointed type).
+// Image index = 2*frame + view (view 0 = left, 1 = right).
+struct DevBatch {
+    int W, H, pitch;       // image size; pitch in bytes of the device copies
+    int W2, H2;            // interp grid
+    int tilesX, tilesY;
+    int maskPitch;         // uint32 words per interp row (= 2*tilesX)
+    int maskRows;          // rows in the mask (= 64*tilesY)
+    int E;                 // edge capacity per image
+    int P;                 // candidate pool capacity per frame
+    int NB;                // edge blocks per image (= E/32)
+    int nImages, nFrames;
+    const uint8_t* raw; const uint8_t* und; size_t imgStride;
+    uint32_t* mask; size_t maskStride;
+    float2* sp; size_t spStride;          // sub-pixel offsets (s*nx, s*ny) at edge samples
+    int* rowcnt; int* rowoff; size_t rowStride;
+    uint32_t* coords;                     // [img][E] packed (i<<16 | j)
+    double *ex, *ey, *eth;                // [img][E]
+    int *nE, *nTot;                       // [img]
+    float *gx, *gy; size_t gStride;       // Sobel planes of the undistorted RIGHT images, [frame][H*W]
+    float4* blk; float* pmax; float* smin;  // right-edge block bounds [frame][NB]
+    double* lines;                        // [frame][E][3]
+    int *cstart, *ccount;                 // [frame][E]
+    int* poolUsed;                        // [frame]
+    int* c_ridx; double *c_x, *c_y, *c_th, *c_score, *c_conf;  // [frame][P]
+    ebvo_mate* mates; int* nMates;        // [frame][E], [frame]
+    int* mateFlag;                        // [frame][E]
+    int* errFlag;                         // single int: capacity overflows
+    unsigned long long* counters;         // [frame][8] work counters (s3 pairs, ncc pairs, gn pairs, gn iters, ncc2 pairs ...)
+    const float* descL; const float* descR; // optional SIFT descriptors (frame 0 only), may be null
+    double* dF;                           // device copy of F21 (9 doubles, row-major)
+    int dumps;                            // != 0: fill dump[] for frame 0
+    DumpBuf dump[DUMP_COUNT];
+};
+
+struct DevParams {
+    double epi, maxdisp, orient_deg, shift_mag, ncc_thresh, bnb_ncc, bnb_sift, sift_thresh;
+    double loc_pert, tang_displ, orient_pert, clus_dist, clus_orient_rad, clus_sigma;
+    int clus_max, gn_max_iter;
+    double gn_tol, gn_huber;
+    float toed_mag_thresh; int toed_border;
+};
+
+// kernel launchers (defined in toed.cu / match.cu); all asynchronous on `st`
+void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_t st, struct Prof* prof);
+void launch_match(const DevBatch& b, const DevParams& p, const double* F21 /*host 9*/, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
+void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* prof);
+void upload_toed_tables();
+
+// stage-dump support (debug): gate lists for stages 0..2 on frame 0
+void launch_gate_count(const DevBatch& b, const DevParams& p, const double* F21, int mode, int* d_counts, cudaStream_t st);
+void launch_gate_fill(const DevBatch& b, const DevParams& p, const double* F21, int mode, const int* d_offsets, int* d_ridx, cudaStream_t st);
+// snapshot of the current candidate CSR of frame 0 into compact arrays (offsets computed on host)
+// src < 0: live pool (counts = ccount); else dump[src]
+void launch_snapshot(const DevBatch& b, int src, const int* d_offsets, int* ridx, double* x, double* y, double* th, double* score, cudaStream_t st);
+void launch_compact(const DevBatch& b, int nFrames, ebvo_mate* d_out, int stride, cudaStream_t st, struct Prof* prof);
+// individual matching stages (used by the stage-dump path, which snapshots between them)
+void match_prologue(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, struct Prof* prof);
+void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
+void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
+void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
+void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
+void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
+
+// small helpers
+void launch_edge_patches(const uint8_t* d_img, int w, int h, int pitch, const double* ex, const double* ey, const double* eth,
+                         int n, double shift, float* plus, float* minus, cudaStream_t st);
+void launch_ncc_pairs(const float* p1, const float* p2, int n, double* out, cudaStream_t st);
+void launch_cluster_one(const double* x, const double* y, const double* th, int n, int by_orient, const DevParams& p,
+                        double* cx, double* cy, double* cth, int* labels, int* nclusters, cudaStream_t st);
+
+// per-kernel event profiling
+struct Prof {
+    bool enabled = false;
+    std::vector<std::string> names;
+    std::vector<const char*> cnames;
+    std::vector<float> ms;
+    std::vector<int> launches;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<int> pendingIdx;
+    int index_of(const char* name);
+    void begin(const char* name, cudaStream_t st);
+    void end(cudaStream_t st);
+    void collect();
+    void reset();
+};
+
+#define EBVO_KERNEL(prof, name, st, ...)            \
+    do {                                            \
+        if ((prof) && (prof)->enabled) (prof)->begin(name, st); \
+        __VA_ARGS__;                                \
+        if ((prof) && (prof)->enabled) (prof)->end(st);         \
+    } while (0)
+
+}  // namespace ebvo

@@ -1,0 +1,1031 @@
+// Stereo edge correspondence on sm_100a: one warp per left edge (candidate set) or per candidate.
+//
+// Replaces Stereo_Matches::get_Stereo_Edge_Pairs + finalize_stereo_edge_mates, no-GT branch
+// (reference src/Stereo_Matches.cpp:1360-1653) with the helpers it calls in src/utility.cpp,
+// include/utility.h and src/EdgeClusterer.cpp.  Stage -> kernel map:
+//   sobel_kernel           util_compute_Img_Gradients            include/utility.h:131-141
+//   bounds_kernel(+scan)   index over the right edges (replaces the brute-force scan of :91-109)
+//   gate_kernel            S1 epipolar distance, S2 disparity, S3 orientation   :381-419, 534-553, 863-915
+//   sift_gate_kernel       S4 with injected descriptors           :691-787
+//   ncc_bnb_kernel         S5/S6 patches + NCC gate, S7 (and S7') :555-616, 789-862 ; utility.cpp:82-212
+//   gn_kernel              S8 epipolar shift, S9 Gauss-Newton     :26-89, 967-1037, 1159-1358
+//   cluster_kernel         S10 second shift + EdgeClusterer, S11 NCC, S12 arg-max   :1483, EdgeClusterer.cpp:119-302, :916-965
+//   compact_kernel         S13 remove_empty_clusters + finalize   :1543-1653
+// Candidate lists live in a per-frame pool (CSR with explicit start/count per left edge); every list keeps
+// the reference's order (ascending right-edge index, then the re-orderings the reference applies).
+#include "ebvo_internal.cuh"
+#include <math_constants.h>
+
+namespace ebvo {
+
+constexpr int MAXC = 128;     // max candidates per left edge held in shared memory by the warp kernels
+constexpr int WPB = 4;        // warps per block in the warp-per-item kernels
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ void warp_sum2(double& a, double& b)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+}
+__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); c += __shfl_xor_sync(FULL, c, o); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sobel 3x3 * 1/8 with BORDER_REFLECT_101 on the undistorted right image (exact in FP32 on 8-bit data)
+// ------------------------------------------------------------------------------------------------------
+__global__ void sobel_kernel(DevBatch b)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= b.W || y >= b.H) return;
+    const uint8_t* I = b.und + (size_t)(2 * f + 1) * b.imgStride;
+    auto R = [](int i, int n) { return n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i)); };
+    int xm = R(x - 1, b.W), xp = R(x + 1, b.W), ym = R(y - 1, b.H), yp = R(y + 1, b.H);
+    auto at = [&](int yy, int xx) { return (float)I[(size_t)yy * b.pitch + xx]; };
+    float gx = (at(ym, xp) - at(ym, xm)) * 0.125f + (at(y, xp) - at(y, xm)) * 0.25f + (at(yp, xp) - at(yp, xm)) * 0.125f;
+    float gy = (at(yp, xm) - at(ym, xm)) * 0.125f + (at(yp, x) - at(ym, x)) * 0.25f + (at(yp, xp) - at(ym, xp)) * 0.125f;
+    b.gx[(size_t)f * b.gStride + (size_t)y * b.W + x] = gx;
+    b.gy[(size_t)f * b.gStride + (size_t)y * b.W + x] = gy;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Bounding intervals of 32-edge blocks of the right edge list + monotone envelopes for binary search.
+// The TOED list is in row-major interp order, so blocks are thin horizontal bands; any order is still correct.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bounds_kernel(DevBatch b)
+{
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = 2 * f + 1;
+    const int nR = b.nE[img];
+    const int nblk = (nR + 31) >> 5;
+    const double* ex = b.ex + (size_t)img * b.E;
+    const double* ey = b.ey + (size_t)img * b.E;
+    float4* blk = b.blk + (size_t)f * b.NB;
+    float* pmax = b.pmax + (size_t)f * b.NB;
+    float* smin = b.smin + (size_t)f * b.NB;
+    for (int k = warp; k < nblk; k += 32) {
+        int e = k * 32 + lane;
+        float ylo = CUDART_INF_F, yhi = -CUDART_INF_F, xlo = CUDART_INF_F, xhi = -CUDART_INF_F;
+        if (e < nR) {
+            double x = ex[e], y = ey[e];
+            ylo = __double2float_rd(y); yhi = __double2float_ru(y);
+            xlo = __double2float_rd(x); xhi = __double2float_ru(x);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            ylo = fminf(ylo, __shfl_xor_sync(FULL, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(FULL, yhi, o));
+            xlo = fminf(xlo, __shfl_xor_sync(FULL, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(FULL, xhi, o));
+        }
+        if (lane == 0) blk[k] = make_float4(ylo, yhi, xlo, xhi);
+    }
+    __syncthreads();
+    // prefix max of yhi, suffix min of ylo (serial per chunk + block scan; nblk <= NB)
+    __shared__ float s_a[1024], s_b[1024];
+    const int per = (nblk + 1023) / 1024;
+    float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+    for (int k = 0; k < per; ++k) {
+        int i = tid * per + k;
+        if (i < nblk) mx = fmaxf(mx, blk[i].y);
+        int j = nblk - 1 - (tid * per + k);
+        if (j >= 0) mn = fminf(mn, blk[j].x);
+    }
+    s_a[tid] = mx; s_b[tid] = mn;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        float a = (tid >= d) ? s_a[tid - d] : -CUDART_INF_F, c = (tid >= d) ? s_b[tid - d] : CUDART_INF_F;
+        __syncthreads();
+        s_a[tid] = fmaxf(s_a[tid], a); s_b[tid] = fminf(s_b[tid], c);
+        __syncthreads();
+    }
+    float runmx = tid ? s_a[tid - 1] : -CUDART_INF_F, runmn = tid ? s_b[tid - 1] : CUDART_INF_F;
+    for (int k = 0; k < per; ++k) {
+        int i = tid * per + k;
+        if (i < nblk) { runmx = fmaxf(runmx, blk[i].y); pmax[i] = runmx; }
+        int j = nblk - 1 - (tid * per + k);
+        if (j >= 0) { runmn = fminf(runmn, blk[j].x); smin[j] = runmn; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Gates.  mode 0: S1 only; 1: S1+S2; 2: S1+S2+S3 (production).  One warp per left edge.
+// ------------------------------------------------------------------------------------------------------
+struct GateCtx {
+    double a, b, c, nrm, xL, yL, thL;
+    double ylo, yhi, xlo, xhi;
+    int blo, bhi;
+};
+
+__device__ __forceinline__ bool gate_test(const GateCtx& g, const DevParams& p, int mode, double xr, double yr, double thr)
+{
+    double d = fabs(g.a * xr + g.b * yr + g.c) / g.nrm;   // Stereo_Matches.cpp:99
+    if (!(d < p.epi)) return false;
+    if (mode >= 1) {
+        double dx = g.xL - xr, dy = g.yL - yr;
+        if (!(sqrt(dx * dx + dy * dy) <= p.maxdisp)) return false;   // :545-546
+    }
+    if (mode >= 2) {
+        double od = fabs((g.thL - thr) * (180.0 / 3.14159265358979323846));   // :887-901
+        if (od > 180.0) od = 360.0 - od;
+        if (!(od < p.orient_deg || fabs(od - 180.0) < p.orient_deg)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const DevParams& p, const double* F, int f, int i, int mode)
+{
+    const int imgL = 2 * f;
+    g.xL = b.ex[(size_t)imgL * b.E + i]; g.yL = b.ey[(size_t)imgL * b.E + i]; g.thL = b.eth[(size_t)imgL * b.E + i];
+    g.a = F[0] * g.xL + F[1] * g.yL + F[2] * 1.0;   // Stereo_Matches.cpp:15-16
+    g.b = F[3] * g.xL + F[4] * g.yL + F[5] * 1.0;
+    g.c = F[6] * g.xL + F[7] * g.yL + F[8] * 1.0;
+    g.nrm = sqrt((g.a * g.a) + (g.b * g.b));
+    // conservative search window
+    if (mode >= 1) { g.xlo = g.xL - p.maxdisp - 1e-6; g.xhi = g.xL + p.maxdisp + 1e-6; g.ylo = g.yL - p.maxdisp - 1e-6; g.yhi = g.yL + p.maxdisp + 1e-6; }
+    else { g.xlo = -1.0; g.xhi = (double)b.W + 1.0; g.ylo = -1.0; g.yhi = (double)b.H + 1.0; }
+    if (fabs(g.b) > 1e-9 * g.nrm) {
+        double y1 = -(g.a * g.xlo + g.c) / g.b, y2 = -(g.a * g.xhi + g.c) / g.b;
+        double m = p.epi * g.nrm / fabs(g.b) + 1e-6;
+        g.ylo = fmax(g.ylo, fmin(y1, y2) - m);
+        g.yhi = fmin(g.yhi, fmax(y1, y2) + m);
+    }
+    const int nR = b.nE[2 * f + 1];
+    const int nblk = (nR + 31) >> 5;
+    const float* pmax = b.pmax + (size_t)f * b.NB;
+    const float* smin = b.smin + (size_t)f * b.NB;
+    const float ylo = (float)g.ylo - 1e-3f, yhi = (float)g.yhi + 1e-3f;
+    int lo = 0, hi = nblk;  // first block with pmax >= ylo
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (pmax[mid] >= ylo) hi = mid; else lo = mid + 1; }
+    g.blo = lo;
+    lo = 0; hi = nblk;      // first block with smin > yhi
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (smin[mid] > yhi) hi = mid; else lo = mid + 1; }
+    g.bhi = lo;             // exclusive
+}
+
+// scan: calls emit(rank, ridx) in ascending ridx order for passing right edges; returns the count
+template <typename Emit>
+__device__ __forceinline__ int gate_scan(const GateCtx& g, const DevBatch& b, const DevParams& p, int f, int mode, int lane, Emit emit)
+{
+    const int imgR = 2 * f + 1;
+    const int nR = b.nE[imgR];
+    const double* ex = b.ex + (size_t)imgR * b.E;
+    const double* ey = b.ey + (size_t)imgR * b.E;
+    const double* eth = b.eth + (size_t)imgR * b.E;
+    const float4* blk = b.blk + (size_t)f * b.NB;
+    const float ylo = (float)g.ylo - 1e-3f, yhi = (float)g.yhi + 1e-3f, xlo = (float)g.xlo - 1e-3f, xhi = (float)g.xhi + 1e-3f;
+    int count = 0;
+    for (int k = g.blo; k < g.bhi; ++k) {
+        float4 bb = blk[k];
+        if (bb.y < ylo || bb.x > yhi || bb.w < xlo || bb.z > xhi) continue;
+        int e = k * 32 + lane;
+        bool ok = false;
+        if (e < nR) ok = gate_test(g, p, mode, ex[e], ey[e], eth[e]);
+        unsigned m = __ballot_sync(FULL, ok);
+        if (ok) emit(count + __popc(m & ((1u << lane) - 1)), e);
+        count += __popc(m);
+    }
+    return count;
+}
+
+__global__ void __launch_bounds__(32 * WPB) gate_kernel(DevBatch b, DevParams p, const double* __restrict__ F)
+{
+    __shared__ int s_buf[WPB][64];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[2 * f];
+    int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    unsigned long long pairs = 0;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        GateCtx g;
+        gate_setup(g, b, p, F, f, i, 2);
+        if (lane == 0) {
+            double* l = b.lines + ((size_t)f * b.E + i) * 3;
+            l[0] = g.a; l[1] = g.b; l[2] = g.c;
+        }
+        int* buf = s_buf[w];
+        int n = gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { if (rank < 64) buf[rank] = e; });
+        int start = 0;
+        if (lane == 0 && n > 0) start = atomicAdd(&b.poolUsed[f], n);
+        start = __shfl_sync(FULL, start, 0);
+        if (n > 0 && start + n > b.P) {  // pool exhausted
+            if (lane == 0) atomicExch(b.errFlag, 2);
+            n = 0;
+        }
+        __syncwarp();
+        if (n > 0) {
+            if (n <= 64) { for (int k = lane; k < n; k += 32) c_ridx[start + k] = buf[k]; }
+            else gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { c_ridx[start + rank] = e; });
+        }
+        if (lane == 0) { cstart[i] = start; ccount[i] = n; }
+        pairs += n;
+        __syncwarp();
+    }
+    if (lane == 0 && pairs) atomicAdd(&b.counters[(size_t)f * 8 + 0], pairs);
+}
+
+// debug variants for the stage dumps (frame 0): count, then fill at host-scanned offsets
+__global__ void __launch_bounds__(32 * WPB) gate_count_kernel(DevBatch b, DevParams p, const double* __restrict__ F, int mode, int* counts)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[0];
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        GateCtx g;
+        gate_setup(g, b, p, F, 0, i, mode);
+        int n = gate_scan(g, b, p, 0, mode, lane, [&](int, int) {});
+        if (lane == 0) counts[i] = n;
+    }
+}
+__global__ void __launch_bounds__(32 * WPB) gate_fill_kernel(DevBatch b, DevParams p, const double* __restrict__ F, int mode, const int* offsets, int* ridx)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[0];
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        GateCtx g;
+        gate_setup(g, b, p, F, 0, i, mode);
+        int o = offsets[i];
+        gate_scan(g, b, p, 0, mode, lane, [&](int rank, int e) { ridx[o + rank] = e; });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Oriented 7x7 patches + NCC.  Lane l owns patch cells t = l and t = l + 32 (< 49) of BOTH the "+" and "-"
+// patch, so the four cross dot products are lane-local before the shuffle reduction.
+// ------------------------------------------------------------------------------------------------------
+// include/utility.h:81-104 on an 8-bit image (convertTo CV_64F is exact): NaN outside or on integer coordinates
+__device__ __forceinline__ double bilinear_u8(const uint8_t* __restrict__ I, int pitch, int W, int H, double px, double py)
+{
+    if (!(px == px) || !(py == py)) return CUDART_NAN;
+    double fx = floor(px), cx = ceil(px), fy = floor(py), cy = ceil(py);
+    if (fx < 0.0 || fy < 0.0 || cx >= (double)W || cy >= (double)H) return CUDART_NAN;
+    if (cx == fx || cy == fy) return CUDART_NAN;   // 0/0 weights in the reference formula
+    int ifx = (int)fx, icx = (int)cx, ify = (int)fy, icy = (int)cy;
+    double v11 = (double)I[(size_t)icy * pitch + ifx], v21 = (double)I[(size_t)icy * pitch + icx];
+    double v12 = (double)I[(size_t)ify * pitch + ifx], v22 = (double)I[(size_t)ify * pitch + icx];
+    double wx1 = cx - px, wx2 = px - fx;          // denominators are exactly 1
+    double f1 = wx1 * v11 + wx2 * v21, f2 = wx1 * v12 + wx2 * v22;
+    return (py - fy) * f1 + (cy - py) * f2;       // (fy-py)/(fy-cy) with fy-cy = -1
+}
+
+struct Patches {      // normalised (zero-mean, unit-norm) cells owned by this lane
+    float p[2], m[2];
+    bool flatP, flatM; // sum of squares < 1e-10  => similarity -1 (utility.cpp:170-172)
+};
+
+__device__ __forceinline__ void raw_patches(const uint8_t* I, int pitch, int W, int H, double x, double y, double th, double shift,
+                                            int lane, float (&vp)[2], float (&vm)[2])
+{
+    double s, c;
+    sincos(th, &s, &c);
+    // utility.cpp:84-87
+    double pxp = x + shift * s, pyp = y + shift * (-c), pxm = x + shift * (-s), pym = y + shift * c;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        int t = lane + 32 * u;
+        vp[u] = 0.f; vm[u] = 0.f;
+        if (t < 49) {
+            int i = t / 7 - 3, j = t % 7 - 3;
+            double ox = c * (double)i - s * (double)j, oy = s * (double)i + c * (double)j;   // utility.cpp:151
+            vp[u] = (float)bilinear_u8(I, pitch, W, H, ox + pxp, oy + pyp);
+            vm[u] = (float)bilinear_u8(I, pitch, W, H, ox + pxm, oy + pym);
+        }
+    }
+}
+
+// utility.cpp:165-178 with OpenCV's CV_32F type mix (double mean/sums, float centred & normalised values)
+__device__ __forceinline__ void normalise_patches(const float (&vp)[2], const float (&vm)[2], int lane, Patches& P)
+{
+    const bool has1 = (lane + 32) < 49;
+    double sp = (double)vp[0] + (has1 ? (double)vp[1] : 0.0), sm = (double)vm[0] + (has1 ? (double)vm[1] : 0.0);
+    warp_sum2(sp, sm);
+    float mp = (float)(sp / 49.0), mm = (float)(sm / 49.0);
+    float dp0 = vp[0] - mp, dp1 = has1 ? vp[1] - mp : 0.f, dm0 = vm[0] - mm, dm1 = has1 ? vm[1] - mm : 0.f;
+    double ssp = (double)(dp0 * dp0) + (double)(dp1 * dp1), ssm = (double)(dm0 * dm0) + (double)(dm1 * dm1);
+    warp_sum2(ssp, ssm);
+    P.flatP = ssp < 1e-10; P.flatM = ssm < 1e-10;
+    float ip = (float)(1.0 / sqrt(ssp)), im = (float)(1.0 / sqrt(ssm));
+    P.p[0] = dp0 * ip; P.p[1] = dp1 * ip; P.m[0] = dm0 * im; P.m[1] = dm1 * im;
+}
+
+// max of the four similarities with std::max({..}) NaN semantics (Stereo_Matches.cpp:592-596)
+__device__ __forceinline__ double ncc_score(const Patches& A, const Patches& B)
+{
+    double pp = (double)A.p[0] * (double)B.p[0] + (double)A.p[1] * (double)B.p[1];
+    double nn = (double)A.m[0] * (double)B.m[0] + (double)A.m[1] * (double)B.m[1];
+    double pn = (double)A.p[0] * (double)B.m[0] + (double)A.p[1] * (double)B.m[1];
+    double np = (double)A.m[0] * (double)B.p[0] + (double)A.m[1] * (double)B.p[1];
+    warp_sum2(pp, nn);
+    warp_sum2(pn, np);
+    if (A.flatP || B.flatP) pp = -1.0;
+    if (A.flatM || B.flatM) nn = -1.0;
+    if (A.flatP || B.flatM) pn = -1.0;
+    if (A.flatM || B.flatP) np = -1.0;
+    double m = pp;
+    if (m < nn) m = nn;
+    if (m < pn) m = pn;
+    if (m < np) m = np;
+    return m;
+}
+
+// Best-nearly-best on a warp-private score list (Stereo_Matches.cpp:789-862).  On return order[k] (k < keep)
+// lists the surviving positions in the order the reference leaves them; returns keep.
+__device__ __forceinline__ int bnb_select(const double* sc, int n, double thr, bool is_ncc, int lane, int* order)
+{
+    if (n < 2) { if (lane == 0 && n == 1) order[0] = 0; __syncwarp(); return n; }
+    // best = max (NCC) or min (SIFT distance)
+    double best = is_ncc ? -CUDART_INF : CUDART_INF;
+    for (int k = lane; k < n; k += 32) best = is_ncc ? fmax(best, sc[k]) : fmin(best, sc[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(FULL, best, o); best = is_ncc ? fmax(best, t) : fmin(best, t); }
+    int keep;
+    if (best == 0.0) keep = 1;
+    else {
+        int c = 0;
+        for (int k = lane; k < n; k += 32) { double r = is_ncc ? sc[k] / best : best / sc[k]; c += (r >= thr) ? 1 : 0; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        keep = c < 1 ? 1 : c;
+    }
+    if (keep >= n) { for (int k = lane; k < n; k += 32) order[k] = k; __syncwarp(); return n; }
+    // stable rank in sorted order
+    for (int k = lane; k < n; k += 32) {
+        double s = sc[k];
+        int r = 0;
+        for (int q = 0; q < n; ++q) {
+            double t = sc[q];
+            bool before = is_ncc ? (t > s) : (t < s);
+            r += (before || (t == s && q < k)) ? 1 : 0;
+        }
+        if (r < keep) order[r] = k;
+    }
+    __syncwarp();
+    return keep;
+}
+
+__device__ __forceinline__ void dump_put(const DumpBuf& d, int o, int ridx, double x, double y, double th, double score)
+{
+    d.ridx[o] = ridx; d.x[o] = x; d.y[o] = y; d.th[o] = th; d.score[o] = score;
+}
+
+__global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams p, int use_sift)
+{
+    __shared__ double s_sc[WPB][MAXC];
+    __shared__ double s_cf[WPB][MAXC];
+    __shared__ double s_tmp[WPB][MAXC];
+    __shared__ int s_ri[WPB][MAXC];
+    __shared__ int s_or[WPB][MAXC];
+    __shared__ int s_or2[WPB][MAXC];
+    __shared__ int s_or3[WPB][MAXC];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int imgL = 2 * f, imgR = 2 * f + 1;
+    const int nL = b.nE[imgL];
+    const uint8_t* IL = b.raw + (size_t)imgL * b.imgStride;   // NCC uses the RAW images (Stereo_Matches.cpp:562-563)
+    const uint8_t* IR = b.raw + (size_t)imgR * b.imgStride;
+    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
+    const double *exR = b.ex + (size_t)imgR * b.E, *eyR = b.ey + (size_t)imgR * b.E, *ethR = b.eth + (size_t)imgR * b.E;
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+    const bool dumps = b.dumps && f == 0;
+    unsigned long long kept = 0;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        const int n = ccount[i];
+        if (n == 0) { if (dumps && lane == 0) { b.dump[DUMP_S6].n[i] = 0; b.dump[DUMP_S7].n[i] = 0; } continue; }
+        const int st = cstart[i];
+        float vp[2], vm[2];
+        Patches PL, PR;
+        raw_patches(IL, b.pitch, b.W, b.H, exL[i], eyL[i], ethL[i], p.shift_mag, lane, vp, vm);
+        normalise_patches(vp, vm, lane, PL);
+        int ns = 0;
+        for (int j = 0; j < n; ++j) {
+            const int r = c_ridx[st + j];
+            raw_patches(IR, b.pitch, b.W, b.H, exR[r], eyR[r], ethR[r], p.shift_mag, lane, vp, vm);
+            normalise_patches(vp, vm, lane, PR);
+            const double s = ncc_score(PL, PR);
+            if (s > p.ncc_thresh) {      // NCC_THRESH gate, :597
+                if (ns < MAXC) {
+                    if (lane == 0) { s_sc[w][ns] = s; s_ri[w][ns] = r; s_cf[w][ns] = use_sift ? c_conf[st + j] : 0.0; }
+                    ++ns;
+                } else if (lane == 0) atomicExch(b.errFlag, 3);
+            }
+        }
+        __syncwarp();
+        if (dumps) {
+            for (int k = lane; k < ns; k += 32) { int r = s_ri[w][k]; dump_put(b.dump[DUMP_S6], st + k, r, exR[r], eyR[r], ethR[r], s_sc[w][k]); }
+            if (lane == 0) b.dump[DUMP_S6].n[i] = ns;
+        }
+        // S7: best-nearly-best on NCC
+        int keep = bnb_select(s_sc[w], ns, p.bnb_ncc, true, lane, s_or[w]);
+        if (dumps) {
+            for (int k = lane; k < keep; k += 32) { int o = s_or[w][k], r = s_ri[w][o]; dump_put(b.dump[DUMP_S7], st + k, r, exR[r], eyR[r], ethR[r], s_sc[w][o]); }
+            if (lane == 0) b.dump[DUMP_S7].n[i] = keep;
+        }
+        if (use_sift && keep >= 2) {
+            // S7': order the survivors by SIFT distance; compose the two selections
+            for (int k = lane; k < keep; k += 32) s_tmp[w][k] = s_cf[w][s_or[w][k]];
+            __syncwarp();
+            const int keep2 = bnb_select(s_tmp[w], keep, p.bnb_sift, false, lane, s_or2[w]);
+            for (int k = lane; k < keep2; k += 32) s_or3[w][k] = s_or[w][s_or2[w][k]];
+            __syncwarp();
+            for (int k = lane; k < keep2; k += 32) s_or[w][k] = s_or3[w][k];
+            keep = keep2;
+            __syncwarp();
+        }
+        for (int k = lane; k < keep; k += 32) {
+            const int o = s_or[w][k], r = s_ri[w][o];
+            c_ridx[st + k] = r;
+            c_x[st + k] = exR[r]; c_y[st + k] = eyR[r]; c_th[st + k] = ethR[r];
+            c_score[st + k] = s_sc[w][o];
+            c_conf[st + k] = s_cf[w][o];
+        }
+        if (lane == 0) ccount[i] = keep;
+        kept += keep;
+        __syncwarp();
+    }
+    if (lane == 0 && kept) atomicAdd(&b.counters[(size_t)f * 8 + 1], kept);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// S4 (optional): SIFT gate with caller-supplied descriptors (frame 0 only).  One warp per left edge.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * WPB) sift_gate_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[2 * f];
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    double* c_conf = b.c_conf + (size_t)f * b.P;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        const int n = ccount[i];
+        if (n == 0) continue;
+        const int st = cstart[i];
+        const float* l1 = b.descL + (size_t)i * 256;
+        const float4 a1 = reinterpret_cast<const float4*>(l1)[lane], a2 = reinterpret_cast<const float4*>(l1 + 128)[lane];
+        int ns = 0;
+        for (int j = 0; j < n; ++j) {
+            const int r = c_ridx[st + j];
+            const float* r1 = b.descR + (size_t)r * 256;
+            const float4 b1 = reinterpret_cast<const float4*>(r1)[lane], b2 = reinterpret_cast<const float4*>(r1 + 128)[lane];
+            auto d2 = [](float4 u, float4 v) {
+                double x = (double)u.x - (double)v.x, y = (double)u.y - (double)v.y, z = (double)u.z - (double)v.z, q = (double)u.w - (double)v.w;
+                return x * x + y * y + z * z + q * q;
+            };
+            double d11 = d2(a1, b1), d21 = d2(a2, b1), d12 = d2(a1, b2), d22 = d2(a2, b2);
+            warp_sum2(d11, d21);
+            warp_sum2(d12, d22);
+            const double d = fmin(fmin(sqrt(d11), sqrt(d21)), fmin(sqrt(d12), sqrt(d22)));   // :736-740
+            __syncwarp();
+            if (d < p.sift_thresh) {
+                if (lane == 0) { c_ridx[st + ns] = r; c_conf[st + ns] = d; }
+                ++ns;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) ccount[i] = ns;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// S8 epipolar shift (Stereo_Matches.cpp:26-89; utility.cpp:46-74)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tangential(double a, double b, double c, double x, double y, double th, double& xi, double& yi)
+{
+    const double ae = tan(th), be = -1.0, ce = -(ae * x - y);
+    xi = (b * ce - be * c) / (a * be - ae * b);
+    yi = (c * ae - ce * a) / (a * be - ae * b);
+    return sqrt((xi - x) * (xi - x) + (yi - y) * (yi - y));
+}
+__device__ __forceinline__ void shift_to_line(double a, double b, double c, const DevParams& p, double& x, double& y, double& th)
+{
+    const double ex = x - a * (a * x + b * y + c) / (a * a + b * b);
+    const double ey = y - b * (a * x + b * y + c) / (a * a + b * b);
+    const double dn = sqrt((x - ex) * (x - ex) + (y - ey) * (y - ey));
+    if (dn < p.loc_pert) { x = ex; y = ey; return; }
+    double xi, yi;
+    if (tangential(a, b, c, x, y, th, xi, yi) < p.tang_displ) { x = xi; y = yi; return; }
+    double s, co;
+    sincos(th, &s, &co);
+    const double pt = a * co + b * s, dpt = -a * s + b * co;
+    double t2 = th;
+    if (pt > 0 && dpt < 0) t2 -= p.orient_pert;
+    else if (pt < 0 && dpt < 0) t2 -= p.orient_pert;
+    else if (pt > 0 && dpt > 0) t2 += p.orient_pert;
+    else if (pt < 0 && dpt > 0) t2 += p.orient_pert;
+    if (tangential(a, b, c, x, y, t2, xi, yi) < p.tang_displ) { x = xi; y = yi; th = t2; }
+}
+
+// include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped, float result
+__device__ __forceinline__ float sample_u8(const uint8_t* __restrict__ I, int pitch, int w, int h, double x, double y)
+{
+    x = fmin(fmax(x, 0.0), (double)w - 1.0);
+    y = fmin(fmax(y, 0.0), (double)h - 1.0);
+    const int x0 = (int)floor(x), y0 = (int)floor(y);
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const double a = x - x0, bb = y - y0;
+    const float v00 = (float)I[(size_t)y0 * pitch + x0], v10 = (float)I[(size_t)y0 * pitch + x1];
+    const float v01 = (float)I[(size_t)y1 * pitch + x0], v11 = (float)I[(size_t)y1 * pitch + x1];
+    return (float)((1 - a) * (1 - bb) * v00 + a * (1 - bb) * v10 + (1 - a) * bb * v01 + a * bb * v11);
+}
+// the same sampler applied to the image and to both Sobel planes at one coordinate
+__device__ __forceinline__ void sample3(const uint8_t* __restrict__ I, int pitch, const float* __restrict__ GX, const float* __restrict__ GY,
+                                        int w, int h, double x, double y, float& vi, float& vgx, float& vgy)
+{
+    x = fmin(fmax(x, 0.0), (double)w - 1.0);
+    y = fmin(fmax(y, 0.0), (double)h - 1.0);
+    const int x0 = (int)floor(x), y0 = (int)floor(y);
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const double a = x - x0, bb = y - y0;
+    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
+    const size_t o00 = (size_t)y0 * w + x0, o10 = (size_t)y0 * w + x1, o01 = (size_t)y1 * w + x0, o11 = (size_t)y1 * w + x1;
+    vi = (float)(w00 * (float)I[(size_t)y0 * pitch + x0] + w10 * (float)I[(size_t)y0 * pitch + x1] +
+                 w01 * (float)I[(size_t)y1 * pitch + x0] + w11 * (float)I[(size_t)y1 * pitch + x1]);
+    vgx = (float)(w00 * GX[o00] + w10 * GX[o10] + w01 * GX[o01] + w11 * GX[o11]);
+    vgy = (float)(w00 * GY[o00] + w10 * GY[o10] + w01 * GY[o01] + w11 * GY[o11]);
+}
+
+// S8 + S9.  One warp per left edge, looping over its candidates.  Lane l owns samples s = l + 32 m (m < 4,
+// s < 98): s < 49 -> "+" patch cell s, else "-" patch cell s - 49 (cell (i,j) = (t/7-3, t%7-3)).
+__global__ void __launch_bounds__(32 * WPB) gn_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int imgL = 2 * f, imgR = 2 * f + 1;
+    const int nL = b.nE[imgL];
+    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
+    const uint8_t* IR = b.und + (size_t)imgR * b.imgStride;
+    const float* GX = b.gx + (size_t)f * b.gStride;
+    const float* GY = b.gy + (size_t)f * b.gStride;
+    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    const int* ccount = b.ccount + (size_t)f * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    const bool dumps = b.dumps && f == 0;
+    unsigned long long npairs = 0, niters = 0;
+    (void)w;
+    for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < nL; i += gridDim.x * WPB) {
+        const int n = ccount[i];
+        if (dumps && lane == 0) b.dump[DUMP_S8].n[i] = n;
+        if (n == 0) continue;
+        const int st = cstart[i];
+        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
+        const double la = ln[0], lb = ln[1], lc = ln[2];
+        double dirx = -lb, diry = la;                         // :1330-1335
+        { const double nn = sqrt(dirx * dirx + diry * diry); dirx /= nn; diry /= nn; }
+        const double xL = exL[i], yL = eyL[i], thL = ethL[i];
+        double st_, ct_;
+        sincos(thL, &st_, &ct_);
+        const double nx = -st_, ny = ct_;                     // n = (-t.y, t.x), :1169-1170
+        const double side = 7 / 2.0 + 1.0;                    // :1171
+        double cox[4], coy[4], rox[4], roy[4], Lc[4];
+        bool val[4], neg[4];
+        double sumP = 0, sumM = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int s = lane + 32 * m;
+            val[m] = s < 98;
+            neg[m] = s >= 49;
+            const int t = s - (neg[m] ? 49 : 0);
+            const int ii = t / 7 - 3, jj = t % 7 - 3;
+            cox[m] = (neg[m] ? -1.0 : 1.0) * (nx * side);     // patch-centre offset +-n*side
+            coy[m] = (neg[m] ? -1.0 : 1.0) * (ny * side);
+            rox[m] = ct_ * ii - st_ * jj;                     // rotated cell offset (utility.h:154)
+            roy[m] = st_ * ii + ct_ * jj;
+            Lc[m] = 0.0;
+            if (val[m]) {
+                Lc[m] = (double)sample_u8(IL, b.pitch, b.W, b.H, (xL + cox[m]) + rox[m], (yL + coy[m]) + roy[m]);
+                if (neg[m]) sumM += Lc[m]; else sumP += Lc[m];
+            }
+        }
+        warp_sum2(sumP, sumM);
+        const double mLp = sumP / 49.0, mLm = sumM / 49.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (val[m]) Lc[m] -= neg[m] ? mLm : mLp;
+
+        for (int j = 0; j < n; ++j) {
+            double xr = c_x[st + j], yr = c_y[st + j], thr = c_th[st + j];
+            shift_to_line(la, lb, lc, p, xr, yr, thr);        // S8
+            if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], st + j, -1, xr, yr, thr, c_score[st + j]);
+            double alpha = 0.0, score = 0.0, conf = 0.0;
+            int logn = 0;
+            for (int it = 0; it < p.gn_max_iter; ++it) {
+                const double sx = alpha * dirx, sy = alpha * diry;
+                float vi[4], vgx[4], vgy[4];
+                double sRp = 0, sRm = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    vi[m] = vgx[m] = vgy[m] = 0.f;
+                    if (val[m]) {
+                        const double cx = (xr + cox[m]) + sx, cy = (yr + coy[m]) + sy;   // :1203-1204
+                        sample3(IR, b.pitch, GX, GY, b.W, b.H, cx + rox[m], cy + roy[m], vi[m], vgx[m], vgy[m]);
+                        if (neg[m]) sRm += (double)vi[m]; else sRp += (double)vi[m];
+                    }
+                }
+                warp_sum2(sRp, sRm);
+                const double mRp = sRp / 49.0, mRm = sRm / 49.0;
+                double Hh = 0, bb = 0, cost = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (val[m]) {
+                        const double r = Lc[m] - ((double)vi[m] - (neg[m] ? mRm : mRp));
+                        const double g = -(double)vgx[m] * dirx + (double)vgy[m] * diry;   // :1240
+                        const double ar = fabs(r);
+                        const double wgt = (ar <= p.gn_huber) ? 1.0 : p.gn_huber / ar;
+                        Hh += wgt * g * g; bb += wgt * g * r; cost += wgt * r * r;
+                    }
+                }
+                warp_sum3(Hh, bb, cost);
+                ++niters;
+                if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+                const double delta = -bb / Hh;
+                alpha += delta;
+                const double rms = sqrt(cost / 98.0);
+                ++logn;
+                if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+                    score = rms; conf = exp(-rms / p.gn_huber);
+                    break;
+                }
+            }
+            ++npairs;
+            if (lane == 0) {
+                c_x[st + j] = xr + alpha * dirx;               // :1350-1352 (moved regardless of validity)
+                c_y[st + j] = yr + alpha * diry;
+                c_th[st + j] = thr;
+                c_score[st + j] = score; c_conf[st + j] = conf;
+                c_ridx[st + j] = -1;                           // right-edge indices are dropped at S8 (:993-997)
+            }
+        }
+    }
+    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// S10 second shift + EdgeClusterer, S11 NCC on the cluster centres, S12 arg-max.  One warp per left edge.
+// ------------------------------------------------------------------------------------------------------
+// EdgeClusterer::performClustering (EdgeClusterer.cpp:119-302) on n <= MAXC warp-private candidates.
+// Returns the number of clusters; centres go to (ox, oy, oth)[0..ncl) in ascending-label order (the order of
+// returned_clusters); lab[] receives the renumbered label of every input.
+__device__ int warp_cluster(const double* sx, const double* sy, const double* sth, int n, bool by_orient, const DevParams& p,
+                            int lane, int* lab, double* ox, double* oy, double* oth)
+{
+    for (int k = lane; k < n; k += 32) lab[k] = k;
+    __syncwarp();
+    bool merged = true;
+    while (merged) {
+        merged = false;
+        for (int i = 0; i < n; ++i) {
+            const int li = lab[i];
+            const double xi = sx[i], yi = sy[i], ti = sth[i];
+            double best = CUDART_INF;
+            int bj = 0x7fffffff;
+            for (int j = lane; j < n; j += 32) {
+                if (lab[j] == li) continue;
+                const double dx = xi - sx[j], dy = yi - sy[j];
+                const double d = sqrt(dx * dx + dy * dy);
+                const bool ok = d < p.clus_dist && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad);
+                if (ok && d < best) { best = d; bj = j; }   // ascending j per lane; strict < keeps the first minimum
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int oj = __shfl_xor_sync(FULL, bj, o);
+                if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+            }
+            if (bj != 0x7fffffff) {
+                const int lold = lab[bj];
+                int cnt = 0;
+                for (int k = lane; k < n; k += 32) cnt += (lab[k] == lold || lab[k] == li) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+                if (cnt <= p.clus_max) {                    // MAX_CLUSTER_SIZE, EdgeClusterer.cpp:179
+                    __syncwarp();
+                    for (int k = lane; k < n; k += 32) if (lab[k] == lold) lab[k] = li;
+                    __syncwarp();
+                    merged = true;
+                    break;
+                }
+            }
+        }
+    }
+    // Clusters in ascending label order (std::map, :209-222).  A live label L always labels element L itself,
+    // so "label L exists" <=> lab[L] == L.  Processed members are re-tagged -1-c to carry the renumbered label.
+    int ncl = 0;
+    for (int L = 0; L < n; ++L) {
+        if (lab[L] != L) continue;
+        double sxx = 0, syy = 0, cntd = 0;
+        for (int k = lane; k < n; k += 32) if (lab[k] == L) { sxx += sx[k]; syy += sy[k]; cntd += 1.0; }
+        warp_sum3(sxx, syy, cntd);
+        const double cx = sxx / cntd, cy = syy / cntd;
+        double tot = 0;
+        for (int k = lane; k < n; k += 32) if (lab[k] == L) { const double dx = sx[k] - cx, dy = sy[k] - cy; tot += sqrt(dx * dx + dy * dy); }
+        tot = warp_sum(tot);
+        const double md = tot / cntd;
+        double wx = 0, wy = 0, wt = 0, ww = 0;
+        for (int k = lane; k < n; k += 32) if (lab[k] == L) {
+            const double dx = sx[k] - cx, dy = sy[k] - cy, d = sqrt(dx * dx + dy * dy);
+            const double z = (d - md) / p.clus_sigma;
+            const double g = exp(-0.5 * (z * z));
+            wx += g * sx[k]; wy += g * sy[k]; wt += g * sth[k]; ww += g;
+        }
+        warp_sum2(wx, wy);
+        warp_sum2(wt, ww);
+        if (lane == 0) { ox[ncl] = wx / ww; oy[ncl] = wy / ww; oth[ncl] = wt / ww; }
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) if (lab[k] == L) lab[k] = -1 - ncl;
+        __syncwarp();
+        ++ncl;
+    }
+    for (int k = lane; k < n; k += 32) lab[k] = -1 - lab[k];
+    __syncwarp();
+    return ncl;
+}
+
+__global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams p)
+{
+    __shared__ double s_x[WPB][MAXC], s_y[WPB][MAXC], s_t[WPB][MAXC];
+    __shared__ double s_ox[WPB][MAXC], s_oy[WPB][MAXC], s_ot[WPB][MAXC];
+    __shared__ int s_lab[WPB][MAXC];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int imgL = 2 * f, imgR = 2 * f + 1;
+    const int nL = b.nE[imgL];
+    const uint8_t* IL = b.raw + (size_t)imgL * b.imgStride;
+    const uint8_t* IR = b.raw + (size_t)imgR * b.imgStride;
+    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    double* c_score = b.c_score + (size_t)f * b.P;
+    int* mateFlag = b.mateFlag + (size_t)f * b.E;
+    ebvo_mate* mates = b.mates + (size_t)f * b.E;   // staging: slot i
+    const bool dumps = b.dumps && f == 0;
+    unsigned long long n2 = 0;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        int n = ccount[i];
+        if (n == 0) {
+            if (lane == 0) { mateFlag[i] = 0; if (dumps) { b.dump[DUMP_S10].n[i] = 0; b.dump[DUMP_S11].n[i] = 0; } }
+            continue;
+        }
+        const int st = cstart[i];
+        if (n > MAXC) { if (lane == 0) atomicExch(b.errFlag, 4); n = MAXC; }
+        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
+        const double la = ln[0], lb = ln[1], lc = ln[2];
+        for (int k = lane; k < n; k += 32) {
+            double x = c_x[st + k], y = c_y[st + k], t = c_th[st + k];
+            shift_to_line(la, lb, lc, p, x, y, t);       // second shift (Stereo_Matches.cpp:1483 -> :981-998)
+            s_x[w][k] = x; s_y[w][k] = y; s_t[w][k] = t;
+        }
+        __syncwarp();
+        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_ox[w], s_oy[w], s_ot[w]);
+        __syncwarp();
+        if (dumps) {
+            for (int k = lane; k < ncl; k += 32) dump_put(b.dump[DUMP_S10], st + k, -1, s_ox[w][k], s_oy[w][k], s_ot[w][k], CUDART_NAN);
+            if (lane == 0) b.dump[DUMP_S10].n[i] = ncl;
+        }
+        // S11 NCC on the centres (raw images, :1500) + S12 arg-max, first maximum wins (:941-951)
+        float vp[2], vm[2];
+        Patches PL, PR;
+        raw_patches(IL, b.pitch, b.W, b.H, exL[i], eyL[i], ethL[i], p.shift_mag, lane, vp, vm);
+        normalise_patches(vp, vm, lane, PL);
+        double bestS = -1.0;
+        int bestK = -1, nsurv = 0;
+        for (int k = 0; k < ncl; ++k) {
+            raw_patches(IR, b.pitch, b.W, b.H, s_ox[w][k], s_oy[w][k], s_ot[w][k], p.shift_mag, lane, vp, vm);
+            normalise_patches(vp, vm, lane, PR);
+            const double s = ncc_score(PL, PR);
+            ++n2;
+            if (s > p.ncc_thresh) {
+                if (dumps && lane == 0) dump_put(b.dump[DUMP_S11], st + nsurv, -1, s_ox[w][k], s_oy[w][k], s_ot[w][k], s);
+                ++nsurv;
+                if (s > bestS) { bestS = s; bestK = k; }
+            }
+        }
+        if (dumps && lane == 0) b.dump[DUMP_S11].n[i] = nsurv;
+        if (lane == 0) {
+            if (bestK >= 0) {
+                ebvo_mate m;
+                m.left_index = i; m.reserved = 0;
+                m.lx = exL[i]; m.ly = eyL[i]; m.ltheta = ethL[i];
+                m.rx = s_ox[w][bestK]; m.ry = s_oy[w][bestK]; m.rtheta = s_ot[w][bestK];
+                m.score = bestS;
+                mates[i] = m;
+                mateFlag[i] = 1;
+                c_x[st] = m.rx; c_y[st] = m.ry; c_th[st] = m.rtheta; c_score[st] = bestS;
+                ccount[i] = 1;
+            } else { mateFlag[i] = 0; ccount[i] = 0; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n2) atomicAdd(&b.counters[(size_t)f * 8 + 4], n2);
+}
+
+// S13: ordered compaction of the per-left-edge staging slots into the mate list (one CTA per frame)
+__global__ void __launch_bounds__(1024) compact_kernel(DevBatch b, ebvo_mate* out, int outStride)
+{
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nL = b.nE[2 * f];
+    const int* flag = b.mateFlag + (size_t)f * b.E;
+    const ebvo_mate* stg = b.mates + (size_t)f * b.E;
+    ebvo_mate* dst = out + (size_t)f * outStride;
+    const int per = (nL + 1023) / 1024;
+    const int i0 = tid * per;
+    int local = 0;
+    for (int k = 0; k < per; ++k) { int i = i0 + k; if (i < nL) local += flag[i]; }
+    __shared__ int s_w[32];
+    int v = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, v, d); if ((tid & 31) >= d) v += t; }
+    if ((tid & 31) == 31) s_w[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        int x = s_w[tid];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, x, d); if (tid >= d) x += t; }
+        s_w[tid] = x;
+    }
+    __syncthreads();
+    int pos = v - local + ((tid >> 5) ? s_w[(tid >> 5) - 1] : 0);
+    for (int k = 0; k < per; ++k) {
+        int i = i0 + k;
+        if (i < nL && flag[i]) { if (pos < outStride) dst[pos] = stg[i]; ++pos; }
+    }
+    if (tid == 1023) b.nMates[f] = pos < outStride ? pos : outStride;
+}
+
+// debug: copy frame 0's live pool (src < 0) or dump[src] into compact arrays at host-scanned offsets
+__global__ void snapshot_kernel(DevBatch b, int src, const int* offsets, int* ridx, double* x, double* y, double* th, double* score)
+{
+    const int nL = b.nE[0];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nL) return;
+    const int st = b.cstart[i];
+    const int n = offsets[i + 1] - offsets[i];
+    for (int k = 0; k < n; ++k) {
+        const int o = offsets[i] + k;
+        if (src < 0) { ridx[o] = b.c_ridx[st + k]; x[o] = b.c_x[st + k]; y[o] = b.c_y[st + k]; th[o] = b.c_th[st + k]; score[o] = b.c_score[st + k]; }
+        else { const DumpBuf& d = b.dump[src]; ridx[o] = d.ridx[st + k]; x[o] = d.x[st + k]; y[o] = d.y[st + k]; th[o] = d.th[st + k]; score[o] = d.score[st + k]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------
+static int g_sms = 0;
+
+static dim3 warp_grid(int nFrames)
+{
+    if (!g_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev); }
+    int gx = (g_sms * 16 + nFrames - 1) / nFrames;   // about 16 CTAs of 4 warps per SM over the whole batch
+    if (gx < 1) gx = 1;
+    return dim3(gx, nFrames);
+}
+
+void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, Prof* prof)
+{
+    dim3 g((b.W + 31) / 32, (b.H + 7) / 8, nFrames), t(32, 8);
+    EBVO_KERNEL(prof, "sobel", st, (sobel_kernel<<<g, t, 0, st>>>(b)));
+}
+
+static const double* upload_F(const DevBatch& b, const double* F21, cudaStream_t st)
+{
+    cudaMemcpyAsync(b.dF, F21, 9 * sizeof(double), cudaMemcpyHostToDevice, st);
+    return b.dF;
+}
+
+void match_prologue(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, Prof* prof)
+{
+    (void)p;
+    upload_F(b, F21, st);
+    cudaMemsetAsync(b.poolUsed, 0, sizeof(int) * nFrames, st);
+    cudaMemsetAsync(b.counters, 0, sizeof(unsigned long long) * 8 * nFrames, st);
+    launch_sobel(b, nFrames, st, prof);
+    EBVO_KERNEL(prof, "bounds", st, (bounds_kernel<<<nFrames, 1024, 0, st>>>(b)));
+}
+void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "gate", st, (gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, b.dF)));
+}
+void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "sift_gate", st, (sift_gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+}
+void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "ncc_bnb", st, (ncc_bnb_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, sift ? 1 : 0)));
+}
+void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "gn", st, (gn_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+}
+void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "cluster_ncc_best", st, (cluster_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+}
+
+void launch_match(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, bool sift, cudaStream_t st, Prof* prof)
+{
+    match_prologue(b, p, F21, nFrames, st, prof);
+    match_gate(b, p, nFrames, st, prof);
+    if (sift) match_sift(b, p, nFrames, st, prof);
+    match_ncc(b, p, nFrames, sift, st, prof);
+    match_gn(b, p, nFrames, st, prof);
+    match_cluster(b, p, nFrames, st, prof);
+}
+
+void launch_compact(const DevBatch& b, int nFrames, ebvo_mate* d_out, int stride, cudaStream_t st, Prof* prof)
+{
+    EBVO_KERNEL(prof, "compact", st, (compact_kernel<<<nFrames, 1024, 0, st>>>(b, d_out, stride)));
+}
+
+void launch_gate_count(const DevBatch& b, const DevParams& p, const double* F21, int mode, int* d_counts, cudaStream_t st)
+{
+    const double* dF = upload_F(b, F21, st);
+    gate_count_kernel<<<592, 32 * WPB, 0, st>>>(b, p, dF, mode, d_counts);
+}
+void launch_gate_fill(const DevBatch& b, const DevParams& p, const double* F21, int mode, const int* d_offsets, int* d_ridx, cudaStream_t st)
+{
+    const double* dF = upload_F(b, F21, st);
+    gate_fill_kernel<<<592, 32 * WPB, 0, st>>>(b, p, dF, mode, d_offsets, d_ridx);
+}
+void launch_snapshot(const DevBatch& b, int src, const int* d_offsets, int* ridx, double* x, double* y, double* th, double* score, cudaStream_t st)
+{
+    snapshot_kernel<<<(b.E + 127) / 128, 128, 0, st>>>(b, src, d_offsets, ridx, x, y, th, score);
+}
+
+// ---- small single-purpose entry points ----------------------------------------------------------------
+__global__ void edge_patches_kernel(const uint8_t* I, int w, int h, int pitch, const double* ex, const double* ey, const double* eth, int n,
+                                    double shift, float* plus, float* minus)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n) return;
+    float vp[2], vm[2];
+    raw_patches(I, pitch, w, h, ex[e], ey[e], eth[e], shift, lane, vp, vm);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int t = lane + 32 * u;
+        if (t < 49) { plus[(size_t)e * 49 + t] = vp[u]; minus[(size_t)e * 49 + t] = vm[u]; }
+    }
+}
+void launch_edge_patches(const uint8_t* d_img, int w, int h, int pitch, const double* ex, const double* ey, const double* eth, int n,
+                         double shift, float* plus, float* minus, cudaStream_t st)
+{
+    if (n > 0) edge_patches_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_img, w, h, pitch, ex, ey, eth, n, shift, plus, minus);
+}
+
+__global__ void ncc_pairs_kernel(const float* p1, const float* p2, int n, double* out)
+{
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= n) return;
+    float a[2], z[2] = {0.f, 0.f}, c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int t = lane + 32 * u;
+        a[u] = t < 49 ? p1[(size_t)e * 49 + t] : 0.f;
+        c[u] = t < 49 ? p2[(size_t)e * 49 + t] : 0.f;
+    }
+    Patches A, B;
+    normalise_patches(a, z, lane, A);
+    normalise_patches(c, z, lane, B);
+    double pp = (double)A.p[0] * (double)B.p[0] + (double)A.p[1] * (double)B.p[1];
+    pp = warp_sum(pp);
+    if (A.flatP || B.flatP) pp = -1.0;
+    if (lane == 0) out[e] = pp;
+}
+void launch_ncc_pairs(const float* p1, const float* p2, int n, double* out, cudaStream_t st)
+{
+    if (n > 0) ncc_pairs_kernel<<<(n + 3) / 4, 128, 0, st>>>(p1, p2, n, out);
+}
+
+__global__ void cluster_one_kernel(const double* x, const double* y, const double* th, int n, int by_orient, DevParams p,
+                                   double* cx, double* cy, double* cth, int* labels, int* nclusters)
+{
+    __shared__ double s_x[MAXC], s_y[MAXC], s_t[MAXC], s_ox[MAXC], s_oy[MAXC], s_ot[MAXC];
+    __shared__ int s_lab[MAXC];
+    const int lane = threadIdx.x;
+    for (int k = lane; k < n; k += 32) { s_x[k] = x[k]; s_y[k] = y[k]; s_t[k] = th[k]; }
+    __syncwarp();
+    const int ncl = warp_cluster(s_x, s_y, s_t, n, by_orient != 0, p, lane, s_lab, s_ox, s_oy, s_ot);
+    __syncwarp();
+    for (int k = lane; k < ncl; k += 32) { cx[k] = s_ox[k]; cy[k] = s_oy[k]; cth[k] = s_ot[k]; }
+    for (int k = lane; k < n; k += 32) labels[k] = s_lab[k];
+    if (lane == 0) *nclusters = ncl;
+}
+void launch_cluster_one(const double* x, const double* y, const double* th, int n, int by_orient, const DevParams& p,
+                        double* cx, double* cy, double* cth, int* labels, int* nclusters, cudaStream_t st)
+{
+    cluster_one_kernel<<<1, 32, 0, st>>>(x, y, th, n, by_orient, p, cx, cy, cth, labels, nclusters);
+}
+
+}  // namespace ebvo

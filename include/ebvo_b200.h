@@ -1,0 +1,170 @@
+/*
+ * ebvo_b200.h - C ABI of libebvo_b200.so: the B200 (sm_100a) implementation of the per-frame hot path of
+ * Brown-LEMS/Edge_Based_Visual_Odometry: third-order edge detection + epipolar-gated stereo edge
+ * correspondence with oriented-patch NCC, Gauss-Newton refinement and edge clustering.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; no C++/torch
+ * types.  Every function returns 0 on success or a negative EBVO_ERR_* code; ebvo_last_error() gives the
+ * text.  There is NO CPU fallback: without a CUDA device ebvo_create() fails with EBVO_ERR_NO_DEVICE.
+ * A context is bound to one GPU and one host thread; calls on a context are synchronous at return.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef EBVO_B200_H
+#define EBVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBVO_OK 0
+#define EBVO_ERR_NO_DEVICE (-1)
+#define EBVO_ERR_INVALID (-2)
+#define EBVO_ERR_CUDA (-3)
+#define EBVO_ERR_CAPACITY (-4)
+#define EBVO_ERR_NOMEM (-5)
+
+typedef struct ebvo_ctx ebvo_ctx;
+
+/* struct Edge, include/toed/cpu_toed.hpp:26-48 (location.x, location.y, orientation, index, frame_source). */
+typedef struct ebvo_edge {
+    double x, y, theta;
+    int32_t index;
+    int32_t frame_source;
+} ebvo_edge;
+
+/* Numeric content of a reference YAML (config/kitti.yaml:13-28 etc.); 3x3 matrices row-major. */
+typedef struct ebvo_calib {
+    double Kl[9], Kr[9], R21[9], T21[3];
+} ebvo_calib;
+
+/* The reference's compile-time knobs, include/definitions.h:17-36,76-77 and Stereo_Matches.h:84. */
+typedef struct ebvo_params {
+    double epipolar_line_dist_thresh; /* EPIPOLAR_LINE_DIST_THRESH 0.5 */
+    double max_disparity;             /* MAX_DISPARITY 25 */
+    double orientation_thresh_deg;    /* apply_orientation_filter(10.0), Stereo_Matches.cpp:1399 */
+    double orthogonal_shift_mag;      /* ORTHOGONAL_SHIFT_MAG 5 */
+    double ncc_thresh;                /* NCC_THRESH 0.6 */
+    double bnb_ncc;                   /* BNB_NCC 0.9 */
+    double bnb_sift;                  /* BNB_SIFT 0.4 */
+    double sift_threshold;            /* SIFT_THRESHOLD 500 */
+    double location_perturbation;     /* LOCATION_PERTURBATION 0.4 */
+    double epip_tangency_displ_thresh;/* EPIP_TANGENCY_DISPL_THRESH 3 */
+    double orient_perturbation;       /* ORIENT_PERTURBATION 0.174533 */
+    double cluster_dist_thresh;       /* CLUSTER_DIST_THRESH 1 */
+    double cluster_orient_thresh_deg; /* CLUSTER_ORIENT_THRESH 20 */
+    double cluster_orient_gauss_sigma;/* CLUSTER_ORIENT_GAUSS_SIGMA 2 */
+    int32_t max_cluster_size;         /* MAX_CLUSTER_SIZE 10 */
+    int32_t gn_max_iter;              /* 20 */
+    double gn_tol;                    /* 1e-3 */
+    double gn_huber_delta;            /* 3.0 */
+    double toed_mag_thresh;           /* "I_grad_mag <= 2" cpu_toed.cpp:406 */
+    int32_t toed_border;              /* 10, cpu_toed.cpp:401-403,553 */
+    int32_t reserved;
+} ebvo_params;
+
+/* One finalised stereo mate: final_stereo_edge_pair.left_edge / right_edge, include/Dataset.h:291-309. */
+typedef struct ebvo_mate {
+    int32_t left_index; /* index of the left edge in the left TOED list */
+    int32_t reserved;
+    double lx, ly, ltheta;
+    double rx, ry, rtheta;
+    double score; /* NCC of the surviving cluster (refine_final_scores[0]) */
+} ebvo_mate;
+
+/* Stage identifiers for debug dumps (get_Stereo_Edge_Pairs stage order, Stereo_Matches.cpp:1360-1540). */
+enum {
+    EBVO_STAGE_EPI = 0,     /* apply_Epipolar_Line_Distance_Filtering */
+    EBVO_STAGE_DISP = 1,    /* apply_Disparity_Filtering */
+    EBVO_STAGE_ORIENT = 2,  /* apply_orientation_filter */
+    EBVO_STAGE_SIFT = 3,    /* apply_SIFT_filtering (descriptors injected) */
+    EBVO_STAGE_NCC = 4,     /* apply_NCC_Filtering (1st) */
+    EBVO_STAGE_BNB_NCC = 5, /* apply_Best_Nearly_Best_Test(NCC) */
+    EBVO_STAGE_BNB_SIFT = 6,/* apply_Best_Nearly_Best_Test(SIFT) */
+    EBVO_STAGE_SHIFT = 7,   /* consolidate_redundant_edge_hypothesis(shift) */
+    EBVO_STAGE_GN = 8,      /* refine_edge_disparity */
+    EBVO_STAGE_CLUSTER = 9, /* consolidate_redundant_edge_hypothesis(shift+cluster) */
+    EBVO_STAGE_NCC2 = 10,   /* apply_NCC_Filtering (2nd) */
+    EBVO_STAGE_BEST = 11,   /* apply_Lowe_Ratio_Test (arg-max) */
+    EBVO_STAGE_COUNT = 12
+};
+
+/* Fills *p with the reference defaults. */
+int ebvo_params_default(ebvo_params* p);
+
+/* Context: owns device buffers for up to max_batch stereo frames of up to max_w x max_h pixels and up to
+ * max_edges edges per image.  params may be NULL (defaults).  Replaces the ThirdOrderEdgeDetectionCPU
+ * constructor/destructor (src/toed/cpu_toed.cpp:24-64,649-663) and Stereo_Matches() (Stereo_Matches.h:52). */
+int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch, int max_edges, const ebvo_params* params);
+void ebvo_destroy(ebvo_ctx* ctx);
+const char* ebvo_last_error(const ebvo_ctx* ctx);
+
+/* S0: F21 = Kr^-T [T21]x R21 Kl^-1 and F12 (src/Dataset.cpp:102-112).  Host FP64, row-major out. */
+int ebvo_fundamental(const ebvo_calib* calib, double F21[9], double F12[9]);
+
+/* ThirdOrderEdgeDetectionCPU::get_Third_Order_Edges (src/toed/cpu_toed.cpp:66-77) on one 8-bit image.
+ * out receives toed_edges in the reference's row-major order; *n_total = Total_Num_Of_TOED. */
+int ebvo_toed(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, ebvo_edge* out, int cap, int* n_edges,
+              int* n_total);
+
+/* Stereo_Matches::get_Stereo_Edge_Pairs + finalize_stereo_edge_mates (src/Stereo_Matches.cpp:1360-1653),
+ * no-GT branch, on caller-supplied edge lists.  L_und/R_und may equal L_raw/R_raw (zero distortion).
+ * descL/descR: optional per-edge SIFT descriptor pairs (n*2*128 floats, augment_Edge_Data layout); NULL =>
+ * the SIFT gate and BNB-SIFT are skipped ("SIFT-off"). */
+int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw,
+                      const uint8_t* L_und, const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL,
+                      const ebvo_edge* R, int nR, const float* descL, const float* descR, ebvo_mate* out, int cap,
+                      int* n_mates);
+
+/* Pipeline::prepare_Stereo_Images edge part + get_Stereo_Edge_Correspondences (src/Pipeline.cpp:93-131):
+ * TOED on both views + matching, edges stay on the device.  Optional edge outputs may be NULL. */
+int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_img, const uint8_t* R_img, int w, int h,
+                      int stride, ebvo_mate* out, int cap, int* n_mates, ebvo_edge* L_edges, int* nL, ebvo_edge* R_edges,
+                      int* nR, int edge_cap);
+
+/* Batch of independent stereo frames (the StereoIterator::getNext loop of cmd/main_VO.cpp:99-113 with
+ * frames already in memory).  L_imgs/R_imgs: n_frames host pointers.  out: n_frames*cap mates;
+ * n_mates: n_frames counts.  Host buffers in, host buffers out (copies are part of the call). */
+int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
+                      const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates);
+
+/* Device-resident variant used to time the kernels alone: upload once, run many times, download once. */
+int ebvo_batch_upload(ebvo_ctx* ctx, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
+                      int h, int stride);
+int ebvo_batch_run(ebvo_ctx* ctx, const ebvo_calib* calib, int do_match); /* async on the context stream */
+int ebvo_batch_sync(ebvo_ctx* ctx);
+int ebvo_batch_download(ebvo_ctx* ctx, ebvo_mate* out, int cap, int* n_mates);
+int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* stage_counts /* n_frames*8 or NULL */);
+
+/* Utility::get_edge_patches (src/utility.cpp:182-212): 7x7 "+" and "-" patches of n edges of one image. */
+int ebvo_edge_patches(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n,
+                      float* plus49, float* minus49);
+/* Utility::get_patch_similarity / MatlabNCCComputer::computeNCC (src/utility.cpp:163-180,
+ * src/MatlabNCCComputer.cpp:58-90): NCC of n pairs of 49-vectors. */
+int ebvo_ncc_patch_pair(ebvo_ctx* ctx, const float* p1, const float* p2, int n_pairs, double* out);
+/* EdgeClusterer::performClustering (src/EdgeClusterer.cpp:119-302) on one candidate set. */
+int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientation, ebvo_edge* centers, int* labels,
+                 int* n_clusters);
+/* util_compute_Img_Gradients (include/utility.h:131-141): Sobel 3x3 * 1/8, reflect-101 border. */
+int ebvo_sobel(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* gx, float* gy);
+
+/* Debug stage dumps of the LAST ebvo_stereo_match call (enable before the call).  Ragged per-left-edge lists:
+ * offsets[nL+1]; per entry right-edge index (or -1), x, y, theta, score. */
+int ebvo_set_stage_dumps(ebvo_ctx* ctx, int enable);
+int ebvo_stage_size(ebvo_ctx* ctx, int stage, int* n_left, int* total);
+int ebvo_stage_fetch(ebvo_ctx* ctx, int stage, int* offsets, int* ridx, double* x, double* y, double* theta,
+                     double* score);
+
+/* Per-kernel device times (ms) of the last batch/frame call, measured with CUDA events on the context
+ * stream when profiling is enabled.  names: array of const char* owned by the library. */
+int ebvo_set_profiling(ebvo_ctx* ctx, int enable);
+int ebvo_get_kernel_times(ebvo_ctx* ctx, const char*** names, const float** ms, const int** launches, int* n);
+/* The CUDA stream (cudaStream_t) the context launches on, for external event timing. */
+void* ebvo_stream(ebvo_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBVO_B200_H */
