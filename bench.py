@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""Benchmark of the TOED + stereo-NCC hot path (BASELINE.json metric: stereo frames/s at KITTI 1241x376).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path (TOED on both views + stereo matching S1..S13, SIFT-off) over
+one batch of B synthetic KITTI-shape stereo pairs per GPU.  `value` is measured with the batch resident in
+HBM (CUDA events on the library's stream); `e2e` goes through the C-ABI batch call with pinned HOST buffers
+(H2D of the images and D2H of the mates inside the timed region).  Frames are independent, so N GPUs each
+process their own batch (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's own CPU implementation on the host cores: the unmodified reference
+TOED compiled in place (oracle/_ref) + the C++ port of the stereo stage (the reference stereo sources need
+OpenCV/Eigen and cannot be compiled here), one frame per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP32_LANES_PER_SM = 128
+TOED_FLOP_PER_PX = 1636.0      # 818 MAC per input pixel, separable form
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(r) > k and r[k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_frame(cal, L, R, threads=0):
+    """One frame through the CPU path: reference TOED (oracle/_ref) x2 + stereo port.  Returns seconds and parts."""
+    import oracle
+    t0 = time.perf_counter()
+    if oracle.have_ref():
+        eL, _, _, _ = oracle.toed_reference(L, threads)
+        eR, _, _, _ = oracle.toed_reference(R, threads)
+        kind = "reference"
+    else:
+        eL, _ = oracle.toed(L)
+        eR, _ = oracle.toed(R)
+        kind = "port"
+    t1 = time.perf_counter()
+    F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    res = oracle.stereo(L, R, eL, eR, F21, want_dumps=False, threads=threads)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, t2 - t1, kind, len(res.mate_left)
+
+
+def run_reference(args, cal, rank):
+    from edge_based_visual_odometry_b200 import synth
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = [synth.stereo_pair(cal, f) for f in range(2)]
+    for w in range(args.warmup):
+        cpu_reference_frame(cal, *frames[w % 2])
+    t0 = time.perf_counter()
+    kind = "port"
+    for k in range(args.steps):
+        _, _, _, kind, _ = cpu_reference_frame(cal, *frames[k % 2])
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": "stereo frames/s (TOED+NCC stereo match) at KITTI 1241x376", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "KITTI-shape 1241x376 synthetic stereo pairs, 1 frame per step, SIFT-off", "frames_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores,
+                             "kind": "reference" if kind == "reference" else "port",
+                             "sample": "TOED = unmodified reference cpu_toed.cpp (oracle/_ref) on both views; stereo S1-S13 = C++ port "
+                                       "(reference stereo sources need OpenCV/Eigen, not buildable here); 1 frame per step"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=160, help="stereo frames per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (cycled to fill the batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gn-fp32", action="store_true", help="use the FP32 Gauss-Newton variant (not the parity default)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from edge_based_visual_odometry_b200 import synth
+    cal = synth.kitti_calib()
+    if args.impl == "reference":
+        run_reference(args, cal, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from edge_based_visual_odometry_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    H, W = cal.height, cal.width
+    CAP = 49152   # mates per frame returned to the host
+    # distinct frames per rank (different seeds per rank), cycled to fill the batch
+    base = [synth.stereo_pair(cal, rank * 1000 + f) for f in range(min(args.distinct, B))]
+    # pinned host staging for the e2e path
+    hL = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    hR = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    for f in range(B):
+        hL[f] = torch.from_numpy(base[f % len(base)][0])
+        hR[f] = torch.from_numpy(base[f % len(base)][1])
+    nL_imgs = [hL[f].numpy() for f in range(B)]
+    nR_imgs = [hR[f].numpy() for f in range(B)]
+    h_out = torch.empty((B, CAP, 64), dtype=torch.uint8).pin_memory()
+    out_np = h_out.numpy().view(_lib.MATE_DTYPE).reshape(B, CAP)
+    n_mates = np.zeros(B, np.int32)
+
+    prm = _lib.default_params()
+    prm.gn_fp32 = 1 if args.gn_fp32 else 0
+    ctx = _lib.Context(local_rank, W, H, max_batch=B, max_edges=65536, params=prm)
+    calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    ctx.batch_upload(nL_imgs, nR_imgs)
+    ctx.batch_sync()
+    for _ in range(args.warmup):
+        ctx.batch_run(calib, True)
+    ctx.batch_sync()
+    ctx.set_profiling(True)           # per-kernel CUDA events on the launching stream, inside the timed region
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ctx.batch_run(calib, True)
+    ev1.record(stream)
+    ctx.batch_sync()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = ev0.elapsed_time(ev1)
+    ktimes = ctx.kernel_times()
+    ctx.set_profiling(False)
+    nL, nR, nM, counters = ctx.batch_counts()
+
+    # ---------------- end to end through the C ABI with host buffers (`e2e`) ----------------
+    for _ in range(2):
+        ctx.stereo_batch(calib, nL_imgs, nR_imgs, CAP, out_np, n_mates)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.stereo_batch(calib, nL_imgs, nR_imgs, CAP, out_np, n_mates)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = t.tolist()
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peaks, peak_src = read_peaks()
+        frames_total = world * B * args.steps
+        value = frames_total / (ms_total / 1e3)
+        e2e_value = frames_total / (e2e_ms / 1e3)
+        # dominant kernel + roofline
+        ksum = sum(v[0] for v in ktimes.values())
+        dom = max(ktimes.items(), key=lambda kv: kv[1][0])
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp32_peak = sms * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12      # TFLOP/s, nominal FP32 FMA peak at max clock
+        toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_orient", (0, 1))[0]
+        toed_flops = TOED_FLOP_PER_PX * W * H * 2 * B * args.steps
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "share": v[0] / ksum if ksum else None, "launches": v[1]} for k, v in ktimes.items()}
+        c = counters.sum(axis=0)
+        # algorithmic bytes of the matching stage per step (SURVEY.md 8(d) formula, this run's counts)
+        match_bytes = (2 * W * H * 2 + 2 * 4 * W * H) * B + 24.0 * (nL.sum() + nR.sum()) + 4.0 * c[0] + 64.0 * nM.sum()
+        roof = {"kernel": "toed_grad_nms+toed_orient", "bound": "fp32", "achieved": toed_flops / (toed_ms / 1e3) / 1e12 if toed_ms else None,
+                "peak": fp32_peak, "unit": "TFLOP/s", "frac": (toed_flops / (toed_ms / 1e3) / 1e12) / fp32_peak if toed_ms else None,
+                "traffic": None,
+                "peak_source": f"nominal FP32 FMA peak = {sms} SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock); "
+                               "tensor cores unused (no dense contraction on this path)",
+                "algorithmic_flop_per_px": TOED_FLOP_PER_PX,
+                "dominant_kernel_by_time": dom[0], "dominant_kernel_share": dom[1][0] / ksum if ksum else None,
+                "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "matching_algorithmic_bytes_per_step": float(match_bytes)}}
+        line = {"metric": "stereo frames/s (TOED+NCC stereo match) at KITTI 1241x376", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 mixed", "data": "synthetic",
+                "config": {"workload": "configs[2]: KITTI-shape 1241x376 synthetic stereo batch, TOED x2 + stereo match S1-S13 (SIFT-off)",
+                           "frames_per_gpu_per_step": B, "distinct_frames": len(base), "l2": "batch inputs (%.0f MB u8 images + per-frame "
+                           "intermediates) exceed the 126 MB L2" % (2 * B * W * H / 1e6),
+                           "edges_per_image": float(nL.mean()), "mates_per_frame": float(nM.mean())},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(2 * B * W * H), "d2h_bytes_per_step": int(64 * nM.sum() + 4 * B)},
+                "gpu_launches": int(sum(v[1] for v in ktimes.values())),
+                "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
+                "work_per_step": {"s3_pairs": int(c[0]), "bnb_pairs": int(c[1]), "gn_pairs": int(c[2]), "gn_iterations": int(c[3]), "ncc2_pairs": int(c[4])}}
+        if world == 1 and not args.no_cpu_baseline:
+            secs, ttoed, tst, kind, nm = cpu_reference_frame(cal, *base[0])
+            secs2, ttoed2, tst2, _, _ = cpu_reference_frame(cal, *base[1 % len(base)])
+            tot = secs + secs2
+            line["cpu_baseline"] = {"value": 2.0 / tot, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind,
+                                    "sample": "2 frames of the same workload: reference TOED (oracle/_ref, OpenMP all cores) %.2f s + "
+                                              "stereo port %.2f s per frame" % ((ttoed + ttoed2) / 2, (tst + tst2) / 2)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,7 @@ void set_devparams(ebvo_ctx* ctx)
     d.clus_orient_rad = q.cluster_orient_thresh_deg * (M_PI / 180.0);   // deg_to_rad, include/utility.h:293-297
     d.clus_sigma = q.cluster_orient_gauss_sigma; d.clus_max = q.max_cluster_size; d.gn_max_iter = q.gn_max_iter;
     d.gn_tol = q.gn_tol; d.gn_huber = q.gn_huber_delta; d.toed_mag_thresh = (float)q.toed_mag_thresh; d.toed_border = q.toed_border;
+    d.gn_fp32 = q.gn_fp32;
 }
 
 // geometry-dependent fields of the device view
@@ -181,7 +182,7 @@ int scan_counts(ebvo_ctx* ctx, const int* d_counts, int nL, std::vector<int>& of
 int snapshot_stage(ebvo_ctx* ctx, int stage, int src, int nL)
 {
     StageData& S = ctx->stages[stage];
-    const int* d_counts = src < 0 ? ctx->b.ccount : ctx->b.dump[src].n;
+    const int* d_counts = (src < 0 || src == DUMP_S8) ? ctx->b.ccount : ctx->b.dump[src].n;   // S8 keeps the S7 counts
     int* d_off = nullptr;
     int rc = scan_counts(ctx, d_counts, nL, S.off, &d_off);
     if (rc) return rc;
@@ -302,7 +303,7 @@ int ebvo_params_default(ebvo_params* p)
     p->ncc_thresh = 0.6; p->bnb_ncc = 0.9; p->bnb_sift = 0.4; p->sift_threshold = 500.0; p->location_perturbation = 0.4;
     p->epip_tangency_displ_thresh = 3.0; p->orient_perturbation = 0.174533; p->cluster_dist_thresh = 1.0;
     p->cluster_orient_thresh_deg = 20.0; p->cluster_orient_gauss_sigma = 2.0; p->max_cluster_size = 10; p->gn_max_iter = 20;
-    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->reserved = 0;
+    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->gn_fp32 = 0;
     return EBVO_OK;
 }
 
@@ -341,7 +342,8 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     CK(dalloc(ctx, &b.coords, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.ex, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.ey, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.eth, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.nE, (size_t)nImg)); CK(dalloc(ctx, &b.nTot, (size_t)nImg));
-    CK(dalloc(ctx, &b.gx, b.gStride * B)); CK(dalloc(ctx, &b.gy, b.gStride * B));
+    if (ctx->params.gn_fp32) CK(dalloc(ctx, &b.pk, b.gStride * B));
+    else CK(dalloc(ctx, &b.pk16, b.gStride * B));
     CK(dalloc(ctx, &b.blk, (size_t)b.NB * B)); CK(dalloc(ctx, &b.pmax, (size_t)b.NB * B)); CK(dalloc(ctx, &b.smin, (size_t)b.NB * B));
     CK(dalloc(ctx, &b.lines, (size_t)b.E * 3 * B));
     CK(dalloc(ctx, &b.cstart, (size_t)b.E * B)); CK(dalloc(ctx, &b.ccount, (size_t)b.E * B));
@@ -349,6 +351,7 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     CK(dalloc(ctx, &b.c_ridx, (size_t)b.P * B));
     CK(dalloc(ctx, &b.c_x, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_y, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_th, (size_t)b.P * B));
     CK(dalloc(ctx, &b.c_score, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_conf, (size_t)b.P * B));
+    CK(dalloc(ctx, &b.c_owner, (size_t)b.P * B));
     CK(dalloc(ctx, &b.mates, (size_t)b.E * B)); CK(dalloc(ctx, &b.nMates, (size_t)B)); CK(dalloc(ctx, &b.mateFlag, (size_t)b.E * B));
     CK(dalloc(ctx, &b.errFlag, (size_t)4)); CK(dalloc(ctx, &b.counters, (size_t)8 * B));
     CK(dalloc(ctx, &ctx->d_out, (size_t)b.E * B));
@@ -659,9 +662,20 @@ int ebvo_sobel(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, floa
     if (rc) return rc;
     if ((rc = upload_image(ctx, ctx->d_raw, 1, img, stride))) return rc;   // slot 1 = right view of frame 0
     launch_sobel(ctx->b, 1, ctx->st, nullptr);
-    CK(cudaMemcpyAsync(gx, ctx->b.gx, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(gy, ctx->b.gy, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));
+    if (ctx->b.pk) {
+        std::vector<float> pk((size_t)w * h * 4);
+        CK(cudaMemcpyAsync(pk.data(), ctx->b.pk, pk.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (size_t k = 0; k < (size_t)w * h; ++k) { gx[k] = pk[4 * k + 1]; gy[k] = pk[4 * k + 2]; }
+    } else {
+        std::vector<uint32_t> pk((size_t)w * h * 2);
+        CK(cudaMemcpyAsync(pk.data(), ctx->b.pk16, pk.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (size_t k = 0; k < (size_t)w * h; ++k) {
+            gx[k] = (float)(int16_t)(pk[2 * k] >> 16) * 0.125f;
+            gy[k] = (float)(int16_t)(pk[2 * k + 1] & 0xffff) * 0.125f;
+        }
+    }
     return EBVO_OK;
 }
 

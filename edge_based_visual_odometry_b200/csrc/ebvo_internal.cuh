@@ -44,12 +44,13 @@ struct DevBatch {
     uint32_t* coords;                     // [img][E] packed (i<<16 | j)
     double *ex, *ey, *eth;                // [img][E]
     int *nE, *nTot;                       // [img]
-    float *gx, *gy; size_t gStride;       // Sobel planes of the undistorted RIGHT images, [frame][H*W]
+    float4* pk; uint2* pk16; size_t gStride;  // pk16: {I, 8gx, 8gy} as int16 for the default (FP64) GN kernel;           // packed {I, gx, gy, 0} of the undistorted RIGHT images, [frame][H*W] (Sobel 3x3 / 8)
     float4* blk; float* pmax; float* smin;  // right-edge block bounds [frame][NB]
     double* lines;                        // [frame][E][3]
     int *cstart, *ccount;                 // [frame][E]
     int* poolUsed;                        // [frame]
     int* c_ridx; double *c_x, *c_y, *c_th, *c_score, *c_conf;  // [frame][P]
+    int* c_owner;                         // [frame][P] left-edge index of a live pool slot, -1 for dead slots
     ebvo_mate* mates; int* nMates;        // [frame][E], [frame]
     int* mateFlag;                        // [frame][E]
     int* errFlag;                         // single int: capacity overflows
@@ -66,6 +67,7 @@ struct DevParams {
     int clus_max, gn_max_iter;
     double gn_tol, gn_huber;
     float toed_mag_thresh; int toed_border;
+    int gn_fp32;
 };
 
 // kernel launchers (defined in toed.cu / match.cu); all asynchronous on `st`

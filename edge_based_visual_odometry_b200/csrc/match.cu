@@ -53,8 +53,12 @@ __global__ void sobel_kernel(DevBatch b)
     auto at = [&](int yy, int xx) { return (float)I[(size_t)yy * b.pitch + xx]; };
     float gx = (at(ym, xp) - at(ym, xm)) * 0.125f + (at(y, xp) - at(y, xm)) * 0.25f + (at(yp, xp) - at(yp, xm)) * 0.125f;
     float gy = (at(yp, xm) - at(ym, xm)) * 0.125f + (at(yp, x) - at(ym, x)) * 0.25f + (at(yp, xp) - at(ym, xp)) * 0.125f;
-    b.gx[(size_t)f * b.gStride + (size_t)y * b.W + x] = gx;
-    b.gy[(size_t)f * b.gStride + (size_t)y * b.W + x] = gy;
+    const size_t o = (size_t)f * b.gStride + (size_t)y * b.W + x;
+    if (b.pk) b.pk[o] = make_float4(at(y, x), gx, gy, 0.f);
+    if (b.pk16) {   // {I, 8*gx, 8*gy} as exact 16-bit integers (|8*g| <= 1020): 8 bytes per pixel
+        const int i8 = (int)at(y, x), gx8 = (int)(gx * 8.f), gy8 = (int)(gy * 8.f);
+        b.pk16[o] = make_uint2((uint32_t)i8 | ((uint32_t)(gx8 & 0xffff) << 16), (uint32_t)(gy8 & 0xffff));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -260,19 +264,22 @@ __global__ void __launch_bounds__(32 * WPB) gate_fill_kernel(DevBatch b, DevPara
 // Oriented 7x7 patches + NCC.  Lane l owns patch cells t = l and t = l + 32 (< 49) of BOTH the "+" and "-"
 // patch, so the four cross dot products are lane-local before the shuffle reduction.
 // ------------------------------------------------------------------------------------------------------
-// include/utility.h:81-104 on an 8-bit image (convertTo CV_64F is exact): NaN outside or on integer coordinates
-__device__ __forceinline__ double bilinear_u8(const uint8_t* __restrict__ I, int pitch, int W, int H, double px, double py)
+// include/utility.h:81-104 on an 8-bit image (convertTo CV_64F is exact): NaN outside the image or when a
+// coordinate is an exact integer (0/0 weights in the reference formula).  FP64 blend, stored as float
+// (utility.cpp:206-209), so that patch values are bit-identical to the reference's.
+__device__ __forceinline__ float bilinear_u8(const uint8_t* __restrict__ I, int pitch, int W, int H, double px, double py)
 {
-    if (!(px == px) || !(py == py)) return CUDART_NAN;
-    double fx = floor(px), cx = ceil(px), fy = floor(py), cy = ceil(py);
-    if (fx < 0.0 || fy < 0.0 || cx >= (double)W || cy >= (double)H) return CUDART_NAN;
-    if (cx == fx || cy == fy) return CUDART_NAN;   // 0/0 weights in the reference formula
-    int ifx = (int)fx, icx = (int)cx, ify = (int)fy, icy = (int)cy;
-    double v11 = (double)I[(size_t)icy * pitch + ifx], v21 = (double)I[(size_t)icy * pitch + icx];
-    double v12 = (double)I[(size_t)ify * pitch + ifx], v22 = (double)I[(size_t)ify * pitch + icx];
-    double wx1 = cx - px, wx2 = px - fx;          // denominators are exactly 1
-    double f1 = wx1 * v11 + wx2 * v21, f2 = wx1 * v12 + wx2 * v22;
-    return (py - fy) * f1 + (cy - py) * f2;       // (fy-py)/(fy-cy) with fy-cy = -1
+    if (!(px == px) || !(py == py)) return CUDART_NAN_F;
+    const double fx = floor(px), fy = floor(py);
+    if (fx < 0.0 || fy < 0.0 || fx == px || fy == py) return CUDART_NAN_F;
+    if (fx + 1.0 >= (double)W || fy + 1.0 >= (double)H) return CUDART_NAN_F;
+    const int ix = (int)fx, iy = (int)fy;
+    const double wx2 = px - fx, wx1 = (fx + 1.0) - px, wy2 = py - fy, wy1 = (fy + 1.0) - py;   // denominators are exactly 1
+    const uint8_t* r0 = I + (size_t)iy * pitch + ix;
+    const double v12 = (double)__ldg(r0), v22 = (double)__ldg(r0 + 1), v11 = (double)__ldg(r0 + pitch), v21 = (double)__ldg(r0 + pitch + 1);
+    const double f1 = wx1 * v11 + wx2 * v21;   // row ceil(y)
+    const double f2 = wx1 * v12 + wx2 * v22;   // row floor(y)
+    return (float)(wy2 * f1 + wy1 * f2);
 }
 
 struct Patches {      // normalised (zero-mean, unit-norm) cells owned by this lane
@@ -294,8 +301,8 @@ __device__ __forceinline__ void raw_patches(const uint8_t* I, int pitch, int W, 
         if (t < 49) {
             int i = t / 7 - 3, j = t % 7 - 3;
             double ox = c * (double)i - s * (double)j, oy = s * (double)i + c * (double)j;   // utility.cpp:151
-            vp[u] = (float)bilinear_u8(I, pitch, W, H, ox + pxp, oy + pyp);
-            vm[u] = (float)bilinear_u8(I, pitch, W, H, ox + pxm, oy + pym);
+            vp[u] = bilinear_u8(I, pitch, W, H, ox + pxp, oy + pyp);
+            vm[u] = bilinear_u8(I, pitch, W, H, ox + pxm, oy + pym);
         }
     }
 }
@@ -396,6 +403,7 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
     int* c_ridx = b.c_ridx + (size_t)f * b.P;
     double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
     double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+    int* c_owner = b.c_owner + (size_t)f * b.P;
     const bool dumps = b.dumps && f == 0;
     unsigned long long kept = 0;
     for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
@@ -447,7 +455,9 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
             c_x[st + k] = exR[r]; c_y[st + k] = eyR[r]; c_th[st + k] = ethR[r];
             c_score[st + k] = s_sc[w][o];
             c_conf[st + k] = s_cf[w][o];
+            c_owner[st + k] = i;
         }
+        for (int k = keep + lane; k < n; k += 32) c_owner[st + k] = -1;   // dead slots of this segment
         if (lane == 0) ccount[i] = keep;
         kept += keep;
         __syncwarp();
@@ -525,60 +535,48 @@ __device__ __forceinline__ void shift_to_line(double a, double b, double c, cons
     if (tangential(a, b, c, x, y, t2, xi, yi) < p.tang_displ) { x = xi; y = yi; th = t2; }
 }
 
-// include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped, float result
+// include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped sampler.
+// Coordinates are split in FP64 into an integer cell and an FP32 fraction; the four-corner blend runs in FP32
+// (the reference blends in FP64 and rounds the result to float: same 2^-24 relative resolution).
+__device__ __forceinline__ void cell_of(double x, int n, int& x0, int& x1, float& a)
+{
+    x = fmin(fmax(x, 0.0), (double)n - 1.0);
+    x0 = __double2int_rd(x);
+    x1 = min(x0 + 1, n - 1);
+    a = (float)(x - (double)x0);
+}
 __device__ __forceinline__ float sample_u8(const uint8_t* __restrict__ I, int pitch, int w, int h, double x, double y)
 {
-    x = fmin(fmax(x, 0.0), (double)w - 1.0);
-    y = fmin(fmax(y, 0.0), (double)h - 1.0);
-    const int x0 = (int)floor(x), y0 = (int)floor(y);
-    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-    const double a = x - x0, bb = y - y0;
-    const float v00 = (float)I[(size_t)y0 * pitch + x0], v10 = (float)I[(size_t)y0 * pitch + x1];
-    const float v01 = (float)I[(size_t)y1 * pitch + x0], v11 = (float)I[(size_t)y1 * pitch + x1];
-    return (float)((1 - a) * (1 - bb) * v00 + a * (1 - bb) * v10 + (1 - a) * bb * v01 + a * bb * v11);
-}
-// the same sampler applied to the image and to both Sobel planes at one coordinate
-__device__ __forceinline__ void sample3(const uint8_t* __restrict__ I, int pitch, const float* __restrict__ GX, const float* __restrict__ GY,
-                                        int w, int h, double x, double y, float& vi, float& vgx, float& vgy)
-{
-    x = fmin(fmax(x, 0.0), (double)w - 1.0);
-    y = fmin(fmax(y, 0.0), (double)h - 1.0);
-    const int x0 = (int)floor(x), y0 = (int)floor(y);
-    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-    const double a = x - x0, bb = y - y0;
-    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
-    const size_t o00 = (size_t)y0 * w + x0, o10 = (size_t)y0 * w + x1, o01 = (size_t)y1 * w + x0, o11 = (size_t)y1 * w + x1;
-    vi = (float)(w00 * (float)I[(size_t)y0 * pitch + x0] + w10 * (float)I[(size_t)y0 * pitch + x1] +
-                 w01 * (float)I[(size_t)y1 * pitch + x0] + w11 * (float)I[(size_t)y1 * pitch + x1]);
-    vgx = (float)(w00 * GX[o00] + w10 * GX[o10] + w01 * GX[o01] + w11 * GX[o11]);
-    vgy = (float)(w00 * GY[o00] + w10 * GY[o10] + w01 * GY[o01] + w11 * GY[o11]);
+    int x0, x1, y0, y1;
+    float a, bb;
+    cell_of(x, w, x0, x1, a);
+    cell_of(y, h, y0, y1, bb);
+    const float v00 = (float)__ldg(I + (size_t)y0 * pitch + x0), v10 = (float)__ldg(I + (size_t)y0 * pitch + x1);
+    const float v01 = (float)__ldg(I + (size_t)y1 * pitch + x0), v11 = (float)__ldg(I + (size_t)y1 * pitch + x1);
+    return (1.f - a) * (1.f - bb) * v00 + a * (1.f - bb) * v10 + (1.f - a) * bb * v01 + a * bb * v11;
 }
 
-// S8 + S9.  One warp per left edge, looping over its candidates.  Lane l owns samples s = l + 32 m (m < 4,
-// s < 98): s < 49 -> "+" patch cell s, else "-" patch cell s - 49 (cell (i,j) = (t/7-3, t%7-3)).
-__global__ void __launch_bounds__(32 * WPB) gn_kernel(DevBatch b, DevParams p)
+// S8 + S9.  One warp per live pool slot (candidate).  Lane l owns samples s = l + 32 m (m < 4, s < 98):
+// s < 49 -> "+" patch cell s, else "-" patch cell s - 49 (cell (i,j) = (t/7-3, t%7-3)).
+__global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams p)
 {
-    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int imgL = 2 * f, imgR = 2 * f + 1;
-    const int nL = b.nE[imgL];
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int imgL = 2 * f;
     const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
-    const uint8_t* IR = b.und + (size_t)imgR * b.imgStride;
-    const float* GX = b.gx + (size_t)f * b.gStride;
-    const float* GY = b.gy + (size_t)f * b.gStride;
+    const float4* __restrict__ PK = b.pk + (size_t)f * b.gStride;   // right view: {I, Sobel gx, Sobel gy}
     const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
-    const int* cstart = b.cstart + (size_t)f * b.E;
-    const int* ccount = b.ccount + (size_t)f * b.E;
     double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
     double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
     int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    const int* c_owner = b.c_owner + (size_t)f * b.P;
     const bool dumps = b.dumps && f == 0;
+    const int used = min(b.poolUsed[f], b.P);
+    const int W = b.W, H = b.H;
+    const float huber = (float)p.gn_huber, tol = (float)p.gn_tol;
     unsigned long long npairs = 0, niters = 0;
-    (void)w;
-    for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < nL; i += gridDim.x * WPB) {
-        const int n = ccount[i];
-        if (dumps && lane == 0) b.dump[DUMP_S8].n[i] = n;
-        if (n == 0) continue;
-        const int st = cstart[i];
+    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
+        const int i = c_owner[q];
+        if (i < 0) continue;
         const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
         const double la = ln[0], lb = ln[1], lc = ln[2];
         double dirx = -lb, diry = la;                         // :1330-1335
@@ -586,85 +584,253 @@ __global__ void __launch_bounds__(32 * WPB) gn_kernel(DevBatch b, DevParams p)
         const double xL = exL[i], yL = eyL[i], thL = ethL[i];
         double st_, ct_;
         sincos(thL, &st_, &ct_);
-        const double nx = -st_, ny = ct_;                     // n = (-t.y, t.x), :1169-1170
         const double side = 7 / 2.0 + 1.0;                    // :1171
-        double cox[4], coy[4], rox[4], roy[4], Lc[4];
-        bool val[4], neg[4];
+        const double nxs = -st_ * side, nys = ct_ * side;     // n * side, n = (-t.y, t.x) (:1169-1170)
+        double xr = c_x[q], yr = c_y[q], thr = c_th[q];
+        shift_to_line(la, lb, lc, p, xr, yr, thr);            // S8
+        if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], q, -1, xr, yr, thr, c_score[q]);
+
+        // Per-sample coordinates.  Left: FP64 (fixed).  Right: FP32 offsets from the integer anchor (ax, ay) of the
+        // candidate; the per-iteration shift alpha*dir is added in FP32 (offsets stay below ~32 px, so the sample
+        // position keeps ~1e-6 px resolution) and the pixel cell is recovered as anchor + floor(offset).
+        const int ax = __double2int_rd(xr), ay = __double2int_rd(yr);
+        const float fxr = (float)(xr - (double)ax), fyr = (float)(yr - (double)ay);
+        float ox[4], oy[4], Lc[4];
+        float sumP = 0.f, sumM = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int s = lane + 32 * m;
+            const bool neg = s >= 49;
+            const int t = s - (neg ? 49 : 0);
+            const int ii = t / 7 - 3, jj = t % 7 - 3;
+            const double dox = (neg ? -nxs : nxs) + (ct_ * ii - st_ * jj);   // +-n*side + rotated cell (utility.h:154)
+            const double doy = (neg ? -nys : nys) + (st_ * ii + ct_ * jj);
+            ox[m] = fxr + (float)dox; oy[m] = fyr + (float)doy;
+            Lc[m] = 0.f;
+            if (s < 98) {
+                Lc[m] = sample_u8(IL, b.pitch, W, H, xL + dox, yL + doy);
+                if (neg) sumM += Lc[m]; else sumP += Lc[m];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { sumP += __shfl_xor_sync(FULL, sumP, o); sumM += __shfl_xor_sync(FULL, sumM, o); }
+        const float mLp = sumP * (1.f / 49.f), mLm = sumM * (1.f / 49.f);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { const int s = lane + 32 * m; if (s < 98) Lc[m] -= (s >= 49) ? mLm : mLp; }
+
+        double alpha = 0.0;
+        float score = 0.f, conf = 0.f;
+        const float fdx = (float)dirx, fdy = (float)diry;
+        for (int it = 0; it < p.gn_max_iter; ++it) {
+            const float sx = (float)(alpha * dirx), sy = (float)(alpha * diry);
+            float vi[4], vg[4];
+            float sRp = 0.f, sRm = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                vi[m] = 0.f; vg[m] = 0.f;
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    // clamped cell (utility.h:161-166): x<0 -> (0, a=0); x>=w-1 -> (w-1, w-1, a=0)
+                    const float xf = ox[m] + sx, yf = oy[m] + sy;
+                    const float flx = floorf(xf), fly = floorf(yf);
+                    int x0 = ax + (int)flx, y0 = ay + (int)fly;
+                    float a = xf - flx, bb = yf - fly;
+                    if (x0 < 0) { x0 = 0; a = 0.f; } else if (x0 >= W - 1) { x0 = W - 1; a = 0.f; }
+                    if (y0 < 0) { y0 = 0; bb = 0.f; } else if (y0 >= H - 1) { y0 = H - 1; bb = 0.f; }
+                    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                    const float4* c00 = PK + (y0 * W + x0);
+                    const int dx1 = x1 - x0, dy1 = (y1 - y0) * W;
+                    const float4 p00 = __ldg(c00), p10 = __ldg(c00 + dx1), p01 = __ldg(c00 + dy1), p11 = __ldg(c00 + dy1 + dx1);
+                    const float w00 = (1.f - a) * (1.f - bb), w10 = a * (1.f - bb), w01 = (1.f - a) * bb, w11 = a * bb;
+                    vi[m] = w00 * p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x;
+                    const float gx = w00 * p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y;
+                    const float gy = w00 * p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z;
+                    vg[m] = -gx * fdx + gy * fdy;                                   // :1240
+                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { sRp += __shfl_xor_sync(FULL, sRp, o); sRm += __shfl_xor_sync(FULL, sRm, o); }
+            const float mRp = sRp * (1.f / 49.f), mRm = sRm * (1.f / 49.f);
+            float Hh = 0.f, bb_ = 0.f, cost = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    const float r = Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp));
+                    const float g = vg[m];
+                    const float ar = fabsf(r);
+                    const float wgt = (ar <= huber) ? 1.f : __fdividef(huber, ar);
+                    const float wg = wgt * g;
+                    Hh = fmaf(wg, g, Hh); bb_ = fmaf(wg, r, bb_); cost = fmaf(wgt * r, r, cost);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                Hh += __shfl_xor_sync(FULL, Hh, o); bb_ += __shfl_xor_sync(FULL, bb_, o); cost += __shfl_xor_sync(FULL, cost, o);
+            }
+            ++niters;
+            if (Hh < 1e-8f) break;                          // :1253 (outputs stay at their initial values)
+            const float delta = -bb_ / Hh;
+            alpha += (double)delta;
+            if (fabsf(delta) < tol || it == p.gn_max_iter - 1) {
+                const float rms = sqrtf(cost * (1.f / 98.f));
+                score = rms; conf = __expf(-rms / huber);
+                break;
+            }
+        }
+        ++npairs;
+        if (lane == 0) {
+            c_x[q] = xr + alpha * dirx;                    // :1350-1352 (moved regardless of validity)
+            c_y[q] = yr + alpha * diry;
+            c_th[q] = thr;
+            c_score[q] = (double)score; c_conf[q] = (double)conf;
+            c_ridx[q] = -1;                                // right-edge indices are dropped at S8 (:993-997)
+        }
+    }
+    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
+}
+
+// (double)(float)v without conversion instructions: Veltkamp split keeping 24 significant bits (round to nearest).
+// Valid for |v| in the float normal range, which holds for 8-bit image samples and their Sobel responses.
+__device__ __forceinline__ double round_to_float(double v)
+{
+    const double c = __dmul_rn(v, 536870913.0);   // 2^29 + 1
+    return __dsub_rn(c, __dsub_rn(c, v));
+}
+
+// exact integer -> double without conversion instructions (2^52 magic); fields of the packed right-view pixel
+__device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x43300000, (int)(u.x & 0xffffu)) - 4503599627370496.0; }
+__device__ __forceinline__ double pk_gx(uint2 u) { return __hiloint2double(0x43300000, (((int)u.x) >> 16) ^ 0x80000000) - 4503601774854144.0; }
+__device__ __forceinline__ double pk_gy(uint2 u) { return __hiloint2double(0x43300000, ((int)(u.y << 16) >> 16) ^ 0x80000000) - 4503601774854144.0; }
+
+// FP64 variant (default): reproduces the reference arithmetic (FP64 blend rounded to float, FP64 residuals and
+// sums) so that even slowly converging / oscillating Gauss-Newton sequences track the reference to ~1e-7 px.
+// gn32_kernel above is the opt-in FP32 variant (ebvo_params.gn_fp32): ~2x faster, but rounding differences are
+// amplified by non-converging sequences (about 0.02% of the mates move by more than 1e-3 px).
+__global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int imgL = 2 * f;
+    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
+    const uint2* __restrict__ PK16 = b.pk16 + (size_t)f * b.gStride;   // right view: {I, 8*Sobel gx, 8*Sobel gy} as int16
+    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    const int* c_owner = b.c_owner + (size_t)f * b.P;
+    const bool dumps = b.dumps && f == 0;
+    const int used = min(b.poolUsed[f], b.P);
+    const int W = b.W, H = b.H;
+    unsigned long long npairs = 0, niters = 0;
+    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
+        const int i = c_owner[q];
+        if (i < 0) continue;
+        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
+        const double la = ln[0], lb = ln[1], lc = ln[2];
+        double dirx = -lb, diry = la;                         // :1330-1335
+        { const double nn = sqrt(dirx * dirx + diry * diry); dirx /= nn; diry /= nn; }
+        const double xL = exL[i], yL = eyL[i], thL = ethL[i];
+        double st_, ct_;
+        sincos(thL, &st_, &ct_);
+        const double side = 7 / 2.0 + 1.0;                    // :1171
+        const double nxs = -st_ * side, nys = ct_ * side;     // n * side, n = (-t.y, t.x) (:1169-1170)
+        double xr = c_x[q], yr = c_y[q], thr = c_th[q];
+        shift_to_line(la, lb, lc, p, xr, yr, thr);            // S8
+        if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], q, -1, xr, yr, thr, c_score[q]);
+
+        double Bx[4], By[4], Lc[4];
         double sumP = 0, sumM = 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int s = lane + 32 * m;
-            val[m] = s < 98;
-            neg[m] = s >= 49;
-            const int t = s - (neg[m] ? 49 : 0);
+            const bool neg = s >= 49;
+            const int t = s - (neg ? 49 : 0);
             const int ii = t / 7 - 3, jj = t % 7 - 3;
-            cox[m] = (neg[m] ? -1.0 : 1.0) * (nx * side);     // patch-centre offset +-n*side
-            coy[m] = (neg[m] ? -1.0 : 1.0) * (ny * side);
-            rox[m] = ct_ * ii - st_ * jj;                     // rotated cell offset (utility.h:154)
-            roy[m] = st_ * ii + ct_ * jj;
+            const double cx = neg ? -nxs : nxs, cy = neg ? -nys : nys;        // +-n*side
+            const double rx = ct_ * ii - st_ * jj, ry = st_ * ii + ct_ * jj;  // rotated cell (utility.h:154)
+            Bx[m] = (xr + cx) + rx; By[m] = (yr + cy) + ry;                   // right: + alpha*dir per iteration
             Lc[m] = 0.0;
-            if (val[m]) {
-                Lc[m] = (double)sample_u8(IL, b.pitch, b.W, b.H, (xL + cox[m]) + rox[m], (yL + coy[m]) + roy[m]);
-                if (neg[m]) sumM += Lc[m]; else sumP += Lc[m];
+            if (s < 98) {
+                // utility.h:159-172 on the left image: FP64 blend, float result
+                double x = fmin(fmax((xL + cx) + rx, 0.0), (double)W - 1.0), y = fmin(fmax((yL + cy) + ry, 0.0), (double)H - 1.0);
+                const int x0 = __double2int_rd(x), y0 = __double2int_rd(y);
+                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                const double a = x - (double)x0, bb = y - (double)y0;
+                const double v00 = (double)__ldg(IL + (size_t)y0 * b.pitch + x0), v10 = (double)__ldg(IL + (size_t)y0 * b.pitch + x1);
+                const double v01 = (double)__ldg(IL + (size_t)y1 * b.pitch + x0), v11 = (double)__ldg(IL + (size_t)y1 * b.pitch + x1);
+                Lc[m] = (double)(float)((1 - a) * (1 - bb) * v00 + a * (1 - bb) * v10 + (1 - a) * bb * v01 + a * bb * v11);
+                if (neg) sumM += Lc[m]; else sumP += Lc[m];
             }
         }
         warp_sum2(sumP, sumM);
         const double mLp = sumP / 49.0, mLm = sumM / 49.0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) if (val[m]) Lc[m] -= neg[m] ? mLm : mLp;
+        for (int m = 0; m < 4; ++m) { const int s = lane + 32 * m; if (s < 98) Lc[m] -= (s >= 49) ? mLm : mLp; }
 
-        for (int j = 0; j < n; ++j) {
-            double xr = c_x[st + j], yr = c_y[st + j], thr = c_th[st + j];
-            shift_to_line(la, lb, lc, p, xr, yr, thr);        // S8
-            if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], st + j, -1, xr, yr, thr, c_score[st + j]);
-            double alpha = 0.0, score = 0.0, conf = 0.0;
-            int logn = 0;
-            for (int it = 0; it < p.gn_max_iter; ++it) {
-                const double sx = alpha * dirx, sy = alpha * diry;
-                float vi[4], vgx[4], vgy[4];
-                double sRp = 0, sRm = 0;
+        double alpha = 0.0, score = 0.0, conf = 0.0;
+        for (int it = 0; it < p.gn_max_iter; ++it) {
+            const double sx = alpha * dirx, sy = alpha * diry;
+            double vi[4], vg[4];
+            double sRp = 0, sRm = 0;
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    vi[m] = vgx[m] = vgy[m] = 0.f;
-                    if (val[m]) {
-                        const double cx = (xr + cox[m]) + sx, cy = (yr + coy[m]) + sy;   // :1203-1204
-                        sample3(IR, b.pitch, GX, GY, b.W, b.H, cx + rox[m], cy + roy[m], vi[m], vgx[m], vgy[m]);
-                        if (neg[m]) sRm += (double)vi[m]; else sRp += (double)vi[m];
-                    }
+            for (int m = 0; m < 4; ++m) {
+                vi[m] = 0.0; vg[m] = 0.0;
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    // utility.h:161-166 without conversions: floor through a round-down add of 1.5*2^52 (the low word of
+                    // the sum is floor(x) in two's complement), clamps applied to the (cell, fraction) pair
+                    const double x = Bx[m] + sx, y = By[m] + sy;
+                    const double tx = __dadd_rd(x, 6755399441055744.0), ty = __dadd_rd(y, 6755399441055744.0);
+                    int x0 = __double2loint(tx), y0 = __double2loint(ty);
+                    double a = x - (tx - 6755399441055744.0), bb = y - (ty - 6755399441055744.0);
+                    if (x0 < 0) { x0 = 0; a = 0.0; } else if (x0 >= W - 1) { x0 = W - 1; a = 0.0; }
+                    if (y0 < 0) { y0 = 0; bb = 0.0; } else if (y0 >= H - 1) { y0 = H - 1; bb = 0.0; }
+                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
+                    const uint2* c00 = PK16 + (y0 * W + x0);
+                    const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
+                    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
+                    // FP64 blend, then rounded to float as util_bilinear_Sample_F returns float (Veltkamp split: 24-bit RN)
+                    const double bi = w00 * pk_i(u00) + w10 * pk_i(u10) + w01 * pk_i(u01) + w11 * pk_i(u11);
+                    const double bgx = w00 * pk_gx(u00) + w10 * pk_gx(u10) + w01 * pk_gx(u01) + w11 * pk_gx(u11);   // 8 * gx
+                    const double bgy = w00 * pk_gy(u00) + w10 * pk_gy(u10) + w01 * pk_gy(u01) + w11 * pk_gy(u11);   // 8 * gy
+                    vi[m] = round_to_float(bi);
+                    vg[m] = (-round_to_float(bgx) * dirx + round_to_float(bgy) * diry) * 0.125;   // :1240 (x 1/8: exact)
+                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
                 }
-                warp_sum2(sRp, sRm);
-                const double mRp = sRp / 49.0, mRm = sRm / 49.0;
-                double Hh = 0, bb = 0, cost = 0;
+            }
+            warp_sum2(sRp, sRm);
+            const double mRp = sRp / 49.0, mRm = sRm / 49.0;
+            double Hh = 0, bb_ = 0, cost = 0;
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    if (val[m]) {
-                        const double r = Lc[m] - ((double)vi[m] - (neg[m] ? mRm : mRp));
-                        const double g = -(double)vgx[m] * dirx + (double)vgy[m] * diry;   // :1240
-                        const double ar = fabs(r);
-                        const double wgt = (ar <= p.gn_huber) ? 1.0 : p.gn_huber / ar;
-                        Hh += wgt * g * g; bb += wgt * g * r; cost += wgt * r * r;
-                    }
+            for (int m = 0; m < 4; ++m) {
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    const double r = Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp));
+                    const double g = vg[m];
+                    const double ar = fabs(r);
+                    const double wgt = (ar <= p.gn_huber) ? 1.0 : p.gn_huber / ar;
+                    Hh += wgt * g * g; bb_ += wgt * g * r; cost += wgt * r * r;
                 }
-                warp_sum3(Hh, bb, cost);
-                ++niters;
-                if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
-                const double delta = -bb / Hh;
-                alpha += delta;
+            }
+            warp_sum3(Hh, bb_, cost);
+            ++niters;
+            if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+            const double delta = -bb_ / Hh;
+            alpha += delta;
+            if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
                 const double rms = sqrt(cost / 98.0);
-                ++logn;
-                if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
-                    score = rms; conf = exp(-rms / p.gn_huber);
-                    break;
-                }
+                score = rms; conf = exp(-rms / p.gn_huber);
+                break;
             }
-            ++npairs;
-            if (lane == 0) {
-                c_x[st + j] = xr + alpha * dirx;               // :1350-1352 (moved regardless of validity)
-                c_y[st + j] = yr + alpha * diry;
-                c_th[st + j] = thr;
-                c_score[st + j] = score; c_conf[st + j] = conf;
-                c_ridx[st + j] = -1;                           // right-edge indices are dropped at S8 (:993-997)
-            }
+        }
+        ++npairs;
+        if (lane == 0) {
+            c_x[q] = xr + alpha * dirx;                    // :1350-1352 (moved regardless of validity)
+            c_y[q] = yr + alpha * diry;
+            c_th[q] = thr;
+            c_score[q] = score; c_conf[q] = conf;
+            c_ridx[q] = -1;                                // right-edge indices are dropped at S8 (:993-997)
         }
     }
     if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
@@ -925,7 +1091,8 @@ void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cu
 }
 void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
-    EBVO_KERNEL(prof, "gn", st, (gn_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    if (p.gn_fp32) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    else EBVO_KERNEL(prof, "gn", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {

@@ -208,7 +208,7 @@ def stereo_pair(cal: Calibration | str = "kitti", frame: int = 0, density: float
 def fundamental_matrices(cal: Calibration):
     """F21 and F12 exactly as the reference builds them (Dataset.cpp:102-112).
 
-    Host-side float64 3x3 algebra only; returned for tests and for the oracle."""
+    Host-side float64 3x3 algebra only (used by the tests as an independent check)."""
     def skew(t):
         return np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], dtype=np.float64)
     Kl_inv, Kr_inv = np.linalg.inv(cal.Kl), np.linalg.inv(cal.Kr)

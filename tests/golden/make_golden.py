@@ -1,0 +1,35 @@
+"""Generates the committed golden fixtures.  Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+* toed_ref_small.npz   : a 200x152 synthetic image and the edges produced by the UNMODIFIED reference detector
+                         (oracle/_ref/libtoed_ref.so = /root/reference/src/toed/cpu_toed.cpp compiled in place).
+* stereo_small.npz     : a 320x200 KITTI-calibrated synthetic pair, its reference TOED edges (both views) and
+                         the oracle's stage counts + final mates (regression pin of the restatement itself).
+"""
+import os, sys
+import numpy as np
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle
+from edge_based_visual_odometry_b200 import synth
+
+assert oracle.have_ref(), "needs oracle/_ref/libtoed_ref.so (build container only)"
+
+cal = synth.kitti_calib(200, 152)
+L, _ = synth.stereo_pair(cal, 7, density=1.5)
+e, nt, _, _ = oracle.toed_reference(L)
+np.savez_compressed(os.path.join(HERE, "toed_ref_small.npz"), image=L, edges=e, n_total=nt)
+print("toed_ref_small", L.shape, len(e), nt)
+
+cal = synth.kitti_calib(320, 200)
+L, R = synth.stereo_pair(cal, 11, density=1.5)
+eL, ntL, _, _ = oracle.toed_reference(L)
+eR, ntR, _, _ = oracle.toed_reference(R)
+F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+res = oracle.stereo(L, R, eL, eR, F21)
+counts = {k: int(v["off"][-1]) for k, v in res.stages.items()}
+np.savez_compressed(os.path.join(HERE, "stereo_small.npz"), L=L, R=R, eL=eL, eR=eR, F21=F21,
+                    stage_names=np.array(list(counts.keys())), stage_totals=np.array(list(counts.values())),
+                    mate_left=res.mate_left, mate_right=res.mate_right, mate_score=res.mate_score)
+print("stereo_small", len(eL), len(eR), counts, len(res.mate_left))

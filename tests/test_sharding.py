@@ -1,0 +1,54 @@
+"""CPU, world_size 2, gloo: the frame-sharding host logic and the final result gather (the only exchange step)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from edge_based_visual_odometry_b200 import _lib, sharding
+
+
+def test_shard_ranges_cover_all_frames_once():
+    for F in (1, 2, 7, 1000):
+        for G in (1, 2, 4, 8):
+            seen = []
+            for r in range(G):
+                lo, hi = sharding.shard_range(F, G, r)
+                seen += list(range(lo, hi))
+            assert seen == list(range(F))
+
+
+def _worker(rank, world, port, F, cap, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(F, world, rank)
+    m = np.zeros((hi - lo, cap), _lib.MATE_DTYPE)
+    c = np.zeros(hi - lo, np.int32)
+    for k, f in enumerate(range(lo, hi)):       # fake per-frame results that encode the global frame id
+        c[k] = (f % cap) + 1
+        m["left_index"][k, :c[k]] = f
+        m["score"][k, :c[k]] = f + 0.5
+    gm, gc = sharding.gather_mates(m, c, F, dist)
+    if rank == 0:
+        ok = all(gc[f] == (f % cap) + 1 and (gm["left_index"][f, :gc[f]] == f).all() and (gm["score"][f, :gc[f]] == f + 0.5).all()
+                 for f in range(F))
+        q.put(bool(ok) and gm.shape == (F, cap))
+    else:
+        assert gm is None
+    dist.destroy_process_group()
+
+
+def test_gather_mates_world2_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 7, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
