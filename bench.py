@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (cycled to fill the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gn-fp32", action="store_true", help="use the FP32 Gauss-Newton variant (not the parity default)")
+    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton arithmetic: 0 mixed (default), 1 FP64, 2 FP32")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -169,7 +169,7 @@ def main():
     n_mates = np.zeros(B, np.int32)
 
     prm = _lib.default_params()
-    prm.gn_fp32 = 1 if args.gn_fp32 else 0
+    prm.gn_mode = args.gn_mode
     ctx = _lib.Context(local_rank, W, H, max_batch=B, max_edges=65536, params=prm)
     calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))

@@ -44,7 +44,7 @@ class Params(C.Structure):
         "bnb_ncc", "bnb_sift", "sift_threshold", "location_perturbation", "epip_tangency_displ_thresh",
         "orient_perturbation", "cluster_dist_thresh", "cluster_orient_thresh_deg", "cluster_orient_gauss_sigma")] + [
         ("max_cluster_size", C.c_int32), ("gn_max_iter", C.c_int32), ("gn_tol", C.c_double), ("gn_huber_delta", C.c_double),
-        ("toed_mag_thresh", C.c_double), ("toed_border", C.c_int32), ("gn_fp32", C.c_int32)]
+        ("toed_mag_thresh", C.c_double), ("toed_border", C.c_int32), ("gn_mode", C.c_int32)]
 
 
 class Mate(C.Structure):

@@ -109,7 +109,7 @@ void set_devparams(ebvo_ctx* ctx)
     d.clus_orient_rad = q.cluster_orient_thresh_deg * (M_PI / 180.0);   // deg_to_rad, include/utility.h:293-297
     d.clus_sigma = q.cluster_orient_gauss_sigma; d.clus_max = q.max_cluster_size; d.gn_max_iter = q.gn_max_iter;
     d.gn_tol = q.gn_tol; d.gn_huber = q.gn_huber_delta; d.toed_mag_thresh = (float)q.toed_mag_thresh; d.toed_border = q.toed_border;
-    d.gn_fp32 = q.gn_fp32;
+    d.gn_mode = q.gn_mode;
 }
 
 // geometry-dependent fields of the device view
@@ -303,7 +303,7 @@ int ebvo_params_default(ebvo_params* p)
     p->ncc_thresh = 0.6; p->bnb_ncc = 0.9; p->bnb_sift = 0.4; p->sift_threshold = 500.0; p->location_perturbation = 0.4;
     p->epip_tangency_displ_thresh = 3.0; p->orient_perturbation = 0.174533; p->cluster_dist_thresh = 1.0;
     p->cluster_orient_thresh_deg = 20.0; p->cluster_orient_gauss_sigma = 2.0; p->max_cluster_size = 10; p->gn_max_iter = 20;
-    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->gn_fp32 = 0;
+    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->gn_mode = 0;
     return EBVO_OK;
 }
 
@@ -342,10 +342,12 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     CK(dalloc(ctx, &b.coords, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.ex, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.ey, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.eth, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.nE, (size_t)nImg)); CK(dalloc(ctx, &b.nTot, (size_t)nImg));
-    if (ctx->params.gn_fp32) CK(dalloc(ctx, &b.pk, b.gStride * B));
-    else CK(dalloc(ctx, &b.pk16, b.gStride * B));
+    if (ctx->params.gn_mode == 2) CK(dalloc(ctx, &b.pk, b.gStride * B));
+    else if (ctx->params.gn_mode == 1) CK(dalloc(ctx, &b.pk16, b.gStride * B));
+    else CK(dalloc(ctx, &b.pkh, b.gStride * B));
+    CK(dalloc(ctx, &b.npatch, (size_t)b.E * 98 * nImg)); CK(dalloc(ctx, &b.pflag, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.blk, (size_t)b.NB * B)); CK(dalloc(ctx, &b.pmax, (size_t)b.NB * B)); CK(dalloc(ctx, &b.smin, (size_t)b.NB * B));
-    CK(dalloc(ctx, &b.lines, (size_t)b.E * 3 * B));
+    CK(dalloc(ctx, &b.lines, (size_t)b.E * 8 * B));
     CK(dalloc(ctx, &b.cstart, (size_t)b.E * B)); CK(dalloc(ctx, &b.ccount, (size_t)b.E * B));
     CK(dalloc(ctx, &b.poolUsed, (size_t)B));
     CK(dalloc(ctx, &b.c_ridx, (size_t)b.P * B));
@@ -662,18 +664,24 @@ int ebvo_sobel(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, floa
     if (rc) return rc;
     if ((rc = upload_image(ctx, ctx->d_raw, 1, img, stride))) return rc;   // slot 1 = right view of frame 0
     launch_sobel(ctx->b, 1, ctx->st, nullptr);
+    const size_t npx = (size_t)w * h;
     if (ctx->b.pk) {
-        std::vector<float> pk((size_t)w * h * 4);
+        std::vector<float> pk(npx * 4);
         CK(cudaMemcpyAsync(pk.data(), ctx->b.pk, pk.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
-        for (size_t k = 0; k < (size_t)w * h; ++k) { gx[k] = pk[4 * k + 1]; gy[k] = pk[4 * k + 2]; }
+        for (size_t k = 0; k < npx; ++k) { gx[k] = pk[4 * k + 1]; gy[k] = pk[4 * k + 2]; }
     } else {
-        std::vector<uint32_t> pk((size_t)w * h * 2);
-        CK(cudaMemcpyAsync(pk.data(), ctx->b.pk16, pk.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+        std::vector<uint32_t> pk(npx * 2);
+        CK(cudaMemcpyAsync(pk.data(), ctx->b.pk16 ? ctx->b.pk16 : ctx->b.pkh, pk.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
-        for (size_t k = 0; k < (size_t)w * h; ++k) {
-            gx[k] = (float)(int16_t)(pk[2 * k] >> 16) * 0.125f;
-            gy[k] = (float)(int16_t)(pk[2 * k + 1] & 0xffff) * 0.125f;
+        auto h2f = [](uint16_t hbits) {   // IEEE half -> float (values here are k/8, |k| <= 1020: normal or zero)
+            const uint32_t s = (hbits >> 15) & 1, e = (hbits >> 10) & 31, mnt = hbits & 1023;
+            if (e == 0) return (s ? -1.f : 1.f) * (float)mnt * (1.f / 16777216.f);
+            return (s ? -1.f : 1.f) * std::ldexp(1.f + (float)mnt / 1024.f, (int)e - 15);
+        };
+        for (size_t k = 0; k < npx; ++k) {
+            if (ctx->b.pk16) { gx[k] = (float)(int16_t)(pk[2 * k] >> 16) * 0.125f; gy[k] = (float)(int16_t)(pk[2 * k + 1] & 0xffff) * 0.125f; }
+            else { gx[k] = h2f((uint16_t)(pk[2 * k + 1] & 0xffff)); gy[k] = h2f((uint16_t)(pk[2 * k + 1] >> 16)); }
         }
     }
     return EBVO_OK;

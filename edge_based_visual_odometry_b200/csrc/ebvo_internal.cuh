@@ -44,9 +44,14 @@ struct DevBatch {
     uint32_t* coords;                     // [img][E] packed (i<<16 | j)
     double *ex, *ey, *eth;                // [img][E]
     int *nE, *nTot;                       // [img]
-    float4* pk; uint2* pk16; size_t gStride;  // pk16: {I, 8gx, 8gy} as int16 for the default (FP64) GN kernel;           // packed {I, gx, gy, 0} of the undistorted RIGHT images, [frame][H*W] (Sobel 3x3 / 8)
+    // right-view image packed with its Sobel/8 gradients, one of (per ebvo_params.gn_mode), [frame][H*W]:
+    uint2* pkh;    // {u16 I, half gx, half gy, 0}   default mixed-precision GN kernel
+    uint2* pk16;   // {I, 8gx, 8gy} as int16           FP64 GN kernel
+    float4* pk;    // {I, gx, gy, 0} floats            FP32 GN kernel
+    size_t gStride;
+    float* npatch; uint8_t* pflag;        // normalised NCC patches [img][E][98] + flat flags [img][E]           // packed {I, gx, gy, 0} of the undistorted RIGHT images, [frame][H*W] (Sobel 3x3 / 8)
     float4* blk; float* pmax; float* smin;  // right-edge block bounds [frame][NB]
-    double* lines;                        // [frame][E][3]
+    double* lines;                        // [frame][E][8]: a, b, c, dirx, diry, sin(thL), cos(thL), pad
     int *cstart, *ccount;                 // [frame][E]
     int* poolUsed;                        // [frame]
     int* c_ridx; double *c_x, *c_y, *c_th, *c_score, *c_conf;  // [frame][P]
@@ -67,7 +72,7 @@ struct DevParams {
     int clus_max, gn_max_iter;
     double gn_tol, gn_huber;
     float toed_mag_thresh; int toed_border;
-    int gn_fp32;
+    int gn_mode;   // 0 mixed (default), 1 FP64, 2 FP32
 };
 
 // kernel launchers (defined in toed.cu / match.cu); all asynchronous on `st`

@@ -7,20 +7,25 @@
 //   bounds_kernel(+scan)   index over the right edges (replaces the brute-force scan of :91-109)
 //   gate_kernel            S1 epipolar distance, S2 disparity, S3 orientation   :381-419, 534-553, 863-915
 //   sift_gate_kernel       S4 with injected descriptors           :691-787
-//   ncc_bnb_kernel         S5/S6 patches + NCC gate, S7 (and S7') :555-616, 789-862 ; utility.cpp:82-212
-//   gn_kernel              S8 epipolar shift, S9 Gauss-Newton     :26-89, 967-1037, 1159-1358
-//   cluster_kernel         S10 second shift + EdgeClusterer, S11 NCC, S12 arg-max   :1483, EdgeClusterer.cpp:119-302, :916-965
+//   patch_kernel           S5 oriented 7x7 patches of every edge, normalised once per edge   utility.cpp:82-212, 165-178
+//   ncc_bnb_kernel         S6 NCC gate, S7 (and S7') best-nearly-best   :555-616, 789-862
+//   shift_kernel           S8 epipolar shift (and the second shift of S10)   :26-89, 967-1037
+//   gn*_kernel             S9 Gauss-Newton along the epipolar line   :1159-1358
+//   cluster_kernel         S10 EdgeClusterer                      :1483, EdgeClusterer.cpp:119-302
+//   ncc2_best_kernel       S11 NCC on the cluster centres, S12 arg-max   :1500, :916-965
 //   compact_kernel         S13 remove_empty_clusters + finalize   :1543-1653
 // Candidate lists live in a per-frame pool (CSR with explicit start/count per left edge); every list keeps
 // the reference's order (ascending right-edge index, then the re-orderings the reference applies).
 #include "ebvo_internal.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 
 namespace ebvo {
 
 constexpr int MAXC = 128;     // max candidates per left edge held in shared memory by the warp kernels
 constexpr int WPB = 4;        // warps per block in the warp-per-item kernels
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int GEO = 8;        // doubles per left edge in DevBatch::lines: a, b, c, dirx, diry, sin(thL), cos(thL), pad
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -55,6 +60,10 @@ __global__ void sobel_kernel(DevBatch b)
     float gy = (at(yp, xm) - at(ym, xm)) * 0.125f + (at(yp, x) - at(ym, x)) * 0.25f + (at(yp, xp) - at(ym, xp)) * 0.125f;
     const size_t o = (size_t)f * b.gStride + (size_t)y * b.W + x;
     if (b.pk) b.pk[o] = make_float4(at(y, x), gx, gy, 0.f);
+    if (b.pkh) {    // {u16 I, half gx, half gy}: Sobel/8 values are k/8 with |k| <= 1020, exact in fp16; 8 bytes per pixel
+        const __half2 hg = __floats2half2_rn(gx, gy);
+        b.pkh[o] = make_uint2((uint32_t)(int)at(y, x), *reinterpret_cast<const uint32_t*>(&hg));
+    }
     if (b.pk16) {   // {I, 8*gx, 8*gy} as exact 16-bit integers (|8*g| <= 1020): 8 bytes per pixel
         const int i8 = (int)at(y, x), gx8 = (int)(gx * 8.f), gy8 = (int)(gy * 8.f);
         b.pk16[o] = make_uint2((uint32_t)i8 | ((uint32_t)(gx8 & 0xffff) << 16), (uint32_t)(gy8 & 0xffff));
@@ -211,9 +220,14 @@ __global__ void __launch_bounds__(32 * WPB) gate_kernel(DevBatch b, DevParams p,
     for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
         GateCtx g;
         gate_setup(g, b, p, F, f, i, 2);
-        if (lane == 0) {
-            double* l = b.lines + ((size_t)f * b.E + i) * 3;
-            l[0] = g.a; l[1] = g.b; l[2] = g.c;
+        if (lane == 0) {   // per-left-edge geometry used by every later stage
+            double* l = b.lines + ((size_t)f * b.E + i) * GEO;
+            double dirx = -g.b, diry = g.a;                         // Stereo_Matches.cpp:1330-1335
+            const double nn = sqrt(dirx * dirx + diry * diry);
+            dirx /= nn; diry /= nn;
+            double sn, cs;
+            sincos(g.thL, &sn, &cs);
+            l[0] = g.a; l[1] = g.b; l[2] = g.c; l[3] = dirx; l[4] = diry; l[5] = sn; l[6] = cs; l[7] = 0.0;
         }
         int* buf = s_buf[w];
         int n = gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { if (rank < 64) buf[rank] = e; });
@@ -382,6 +396,42 @@ __device__ __forceinline__ void dump_put(const DumpBuf& d, int o, int ridx, doub
     d.ridx[o] = ridx; d.x[o] = x; d.y[o] = y; d.th[o] = th; d.score[o] = score;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// S5: the "+"/"-" patches of EVERY edge of both views, sampled from the RAW image (Stereo_Matches.cpp:562-563)
+// and normalised once.  A right edge is a candidate of ~5 left edges; the reference re-samples it for each pair.
+// Layout: npatch[img][e][0..48] = "+" cells, [49..97] = "-" cells (zero-mean, unit-norm floats); pflag bit0/bit1 =
+// flat "+"/"-" patch (sum of squares < 1e-10 => similarity -1).  One warp per edge.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * WPB) patch_kernel(DevBatch b, DevParams p)
+{
+    const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = b.nE[img];
+    const uint8_t* I = b.raw + (size_t)img * b.imgStride;
+    const double *ex = b.ex + (size_t)img * b.E, *ey = b.ey + (size_t)img * b.E, *eth = b.eth + (size_t)img * b.E;
+    float* np_ = b.npatch + (size_t)img * b.E * 98;
+    uint8_t* pf = b.pflag + (size_t)img * b.E;
+    for (int e = blockIdx.x * WPB + (threadIdx.x >> 5); e < n; e += gridDim.x * WPB) {
+        float vp[2], vm[2];
+        Patches P;
+        raw_patches(I, b.pitch, b.W, b.H, ex[e], ey[e], eth[e], p.shift_mag, lane, vp, vm);
+        normalise_patches(vp, vm, lane, P);
+        float* o = np_ + (size_t)e * 98;
+        o[lane] = P.p[0]; o[49 + lane] = P.m[0];
+        if (lane + 32 < 49) { o[lane + 32] = P.p[1]; o[49 + lane + 32] = P.m[1]; }
+        if (lane == 0) pf[e] = (P.flatP ? 1 : 0) | (P.flatM ? 2 : 0);
+    }
+}
+
+__device__ __forceinline__ void load_patches(const float* __restrict__ np_, const uint8_t* __restrict__ pf, int e, int lane, Patches& P)
+{
+    const float* o = np_ + (size_t)e * 98;
+    const bool has1 = lane + 32 < 49;
+    P.p[0] = o[lane]; P.m[0] = o[49 + lane];
+    P.p[1] = has1 ? o[lane + 32] : 0.f; P.m[1] = has1 ? o[49 + lane + 32] : 0.f;
+    const int fl = pf[e];
+    P.flatP = fl & 1; P.flatM = fl & 2;
+}
+
 __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams p, int use_sift)
 {
     __shared__ double s_sc[WPB][MAXC];
@@ -394,9 +444,8 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int imgL = 2 * f, imgR = 2 * f + 1;
     const int nL = b.nE[imgL];
-    const uint8_t* IL = b.raw + (size_t)imgL * b.imgStride;   // NCC uses the RAW images (Stereo_Matches.cpp:562-563)
-    const uint8_t* IR = b.raw + (size_t)imgR * b.imgStride;
-    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
+    const float *npL = b.npatch + (size_t)imgL * b.E * 98, *npR = b.npatch + (size_t)imgR * b.E * 98;
+    const uint8_t *pfL = b.pflag + (size_t)imgL * b.E, *pfR = b.pflag + (size_t)imgR * b.E;
     const double *exR = b.ex + (size_t)imgR * b.E, *eyR = b.ey + (size_t)imgR * b.E, *ethR = b.eth + (size_t)imgR * b.E;
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
@@ -410,15 +459,12 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
         const int n = ccount[i];
         if (n == 0) { if (dumps && lane == 0) { b.dump[DUMP_S6].n[i] = 0; b.dump[DUMP_S7].n[i] = 0; } continue; }
         const int st = cstart[i];
-        float vp[2], vm[2];
         Patches PL, PR;
-        raw_patches(IL, b.pitch, b.W, b.H, exL[i], eyL[i], ethL[i], p.shift_mag, lane, vp, vm);
-        normalise_patches(vp, vm, lane, PL);
+        load_patches(npL, pfL, i, lane, PL);
         int ns = 0;
         for (int j = 0; j < n; ++j) {
             const int r = c_ridx[st + j];
-            raw_patches(IR, b.pitch, b.W, b.H, exR[r], eyR[r], ethR[r], p.shift_mag, lane, vp, vm);
-            normalise_patches(vp, vm, lane, PR);
+            load_patches(npR, pfR, r, lane, PR);
             const double s = ncc_score(PL, PR);
             if (s > p.ncc_thresh) {      // NCC_THRESH gate, :597
                 if (ns < MAXC) {
@@ -507,7 +553,10 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate_kernel(DevBatch b, DevPara
 }
 
 // ------------------------------------------------------------------------------------------------------
-// S8 epipolar shift (Stereo_Matches.cpp:26-89; utility.cpp:46-74)
+// S8 epipolar shift (Stereo_Matches.cpp:26-89; utility.cpp:46-74).  One THREAD per live pool slot: scalar FP64
+// trigonometry is 32x cheaper here than replicated across the lanes of a warp-per-candidate kernel.
+// which = 0: first shift (S8, positions + orientation written back, right-edge index dropped as at :993-997);
+// which = 1: second shift at the head of S10 (Stereo_Matches.cpp:1483 -> :981-998).
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double tangential(double a, double b, double c, double x, double y, double th, double& xi, double& yi)
 {
@@ -535,9 +584,36 @@ __device__ __forceinline__ void shift_to_line(double a, double b, double c, cons
     if (tangential(a, b, c, x, y, t2, xi, yi) < p.tang_displ) { x = xi; y = yi; th = t2; }
 }
 
-// include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped sampler.
-// Coordinates are split in FP64 into an integer cell and an FP32 fraction; the four-corner blend runs in FP32
-// (the reference blends in FP64 and rounds the result to float: same 2^-24 relative resolution).
+__global__ void __launch_bounds__(128) shift_kernel(DevBatch b, DevParams p, int which)
+{
+    const int f = blockIdx.y;
+    const int used = min(b.poolUsed[f], b.P);
+    const bool dumps = b.dumps && f == 0 && which == 0;
+    const int* c_owner = b.c_owner + (size_t)f * b.P;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    for (int q = blockIdx.x * 128 + threadIdx.x; q < used; q += gridDim.x * 128) {
+        const int i = c_owner[q];
+        if (i < 0) continue;
+        const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+        double x = c_x[q], y = c_y[q], th = c_th[q];
+        shift_to_line(ln[0], ln[1], ln[2], p, x, y, th);
+        c_x[q] = x; c_y[q] = y; c_th[q] = th;
+        if (which == 0) b.c_ridx[(size_t)f * b.P + q] = -1;
+        if (dumps) dump_put(b.dump[DUMP_S8], q, -1, x, y, th, b.c_score[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  One warp per live pool slot.
+// Lane l owns samples s = l + 32 m (m < 4, s < 98): s < 49 -> "+" patch cell s, else "-" patch cell s - 49
+// (cell (i,j) = (t/7-3, t%7-3)).  Three arithmetic variants share this structure:
+//   gn_mixed_kernel (default)  image channel + residuals exactly as the reference (FP64 blend rounded to float,
+//                              FP64 residual and sums); the two Sobel channels, Huber weights and per-lane partial
+//                              products in FP32 (they only scale the step: measured effect < 1e-6 px)
+//   gn64_kernel                everything as the reference (FP64), for strict comparisons
+//   gn32_kernel                everything FP32: fastest, 0.02 % of the mates move by > 1e-3 px (non-converging GN)
+// ------------------------------------------------------------------------------------------------------
+// include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped sampler, FP32 blend
 __device__ __forceinline__ void cell_of(double x, int n, int& x0, int& x1, float& a)
 {
     x = fmin(fmax(x, 0.0), (double)n - 1.0);
@@ -555,21 +631,244 @@ __device__ __forceinline__ float sample_u8(const uint8_t* __restrict__ I, int pi
     const float v01 = (float)__ldg(I + (size_t)y1 * pitch + x0), v11 = (float)__ldg(I + (size_t)y1 * pitch + x1);
     return (1.f - a) * (1.f - bb) * v00 + a * (1.f - bb) * v10 + (1.f - a) * bb * v01 + a * bb * v11;
 }
+// the same sampler with the FP64 blend of the reference, result rounded to float (utility.h:171)
+__device__ __forceinline__ double sample_u8_exact(const uint8_t* __restrict__ I, int pitch, int W, int H, double x, double y)
+{
+    x = fmin(fmax(x, 0.0), (double)W - 1.0); y = fmin(fmax(y, 0.0), (double)H - 1.0);
+    const int x0 = __double2int_rd(x), y0 = __double2int_rd(y);
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const double a = x - (double)x0, bb = y - (double)y0;
+    const double v00 = (double)__ldg(I + (size_t)y0 * pitch + x0), v10 = (double)__ldg(I + (size_t)y0 * pitch + x1);
+    const double v01 = (double)__ldg(I + (size_t)y1 * pitch + x0), v11 = (double)__ldg(I + (size_t)y1 * pitch + x1);
+    return (double)(float)((1 - a) * (1 - bb) * v00 + a * (1 - bb) * v10 + (1 - a) * bb * v01 + a * bb * v11);
+}
 
-// S8 + S9.  One warp per live pool slot (candidate).  Lane l owns samples s = l + 32 m (m < 4, s < 98):
-// s < 49 -> "+" patch cell s, else "-" patch cell s - 49 (cell (i,j) = (t/7-3, t%7-3)).
+// (double)(float)v without conversion instructions: Veltkamp split keeping 24 significant bits (round to nearest).
+// Valid for |v| in the float normal range, which holds for 8-bit image samples and their Sobel responses.
+__device__ __forceinline__ double round_to_float(double v)
+{
+    const double c = __dmul_rn(v, 536870913.0);   // 2^29 + 1
+    return __dsub_rn(c, __dsub_rn(c, v));
+}
+// exact integer -> double without conversion instructions (2^52 magic); fields of the packed right-view pixel
+__device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x43300000, (int)(u.x & 0xffffu)) - 4503599627370496.0; }
+__device__ __forceinline__ double pk_gx(uint2 u) { return __hiloint2double(0x43300000, (((int)u.x) >> 16) ^ 0x80000000) - 4503601774854144.0; }
+__device__ __forceinline__ double pk_gy(uint2 u) { return __hiloint2double(0x43300000, ((int)(u.y << 16) >> 16) ^ 0x80000000) - 4503601774854144.0; }
+
+// floor + fraction of a clamped coordinate without conversions (utility.h:161-166): round-down add of 1.5*2^52 puts
+// floor(x) in the low word; the clamp to [0, n-1] is applied to the (cell, fraction) pair.
+__device__ __forceinline__ void cell_magic(double x, int n, int& x0, double& a)
+{
+    const double t = __dadd_rd(x, 6755399441055744.0);
+    x0 = __double2loint(t);
+    a = x - (t - 6755399441055744.0);
+    if (x0 < 0) { x0 = 0; a = 0.0; } else if (x0 >= n - 1) { x0 = n - 1; a = 0.0; }
+}
+
+struct GnSetup {
+    double dirx, diry, xr, yr;
+    double Bx[4], By[4], Lc[4];
+};
+
+// common prologue: geometry, per-sample base coordinates of the right patches, centred left samples
+__device__ __forceinline__ void gn_setup(const DevBatch& b, int f, int i, int q, int lane, GnSetup& g)
+{
+    const int imgL = 2 * f;
+    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
+    const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+    g.dirx = ln[3]; g.diry = ln[4];
+    const double st_ = ln[5], ct_ = ln[6];
+    const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
+    const double side = 7 / 2.0 + 1.0;                         // :1171
+    const double nxs = -st_ * side, nys = ct_ * side;          // n * side, n = (-t.y, t.x) (:1169-1170)
+    g.xr = b.c_x[(size_t)f * b.P + q]; g.yr = b.c_y[(size_t)f * b.P + q];
+    double sumP = 0, sumM = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int s = lane + 32 * m;
+        const bool neg = s >= 49;
+        const int t = s - (neg ? 49 : 0);
+        const int ii = t / 7 - 3, jj = t % 7 - 3;
+        const double cx = neg ? -nxs : nxs, cy = neg ? -nys : nys;        // +-n*side
+        const double rx = ct_ * ii - st_ * jj, ry = st_ * ii + ct_ * jj;  // rotated cell (utility.h:154)
+        g.Bx[m] = (g.xr + cx) + rx; g.By[m] = (g.yr + cy) + ry;           // right: + alpha*dir per iteration (:1203-1204)
+        g.Lc[m] = 0.0;
+        if (s < 98) {
+            g.Lc[m] = sample_u8_exact(IL, b.pitch, b.W, b.H, (xL + cx) + rx, (yL + cy) + ry);
+            if (neg) sumM += g.Lc[m]; else sumP += g.Lc[m];
+        }
+    }
+    warp_sum2(sumP, sumM);
+    const double mLp = sumP / 49.0, mLm = sumM / 49.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { const int s = lane + 32 * m; if (s < 98) g.Lc[m] -= (s >= 49) ? mLm : mLp; }
+}
+
+__device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const GnSetup& g, double alpha, double score, double conf)
+{
+    const size_t o = (size_t)f * b.P + q;
+    b.c_x[o] = g.xr + alpha * g.dirx;          // :1350-1352 (moved regardless of validity)
+    b.c_y[o] = g.yr + alpha * g.diry;
+    b.c_score[o] = score; b.c_conf[o] = conf;
+}
+
+__global__ void __launch_bounds__(32 * WPB, 6) gn_mixed_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy, 0}
+    const int* c_owner = b.c_owner + (size_t)f * b.P;
+    const int used = min(b.poolUsed[f], b.P);
+    const int W = b.W, H = b.H;
+    const float huber = (float)p.gn_huber;
+    unsigned long long npairs = 0, niters = 0;
+    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
+        const int i = c_owner[q];
+        if (i < 0) continue;
+        GnSetup g;
+        gn_setup(b, f, i, q, lane, g);
+        const float fdx = (float)g.dirx, fdy = (float)g.diry;
+        double alpha = 0.0, score = 0.0, conf = 0.0;
+        for (int it = 0; it < p.gn_max_iter; ++it) {
+            const double sx = alpha * g.dirx, sy = alpha * g.diry;
+            double vi[4];
+            float vg[4];
+            double sRp = 0, sRm = 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                vi[m] = 0.0; vg[m] = 0.f;
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    int x0, y0;
+                    double a, bb;
+                    cell_magic(g.Bx[m] + sx, W, x0, a);
+                    cell_magic(g.By[m] + sy, H, y0, bb);
+                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
+                    const uint2* c00 = PK + (y0 * W + x0);
+                    const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
+                    // image channel: FP64 blend rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172)
+                    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
+                    vi[m] = round_to_float(w00 * pk_i(u00) + w10 * pk_i(u10) + w01 * pk_i(u01) + w11 * pk_i(u11));
+                    // Sobel channels: FP32 blend of the exact half-precision samples
+                    const float af = (float)a, bf = (float)bb;
+                    const float f00 = (1.f - af) * (1.f - bf), f10 = af * (1.f - bf), f01 = (1.f - af) * bf, f11 = af * bf;
+                    const float2 g00 = __half22float2(*reinterpret_cast<const __half2*>(&u00.y)), g10 = __half22float2(*reinterpret_cast<const __half2*>(&u10.y));
+                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&u01.y)), g11 = __half22float2(*reinterpret_cast<const __half2*>(&u11.y));
+                    const float gx = f00 * g00.x + f10 * g10.x + f01 * g01.x + f11 * g11.x;
+                    const float gy = f00 * g00.y + f10 * g10.y + f01 * g01.y + f11 * g11.y;
+                    vg[m] = -gx * fdx + gy * fdy;                                    // :1240
+                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
+                }
+            }
+            warp_sum2(sRp, sRm);
+            const double mRp = sRp / 49.0, mRm = sRm / 49.0;
+            float Hf = 0.f, bf_ = 0.f, cf = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    const float r = (float)(g.Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp)));   // FP64 residual, then float
+                    const float ar = fabsf(r);
+                    const float wgt = (ar <= huber) ? 1.f : __fdividef(huber, ar);
+                    const float wg = wgt * vg[m];
+                    Hf = fmaf(wg, vg[m], Hf); bf_ = fmaf(wg, r, bf_); cf = fmaf(wgt * r, r, cf);
+                }
+            }
+            double Hh = (double)Hf, bb_ = (double)bf_, cost = (double)cf;   // per-lane partials (<= 4 terms) -> FP64 reduction
+            warp_sum3(Hh, bb_, cost);
+            ++niters;
+            if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+            const double delta = -bb_ / Hh;
+            alpha += delta;
+            if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+                const double rms = sqrt(cost / 98.0);
+                score = rms; conf = exp(-rms / p.gn_huber);
+                break;
+            }
+        }
+        ++npairs;
+        if (lane == 0) gn_store(b, f, q, g, alpha, score, conf);
+    }
+    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
+}
+
+__global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const uint2* __restrict__ PK16 = b.pk16 + (size_t)f * b.gStride;   // right view: {I, 8*Sobel gx, 8*Sobel gy} as int16
+    const int* c_owner = b.c_owner + (size_t)f * b.P;
+    const int used = min(b.poolUsed[f], b.P);
+    const int W = b.W, H = b.H;
+    unsigned long long npairs = 0, niters = 0;
+    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
+        const int i = c_owner[q];
+        if (i < 0) continue;
+        GnSetup g;
+        gn_setup(b, f, i, q, lane, g);
+        double alpha = 0.0, score = 0.0, conf = 0.0;
+        for (int it = 0; it < p.gn_max_iter; ++it) {
+            const double sx = alpha * g.dirx, sy = alpha * g.diry;
+            double vi[4], vg[4];
+            double sRp = 0, sRm = 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                vi[m] = 0.0; vg[m] = 0.0;
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    int x0, y0;
+                    double a, bb;
+                    cell_magic(g.Bx[m] + sx, W, x0, a);
+                    cell_magic(g.By[m] + sy, H, y0, bb);
+                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
+                    const uint2* c00 = PK16 + (y0 * W + x0);
+                    const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
+                    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
+                    // FP64 blend, then rounded to float as util_bilinear_Sample_F returns float (Veltkamp split: 24-bit RN)
+                    const double bi = w00 * pk_i(u00) + w10 * pk_i(u10) + w01 * pk_i(u01) + w11 * pk_i(u11);
+                    const double bgx = w00 * pk_gx(u00) + w10 * pk_gx(u10) + w01 * pk_gx(u01) + w11 * pk_gx(u11);   // 8 * gx
+                    const double bgy = w00 * pk_gy(u00) + w10 * pk_gy(u10) + w01 * pk_gy(u01) + w11 * pk_gy(u11);   // 8 * gy
+                    vi[m] = round_to_float(bi);
+                    vg[m] = (-round_to_float(bgx) * g.dirx + round_to_float(bgy) * g.diry) * 0.125;   // :1240 (x 1/8: exact)
+                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
+                }
+            }
+            warp_sum2(sRp, sRm);
+            const double mRp = sRp / 49.0, mRm = sRm / 49.0;
+            double Hh = 0, bb_ = 0, cost = 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int s = lane + 32 * m;
+                if (s < 98) {
+                    const double r = g.Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp));
+                    const double gg = vg[m];
+                    const double ar = fabs(r);
+                    const double wgt = (ar <= p.gn_huber) ? 1.0 : p.gn_huber / ar;
+                    Hh += wgt * gg * gg; bb_ += wgt * gg * r; cost += wgt * r * r;
+                }
+            }
+            warp_sum3(Hh, bb_, cost);
+            ++niters;
+            if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+            const double delta = -bb_ / Hh;
+            alpha += delta;
+            if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+                const double rms = sqrt(cost / 98.0);
+                score = rms; conf = exp(-rms / p.gn_huber);
+                break;
+            }
+        }
+        ++npairs;
+        if (lane == 0) gn_store(b, f, q, g, alpha, score, conf);
+    }
+    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
+}
+
 __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams p)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int imgL = 2 * f;
-    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
+    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;
     const float4* __restrict__ PK = b.pk + (size_t)f * b.gStride;   // right view: {I, Sobel gx, Sobel gy}
-    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
-    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
-    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
-    int* c_ridx = b.c_ridx + (size_t)f * b.P;
     const int* c_owner = b.c_owner + (size_t)f * b.P;
-    const bool dumps = b.dumps && f == 0;
     const int used = min(b.poolUsed[f], b.P);
     const int W = b.W, H = b.H;
     const float huber = (float)p.gn_huber, tol = (float)p.gn_tol;
@@ -577,22 +876,13 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
     for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
         const int i = c_owner[q];
         if (i < 0) continue;
-        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
-        const double la = ln[0], lb = ln[1], lc = ln[2];
-        double dirx = -lb, diry = la;                         // :1330-1335
-        { const double nn = sqrt(dirx * dirx + diry * diry); dirx /= nn; diry /= nn; }
-        const double xL = exL[i], yL = eyL[i], thL = ethL[i];
-        double st_, ct_;
-        sincos(thL, &st_, &ct_);
-        const double side = 7 / 2.0 + 1.0;                    // :1171
-        const double nxs = -st_ * side, nys = ct_ * side;     // n * side, n = (-t.y, t.x) (:1169-1170)
-        double xr = c_x[q], yr = c_y[q], thr = c_th[q];
-        shift_to_line(la, lb, lc, p, xr, yr, thr);            // S8
-        if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], q, -1, xr, yr, thr, c_score[q]);
-
-        // Per-sample coordinates.  Left: FP64 (fixed).  Right: FP32 offsets from the integer anchor (ax, ay) of the
-        // candidate; the per-iteration shift alpha*dir is added in FP32 (offsets stay below ~32 px, so the sample
-        // position keeps ~1e-6 px resolution) and the pixel cell is recovered as anchor + floor(offset).
+        const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+        const double dirx = ln[3], diry = ln[4], st_ = ln[5], ct_ = ln[6];
+        const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
+        const double side = 7 / 2.0 + 1.0;
+        const double nxs = -st_ * side, nys = ct_ * side;
+        const double xr = b.c_x[(size_t)f * b.P + q], yr = b.c_y[(size_t)f * b.P + q];
+        // Right samples: FP32 offsets from the integer anchor (ax, ay) of the candidate; alpha*dir added in FP32
         const int ax = __double2int_rd(xr), ay = __double2int_rd(yr);
         const float fxr = (float)(xr - (double)ax), fyr = (float)(yr - (double)ay);
         float ox[4], oy[4], Lc[4];
@@ -603,7 +893,7 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
             const bool neg = s >= 49;
             const int t = s - (neg ? 49 : 0);
             const int ii = t / 7 - 3, jj = t % 7 - 3;
-            const double dox = (neg ? -nxs : nxs) + (ct_ * ii - st_ * jj);   // +-n*side + rotated cell (utility.h:154)
+            const double dox = (neg ? -nxs : nxs) + (ct_ * ii - st_ * jj);
             const double doy = (neg ? -nys : nys) + (st_ * ii + ct_ * jj);
             ox[m] = fxr + (float)dox; oy[m] = fyr + (float)doy;
             Lc[m] = 0.f;
@@ -630,22 +920,20 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
                 vi[m] = 0.f; vg[m] = 0.f;
                 const int s = lane + 32 * m;
                 if (s < 98) {
-                    // clamped cell (utility.h:161-166): x<0 -> (0, a=0); x>=w-1 -> (w-1, w-1, a=0)
                     const float xf = ox[m] + sx, yf = oy[m] + sy;
                     const float flx = floorf(xf), fly = floorf(yf);
                     int x0 = ax + (int)flx, y0 = ay + (int)fly;
                     float a = xf - flx, bb = yf - fly;
                     if (x0 < 0) { x0 = 0; a = 0.f; } else if (x0 >= W - 1) { x0 = W - 1; a = 0.f; }
                     if (y0 < 0) { y0 = 0; bb = 0.f; } else if (y0 >= H - 1) { y0 = H - 1; bb = 0.f; }
-                    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
                     const float4* c00 = PK + (y0 * W + x0);
-                    const int dx1 = x1 - x0, dy1 = (y1 - y0) * W;
                     const float4 p00 = __ldg(c00), p10 = __ldg(c00 + dx1), p01 = __ldg(c00 + dy1), p11 = __ldg(c00 + dy1 + dx1);
                     const float w00 = (1.f - a) * (1.f - bb), w10 = a * (1.f - bb), w01 = (1.f - a) * bb, w11 = a * bb;
                     vi[m] = w00 * p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x;
                     const float gx = w00 * p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y;
                     const float gy = w00 * p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z;
-                    vg[m] = -gx * fdx + gy * fdy;                                   // :1240
+                    vg[m] = -gx * fdx + gy * fdy;
                     if (s >= 49) sRm += vi[m]; else sRp += vi[m];
                 }
             }
@@ -658,11 +946,11 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
                 const int s = lane + 32 * m;
                 if (s < 98) {
                     const float r = Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp));
-                    const float g = vg[m];
+                    const float gg = vg[m];
                     const float ar = fabsf(r);
                     const float wgt = (ar <= huber) ? 1.f : __fdividef(huber, ar);
-                    const float wg = wgt * g;
-                    Hh = fmaf(wg, g, Hh); bb_ = fmaf(wg, r, bb_); cost = fmaf(wgt * r, r, cost);
+                    const float wg = wgt * gg;
+                    Hh = fmaf(wg, gg, Hh); bb_ = fmaf(wg, r, bb_); cost = fmaf(wgt * r, r, cost);
                 }
             }
 #pragma unroll
@@ -670,7 +958,7 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
                 Hh += __shfl_xor_sync(FULL, Hh, o); bb_ += __shfl_xor_sync(FULL, bb_, o); cost += __shfl_xor_sync(FULL, cost, o);
             }
             ++niters;
-            if (Hh < 1e-8f) break;                          // :1253 (outputs stay at their initial values)
+            if (Hh < 1e-8f) break;
             const float delta = -bb_ / Hh;
             alpha += (double)delta;
             if (fabsf(delta) < tol || it == p.gn_max_iter - 1) {
@@ -681,163 +969,16 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
         }
         ++npairs;
         if (lane == 0) {
-            c_x[q] = xr + alpha * dirx;                    // :1350-1352 (moved regardless of validity)
-            c_y[q] = yr + alpha * diry;
-            c_th[q] = thr;
-            c_score[q] = (double)score; c_conf[q] = (double)conf;
-            c_ridx[q] = -1;                                // right-edge indices are dropped at S8 (:993-997)
-        }
-    }
-    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
-}
-
-// (double)(float)v without conversion instructions: Veltkamp split keeping 24 significant bits (round to nearest).
-// Valid for |v| in the float normal range, which holds for 8-bit image samples and their Sobel responses.
-__device__ __forceinline__ double round_to_float(double v)
-{
-    const double c = __dmul_rn(v, 536870913.0);   // 2^29 + 1
-    return __dsub_rn(c, __dsub_rn(c, v));
-}
-
-// exact integer -> double without conversion instructions (2^52 magic); fields of the packed right-view pixel
-__device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x43300000, (int)(u.x & 0xffffu)) - 4503599627370496.0; }
-__device__ __forceinline__ double pk_gx(uint2 u) { return __hiloint2double(0x43300000, (((int)u.x) >> 16) ^ 0x80000000) - 4503601774854144.0; }
-__device__ __forceinline__ double pk_gy(uint2 u) { return __hiloint2double(0x43300000, ((int)(u.y << 16) >> 16) ^ 0x80000000) - 4503601774854144.0; }
-
-// FP64 variant (default): reproduces the reference arithmetic (FP64 blend rounded to float, FP64 residuals and
-// sums) so that even slowly converging / oscillating Gauss-Newton sequences track the reference to ~1e-7 px.
-// gn32_kernel above is the opt-in FP32 variant (ebvo_params.gn_fp32): ~2x faster, but rounding differences are
-// amplified by non-converging sequences (about 0.02% of the mates move by more than 1e-3 px).
-__global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams p)
-{
-    const int f = blockIdx.y, lane = threadIdx.x & 31;
-    const int imgL = 2 * f;
-    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;   // GN uses the UNDISTORTED images (:1293-1294)
-    const uint2* __restrict__ PK16 = b.pk16 + (size_t)f * b.gStride;   // right view: {I, 8*Sobel gx, 8*Sobel gy} as int16
-    const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
-    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
-    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
-    int* c_ridx = b.c_ridx + (size_t)f * b.P;
-    const int* c_owner = b.c_owner + (size_t)f * b.P;
-    const bool dumps = b.dumps && f == 0;
-    const int used = min(b.poolUsed[f], b.P);
-    const int W = b.W, H = b.H;
-    unsigned long long npairs = 0, niters = 0;
-    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
-        const int i = c_owner[q];
-        if (i < 0) continue;
-        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
-        const double la = ln[0], lb = ln[1], lc = ln[2];
-        double dirx = -lb, diry = la;                         // :1330-1335
-        { const double nn = sqrt(dirx * dirx + diry * diry); dirx /= nn; diry /= nn; }
-        const double xL = exL[i], yL = eyL[i], thL = ethL[i];
-        double st_, ct_;
-        sincos(thL, &st_, &ct_);
-        const double side = 7 / 2.0 + 1.0;                    // :1171
-        const double nxs = -st_ * side, nys = ct_ * side;     // n * side, n = (-t.y, t.x) (:1169-1170)
-        double xr = c_x[q], yr = c_y[q], thr = c_th[q];
-        shift_to_line(la, lb, lc, p, xr, yr, thr);            // S8
-        if (dumps && lane == 0) dump_put(b.dump[DUMP_S8], q, -1, xr, yr, thr, c_score[q]);
-
-        double Bx[4], By[4], Lc[4];
-        double sumP = 0, sumM = 0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int s = lane + 32 * m;
-            const bool neg = s >= 49;
-            const int t = s - (neg ? 49 : 0);
-            const int ii = t / 7 - 3, jj = t % 7 - 3;
-            const double cx = neg ? -nxs : nxs, cy = neg ? -nys : nys;        // +-n*side
-            const double rx = ct_ * ii - st_ * jj, ry = st_ * ii + ct_ * jj;  // rotated cell (utility.h:154)
-            Bx[m] = (xr + cx) + rx; By[m] = (yr + cy) + ry;                   // right: + alpha*dir per iteration
-            Lc[m] = 0.0;
-            if (s < 98) {
-                // utility.h:159-172 on the left image: FP64 blend, float result
-                double x = fmin(fmax((xL + cx) + rx, 0.0), (double)W - 1.0), y = fmin(fmax((yL + cy) + ry, 0.0), (double)H - 1.0);
-                const int x0 = __double2int_rd(x), y0 = __double2int_rd(y);
-                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-                const double a = x - (double)x0, bb = y - (double)y0;
-                const double v00 = (double)__ldg(IL + (size_t)y0 * b.pitch + x0), v10 = (double)__ldg(IL + (size_t)y0 * b.pitch + x1);
-                const double v01 = (double)__ldg(IL + (size_t)y1 * b.pitch + x0), v11 = (double)__ldg(IL + (size_t)y1 * b.pitch + x1);
-                Lc[m] = (double)(float)((1 - a) * (1 - bb) * v00 + a * (1 - bb) * v10 + (1 - a) * bb * v01 + a * bb * v11);
-                if (neg) sumM += Lc[m]; else sumP += Lc[m];
-            }
-        }
-        warp_sum2(sumP, sumM);
-        const double mLp = sumP / 49.0, mLm = sumM / 49.0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) { const int s = lane + 32 * m; if (s < 98) Lc[m] -= (s >= 49) ? mLm : mLp; }
-
-        double alpha = 0.0, score = 0.0, conf = 0.0;
-        for (int it = 0; it < p.gn_max_iter; ++it) {
-            const double sx = alpha * dirx, sy = alpha * diry;
-            double vi[4], vg[4];
-            double sRp = 0, sRm = 0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                vi[m] = 0.0; vg[m] = 0.0;
-                const int s = lane + 32 * m;
-                if (s < 98) {
-                    // utility.h:161-166 without conversions: floor through a round-down add of 1.5*2^52 (the low word of
-                    // the sum is floor(x) in two's complement), clamps applied to the (cell, fraction) pair
-                    const double x = Bx[m] + sx, y = By[m] + sy;
-                    const double tx = __dadd_rd(x, 6755399441055744.0), ty = __dadd_rd(y, 6755399441055744.0);
-                    int x0 = __double2loint(tx), y0 = __double2loint(ty);
-                    double a = x - (tx - 6755399441055744.0), bb = y - (ty - 6755399441055744.0);
-                    if (x0 < 0) { x0 = 0; a = 0.0; } else if (x0 >= W - 1) { x0 = W - 1; a = 0.0; }
-                    if (y0 < 0) { y0 = 0; bb = 0.0; } else if (y0 >= H - 1) { y0 = H - 1; bb = 0.0; }
-                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
-                    const uint2* c00 = PK16 + (y0 * W + x0);
-                    const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
-                    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
-                    // FP64 blend, then rounded to float as util_bilinear_Sample_F returns float (Veltkamp split: 24-bit RN)
-                    const double bi = w00 * pk_i(u00) + w10 * pk_i(u10) + w01 * pk_i(u01) + w11 * pk_i(u11);
-                    const double bgx = w00 * pk_gx(u00) + w10 * pk_gx(u10) + w01 * pk_gx(u01) + w11 * pk_gx(u11);   // 8 * gx
-                    const double bgy = w00 * pk_gy(u00) + w10 * pk_gy(u10) + w01 * pk_gy(u01) + w11 * pk_gy(u11);   // 8 * gy
-                    vi[m] = round_to_float(bi);
-                    vg[m] = (-round_to_float(bgx) * dirx + round_to_float(bgy) * diry) * 0.125;   // :1240 (x 1/8: exact)
-                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
-                }
-            }
-            warp_sum2(sRp, sRm);
-            const double mRp = sRp / 49.0, mRm = sRm / 49.0;
-            double Hh = 0, bb_ = 0, cost = 0;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int s = lane + 32 * m;
-                if (s < 98) {
-                    const double r = Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp));
-                    const double g = vg[m];
-                    const double ar = fabs(r);
-                    const double wgt = (ar <= p.gn_huber) ? 1.0 : p.gn_huber / ar;
-                    Hh += wgt * g * g; bb_ += wgt * g * r; cost += wgt * r * r;
-                }
-            }
-            warp_sum3(Hh, bb_, cost);
-            ++niters;
-            if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
-            const double delta = -bb_ / Hh;
-            alpha += delta;
-            if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
-                const double rms = sqrt(cost / 98.0);
-                score = rms; conf = exp(-rms / p.gn_huber);
-                break;
-            }
-        }
-        ++npairs;
-        if (lane == 0) {
-            c_x[q] = xr + alpha * dirx;                    // :1350-1352 (moved regardless of validity)
-            c_y[q] = yr + alpha * diry;
-            c_th[q] = thr;
-            c_score[q] = score; c_conf[q] = conf;
-            c_ridx[q] = -1;                                // right-edge indices are dropped at S8 (:993-997)
+            const size_t o = (size_t)f * b.P + q;
+            b.c_x[o] = xr + alpha * dirx; b.c_y[o] = yr + alpha * diry;
+            b.c_score[o] = (double)score; b.c_conf[o] = (double)conf;
         }
     }
     if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// S10 second shift + EdgeClusterer, S11 NCC on the cluster centres, S12 arg-max.  One warp per left edge.
+// S10 EdgeClusterer, then S11 NCC on the cluster centres + S12 arg-max.  One warp per left edge.
 // ------------------------------------------------------------------------------------------------------
 // EdgeClusterer::performClustering (EdgeClusterer.cpp:119-302) on n <= MAXC warp-private candidates.
 // Returns the number of clusters; centres go to (ox, oy, oth)[0..ncl) in ascending-label order (the order of
@@ -923,10 +1064,38 @@ __global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams
     __shared__ double s_ox[WPB][MAXC], s_oy[WPB][MAXC], s_ot[WPB][MAXC];
     __shared__ int s_lab[WPB][MAXC];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[2 * f];
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    const bool dumps = b.dumps && f == 0;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        int n = ccount[i];
+        if (n == 0) { if (dumps && lane == 0) b.dump[DUMP_S10].n[i] = 0; continue; }
+        const int st = cstart[i];
+        if (n > MAXC) { if (lane == 0) atomicExch(b.errFlag, 4); n = MAXC; }
+        for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
+        __syncwarp();
+        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_ox[w], s_oy[w], s_ot[w]);
+        __syncwarp();
+        for (int k = lane; k < ncl; k += 32) {
+            c_x[st + k] = s_ox[w][k]; c_y[st + k] = s_oy[w][k]; c_th[st + k] = s_ot[w][k];
+            if (dumps) dump_put(b.dump[DUMP_S10], st + k, -1, s_ox[w][k], s_oy[w][k], s_ot[w][k], CUDART_NAN);
+        }
+        if (lane == 0) { ccount[i] = ncl; if (dumps) b.dump[DUMP_S10].n[i] = ncl; }
+        __syncwarp();
+    }
+}
+
+// S11 NCC of every cluster centre against the left patches (raw images, :1500) + S12 arg-max (first maximum wins, :941-951)
+__global__ void __launch_bounds__(32 * WPB) ncc2_best_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int imgL = 2 * f, imgR = 2 * f + 1;
     const int nL = b.nE[imgL];
-    const uint8_t* IL = b.raw + (size_t)imgL * b.imgStride;
     const uint8_t* IR = b.raw + (size_t)imgR * b.imgStride;
+    const float* npL = b.npatch + (size_t)imgL * b.E * 98;
+    const uint8_t* pfL = b.pflag + (size_t)imgL * b.E;
     const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
@@ -936,57 +1105,40 @@ __global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams
     ebvo_mate* mates = b.mates + (size_t)f * b.E;   // staging: slot i
     const bool dumps = b.dumps && f == 0;
     unsigned long long n2 = 0;
-    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
-        int n = ccount[i];
-        if (n == 0) {
-            if (lane == 0) { mateFlag[i] = 0; if (dumps) { b.dump[DUMP_S10].n[i] = 0; b.dump[DUMP_S11].n[i] = 0; } }
-            continue;
-        }
+    (void)w;
+    for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < nL; i += gridDim.x * WPB) {
+        const int ncl = ccount[i];
+        if (ncl == 0) { if (lane == 0) { mateFlag[i] = 0; if (dumps) b.dump[DUMP_S11].n[i] = 0; } continue; }
         const int st = cstart[i];
-        if (n > MAXC) { if (lane == 0) atomicExch(b.errFlag, 4); n = MAXC; }
-        const double* ln = b.lines + ((size_t)f * b.E + i) * 3;
-        const double la = ln[0], lb = ln[1], lc = ln[2];
-        for (int k = lane; k < n; k += 32) {
-            double x = c_x[st + k], y = c_y[st + k], t = c_th[st + k];
-            shift_to_line(la, lb, lc, p, x, y, t);       // second shift (Stereo_Matches.cpp:1483 -> :981-998)
-            s_x[w][k] = x; s_y[w][k] = y; s_t[w][k] = t;
-        }
-        __syncwarp();
-        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_ox[w], s_oy[w], s_ot[w]);
-        __syncwarp();
-        if (dumps) {
-            for (int k = lane; k < ncl; k += 32) dump_put(b.dump[DUMP_S10], st + k, -1, s_ox[w][k], s_oy[w][k], s_ot[w][k], CUDART_NAN);
-            if (lane == 0) b.dump[DUMP_S10].n[i] = ncl;
-        }
-        // S11 NCC on the centres (raw images, :1500) + S12 arg-max, first maximum wins (:941-951)
-        float vp[2], vm[2];
         Patches PL, PR;
-        raw_patches(IL, b.pitch, b.W, b.H, exL[i], eyL[i], ethL[i], p.shift_mag, lane, vp, vm);
-        normalise_patches(vp, vm, lane, PL);
-        double bestS = -1.0;
+        load_patches(npL, pfL, i, lane, PL);
+        double bestS = -1.0, bx = 0, by = 0, bt = 0;
         int bestK = -1, nsurv = 0;
         for (int k = 0; k < ncl; ++k) {
-            raw_patches(IR, b.pitch, b.W, b.H, s_ox[w][k], s_oy[w][k], s_ot[w][k], p.shift_mag, lane, vp, vm);
+            const double cx = c_x[st + k], cy = c_y[st + k], ct = c_th[st + k];
+            float vp[2], vm[2];
+            raw_patches(IR, b.pitch, b.W, b.H, cx, cy, ct, p.shift_mag, lane, vp, vm);
             normalise_patches(vp, vm, lane, PR);
             const double s = ncc_score(PL, PR);
             ++n2;
             if (s > p.ncc_thresh) {
-                if (dumps && lane == 0) dump_put(b.dump[DUMP_S11], st + nsurv, -1, s_ox[w][k], s_oy[w][k], s_ot[w][k], s);
+                if (dumps && lane == 0) dump_put(b.dump[DUMP_S11], st + nsurv, -1, cx, cy, ct, s);
                 ++nsurv;
-                if (s > bestS) { bestS = s; bestK = k; }
+                if (s > bestS) { bestS = s; bestK = k; bx = cx; by = cy; bt = ct; }
             }
         }
-        if (dumps && lane == 0) b.dump[DUMP_S11].n[i] = nsurv;
+        __syncwarp();
         if (lane == 0) {
+            if (dumps) b.dump[DUMP_S11].n[i] = nsurv;
             if (bestK >= 0) {
                 ebvo_mate m;
                 m.left_index = i; m.reserved = 0;
                 m.lx = exL[i]; m.ly = eyL[i]; m.ltheta = ethL[i];
-                m.rx = s_ox[w][bestK]; m.ry = s_oy[w][bestK]; m.rtheta = s_ot[w][bestK];
+                m.rx = bx; m.ry = by; m.rtheta = bt;
                 m.score = bestS;
                 mates[i] = m;
                 mateFlag[i] = 1;
-                c_x[st] = m.rx; c_y[st] = m.ry; c_th[st] = m.rtheta; c_score[st] = bestS;
+                c_x[st] = bx; c_y[st] = by; c_th[st] = bt; c_score[st] = bestS;
                 ccount[i] = 1;
             } else { mateFlag[i] = 0; ccount[i] = 0; }
         }
@@ -1087,16 +1239,28 @@ void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t
 }
 void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cudaStream_t st, Prof* prof)
 {
+    dim3 gp(warp_grid(nFrames).x, 2 * nFrames);
+    EBVO_KERNEL(prof, "patch", st, (patch_kernel<<<gp, 32 * WPB, 0, st>>>(b, p)));
     EBVO_KERNEL(prof, "ncc_bnb", st, (ncc_bnb_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, sift ? 1 : 0)));
+}
+static dim3 slot_grid(int nFrames)
+{
+    dim3 g = warp_grid(nFrames);
+    g.x = (g.x + 3) / 4;
+    return g;
 }
 void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
-    if (p.gn_fp32) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
-    else EBVO_KERNEL(prof, "gn", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 0)));
+    if (p.gn_mode == 2) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    else EBVO_KERNEL(prof, "gn", st, (gn_mixed_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
-    EBVO_KERNEL(prof, "cluster_ncc_best", st, (cluster_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 1)));
+    EBVO_KERNEL(prof, "cluster", st, (cluster_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    EBVO_KERNEL(prof, "ncc2_best", st, (ncc2_best_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 
 void launch_match(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, bool sift, cudaStream_t st, Prof* prof)

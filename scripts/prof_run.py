@@ -9,7 +9,7 @@ cal = synth.kitti_calib()
 pairs = [synth.stereo_pair(cal, f) for f in range(min(B, 4))]
 Ls = [pairs[f % len(pairs)][0] for f in range(B)]
 Rs = [pairs[f % len(pairs)][1] for f in range(B)]
-prm = _lib.default_params(); prm.gn_fp32 = fp32
+prm = _lib.default_params(); prm.gn_mode = fp32
 ctx = _lib.Context(0, cal.width, cal.height, max_batch=B, max_edges=65536, params=prm)
 calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
 ctx.batch_upload(Ls, Rs)

@@ -33,7 +33,7 @@ def test_struct_layouts():
     assert (p.epipolar_line_dist_thresh, p.max_disparity, p.ncc_thresh, p.bnb_ncc) == (0.5, 25.0, 0.6, 0.9)
     assert (p.location_perturbation, p.epip_tangency_displ_thresh, p.orient_perturbation) == (0.4, 3.0, 0.174533)
     assert (p.cluster_dist_thresh, p.cluster_orient_thresh_deg, p.max_cluster_size) == (1.0, 20.0, 10)
-    assert (p.gn_max_iter, p.gn_tol, p.gn_huber_delta, p.gn_fp32) == (20, 1e-3, 3.0, 0)
+    assert (p.gn_max_iter, p.gn_tol, p.gn_huber_delta, p.gn_mode) == (20, 1e-3, 3.0, 0)
 
 
 def test_fundamental_is_host_side_and_matches_reference_formula():

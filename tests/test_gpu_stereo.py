@@ -151,7 +151,7 @@ def test_empty_inputs(gpu_ctx):
 def test_gn_fp32_variant_within_documented_tolerance(kitti_case):
     """Opt-in FP32 Gauss-Newton: >= 99.9 % of the mates within 1e-3 px of the oracle (rest: non-converging sequences)."""
     k = kitti_case
-    prm = _lib.default_params(); prm.gn_fp32 = 1
+    prm = _lib.default_params(); prm.gn_mode = 2
     ctx = _lib.Context(0, 1241, 376, max_batch=1, max_edges=65536, params=prm)
     mates = ctx.stereo_match(_calib(k["cal"]), k["L"], k["R"], _lib.edges_from_xyt(k["eL"]), _lib.edges_from_xyt(k["eR"]))
     ctx.close()
