@@ -224,26 +224,47 @@ def main():
         frames_total = world * B * args.steps
         value = frames_total / (ms_total / 1e3)
         e2e_value = frames_total / (e2e_ms / 1e3)
-        # dominant kernel + roofline
+        # dominant kernel + roofline.  Algorithmic work per unit (DESIGN.md section 5 / SURVEY.md 8(d)):
+        #   TOED        1636 flop per input pixel (818 MAC, separable dense form) x W*H x 2 views
+        #   GN          4.5 kflop per Gauss-Newton iteration (98 samples x 3 channels bilinear + residual/normal equations)
+        #   NCC         2.3 kflop per scored pair
+        # Bound = FP32 pipe (no dense contraction on this path, tensor cores unused); HBM traffic is far below the
+        # compute time for every kernel (the per-frame working set is L2-resident), see `hbm` for the byte side.
         ksum = sum(v[0] for v in ktimes.values())
         dom = max(ktimes.items(), key=lambda kv: kv[1][0])
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         fp32_peak = sms * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12      # TFLOP/s, nominal FP32 FMA peak at max clock
+        c = counters.sum(axis=0)
         toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_orient", (0, 1))[0]
         toed_flops = TOED_FLOP_PER_PX * W * H * 2 * B * args.steps
+        gn_name = next((k for k in ("gn", "gn64", "gn32") if k in ktimes), None)
+        gn_ms = ktimes[gn_name][0] if gn_name else 0.0
+        gn_flops = 4500.0 * float(c[3]) * args.steps
+        ncc_ms = ktimes.get("patch", (0, 1))[0] + ktimes.get("ncc_bnb", (0, 1))[0]
+        ncc_flops = 2300.0 * float(c[0]) * args.steps
+
+        def tf(fl, ms):
+            return fl / (ms / 1e3) / 1e12 if ms else None
+
         kernels = {k: {"ms_per_step": v[0] / args.steps, "share": v[0] / ksum if ksum else None, "launches": v[1]} for k, v in ktimes.items()}
-        c = counters.sum(axis=0)
         # algorithmic bytes of the matching stage per step (SURVEY.md 8(d) formula, this run's counts)
         match_bytes = (2 * W * H * 2 + 2 * 4 * W * H) * B + 24.0 * (nL.sum() + nR.sum()) + 4.0 * c[0] + 64.0 * nM.sum()
-        roof = {"kernel": "toed_grad_nms+toed_orient", "bound": "fp32", "achieved": toed_flops / (toed_ms / 1e3) / 1e12 if toed_ms else None,
-                "peak": fp32_peak, "unit": "TFLOP/s", "frac": (toed_flops / (toed_ms / 1e3) / 1e12) / fp32_peak if toed_ms else None,
-                "traffic": None,
+        dom_is_gn = dom[0] == gn_name
+        ach = tf(gn_flops, gn_ms) if dom_is_gn else tf(toed_flops, toed_ms)
+        roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak if ach else None, "traffic": None,
                 "peak_source": f"nominal FP32 FMA peak = {sms} SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock); "
                                "tensor cores unused (no dense contraction on this path)",
-                "algorithmic_flop_per_px": TOED_FLOP_PER_PX,
                 "dominant_kernel_by_time": dom[0], "dominant_kernel_share": dom[1][0] / ksum if ksum else None,
-                "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "matching_algorithmic_bytes_per_step": float(match_bytes)}}
+                "per_stage": {"toed": {"algorithmic_flop_per_px": TOED_FLOP_PER_PX, "achieved_tflops": tf(toed_flops, toed_ms),
+                                       "frac": (tf(toed_flops, toed_ms) or 0) / fp32_peak},
+                              "gauss_newton": {"algorithmic_flop_per_iteration": 4500.0, "achieved_tflops": tf(gn_flops, gn_ms),
+                                               "frac": (tf(gn_flops, gn_ms) or 0) / fp32_peak},
+                              "ncc": {"algorithmic_flop_per_pair": 2300.0, "achieved_tflops": tf(ncc_flops, ncc_ms),
+                                      "frac": (tf(ncc_flops, ncc_ms) or 0) / fp32_peak}},
+                "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "matching_algorithmic_bytes_per_step": float(match_bytes),
+                        "matching_algorithmic_gbs": float(match_bytes) / ((ksum - toed_ms) / args.steps / 1e3) / 1e9 if ksum > toed_ms else None}}
         line = {"metric": "stereo frames/s (TOED+NCC stereo match) at KITTI 1241x376", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 mixed", "data": "synthetic",

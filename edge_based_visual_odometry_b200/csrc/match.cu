@@ -655,14 +655,17 @@ __device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x4330
 __device__ __forceinline__ double pk_gx(uint2 u) { return __hiloint2double(0x43300000, (((int)u.x) >> 16) ^ 0x80000000) - 4503601774854144.0; }
 __device__ __forceinline__ double pk_gy(uint2 u) { return __hiloint2double(0x43300000, ((int)(u.y << 16) >> 16) ^ 0x80000000) - 4503601774854144.0; }
 
-// floor + fraction of a clamped coordinate without conversions (utility.h:161-166): round-down add of 1.5*2^52 puts
-// floor(x) in the low word; the clamp to [0, n-1] is applied to the (cell, fraction) pair.
-__device__ __forceinline__ void cell_magic(double x, int n, int& x0, double& a)
+// floor + fraction of a clamped coordinate without conversions (utility.h:161-166): a round-down add of 1.5*2^52 puts
+// floor(x) in the low word.  The clamp to [0, n-1] is applied to the cell; d1 (offset of the second corner) is 0
+// when the coordinate was clamped, which makes both corners the same pixel, so the fraction needs no fix-up
+// (the reference sets it to 0 there: (1-a)v + a v = v).
+__device__ __forceinline__ void cell_magic(double x, int n, int stride, int& x0, int& d1, double& a)
 {
     const double t = __dadd_rd(x, 6755399441055744.0);
-    x0 = __double2loint(t);
+    const int xu = __double2loint(t);
     a = x - (t - 6755399441055744.0);
-    if (x0 < 0) { x0 = 0; a = 0.0; } else if (x0 >= n - 1) { x0 = n - 1; a = 0.0; }
+    d1 = ((unsigned)xu < (unsigned)(n - 1)) ? stride : 0;
+    x0 = min(max(xu, 0), n - 1);
 }
 
 struct GnSetup {
@@ -738,11 +741,10 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn_mixed_kernel(DevBatch b, DevPa
                 vi[m] = 0.0; vg[m] = 0.f;
                 const int s = lane + 32 * m;
                 if (s < 98) {
-                    int x0, y0;
+                    int x0, y0, dx1, dy1;
                     double a, bb;
-                    cell_magic(g.Bx[m] + sx, W, x0, a);
-                    cell_magic(g.By[m] + sy, H, y0, bb);
-                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
+                    cell_magic(g.Bx[m] + sx, W, 1, x0, dx1, a);
+                    cell_magic(g.By[m] + sy, H, W, y0, dy1, bb);
                     const uint2* c00 = PK + (y0 * W + x0);
                     const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
                     // image channel: FP64 blend rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172)
@@ -814,11 +816,10 @@ __global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams
                 vi[m] = 0.0; vg[m] = 0.0;
                 const int s = lane + 32 * m;
                 if (s < 98) {
-                    int x0, y0;
+                    int x0, y0, dx1, dy1;
                     double a, bb;
-                    cell_magic(g.Bx[m] + sx, W, x0, a);
-                    cell_magic(g.By[m] + sy, H, y0, bb);
-                    const int dx1 = (x0 < W - 1) ? 1 : 0, dy1 = (y0 < H - 1) ? W : 0;
+                    cell_magic(g.Bx[m] + sx, W, 1, x0, dx1, a);
+                    cell_magic(g.By[m] + sy, H, W, y0, dy1, bb);
                     const uint2* c00 = PK16 + (y0 * W + x0);
                     const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
                     const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
@@ -982,78 +983,92 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
 // ------------------------------------------------------------------------------------------------------
 // EdgeClusterer::performClustering (EdgeClusterer.cpp:119-302) on n <= MAXC warp-private candidates.
 // Returns the number of clusters; centres go to (ox, oy, oth)[0..ncl) in ascending-label order (the order of
-// returned_clusters); lab[] receives the renumbered label of every input.
+// returned_clusters); lab[] receives the renumbered label of every input; csz[] (n ints) and dk[], gk[] (n doubles) are scratch.
+//
+// The reference repeats: scan the points in index order; the first point whose nearest admissible neighbour
+// (other cluster, d < 1 px, |dtheta| < 20 deg when clustering by orientation; first minimum on ties) can be merged
+// without exceeding MAX_CLUSTER_SIZE triggers a merge and restarts the scan.  Here every lane evaluates "its"
+// point's nearest admissible neighbour at once and a ballot picks the first feasible point: same merges, same
+// order, O(n) work per merge instead of O(n^2).  Distances are compared squared (sqrt is monotone; d < 1 <=> d^2 < 1).
 __device__ int warp_cluster(const double* sx, const double* sy, const double* sth, int n, bool by_orient, const DevParams& p,
-                            int lane, int* lab, double* ox, double* oy, double* oth)
+                            int lane, int* lab, int* csz, double* dk, double* gk, double* ox, double* oy, double* oth)
 {
-    for (int k = lane; k < n; k += 32) lab[k] = k;
+    for (int k = lane; k < n; k += 32) { lab[k] = k; csz[k] = 1; }
     __syncwarp();
-    bool merged = true;
-    while (merged) {
-        merged = false;
-        for (int i = 0; i < n; ++i) {
-            const int li = lab[i];
-            const double xi = sx[i], yi = sy[i], ti = sth[i];
-            double best = CUDART_INF;
-            int bj = 0x7fffffff;
-            for (int j = lane; j < n; j += 32) {
-                if (lab[j] == li) continue;
-                const double dx = xi - sx[j], dy = yi - sy[j];
-                const double d = sqrt(dx * dx + dy * dy);
-                const bool ok = d < p.clus_dist && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad);
-                if (ok && d < best) { best = d; bj = j; }   // ascending j per lane; strict < keeps the first minimum
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int oj = __shfl_xor_sync(FULL, bj, o);
-                if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
-            }
-            if (bj != 0x7fffffff) {
-                const int lold = lab[bj];
-                int cnt = 0;
-                for (int k = lane; k < n; k += 32) cnt += (lab[k] == lold || lab[k] == li) ? 1 : 0;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-                if (cnt <= p.clus_max) {                    // MAX_CLUSTER_SIZE, EdgeClusterer.cpp:179
-                    __syncwarp();
-                    for (int k = lane; k < n; k += 32) if (lab[k] == lold) lab[k] = li;
-                    __syncwarp();
-                    merged = true;
-                    break;
+    const double d2max = p.clus_dist * p.clus_dist;
+    for (;;) {
+        int pick_i = -1, pick_j = -1;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int i = c0 + lane;
+            int bj = -1;
+            if (i < n) {
+                const int li = lab[i];
+                const double xi = sx[i], yi = sy[i], ti = sth[i];
+                double best = CUDART_INF;
+                for (int j = 0; j < n; ++j) {
+                    if (lab[j] == li) continue;
+                    const double dx = xi - sx[j], dy = yi - sy[j];
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < best && d2 < d2max && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad)) { best = d2; bj = j; }
                 }
+                if (bj >= 0 && csz[li] + csz[lab[bj]] > p.clus_max) bj = -1;   // MAX_CLUSTER_SIZE, EdgeClusterer.cpp:179
+            }
+            const unsigned m = __ballot_sync(FULL, bj >= 0);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                pick_i = c0 + src;
+                pick_j = __shfl_sync(FULL, bj, src);
+                break;
             }
         }
+        if (pick_i < 0) break;
+        const int li = lab[pick_i], lold = lab[pick_j];
+        const int merged_size = csz[li] + csz[lold];
+        __syncwarp();
+        for (int k = lane; k < n; k += 32) if (lab[k] == lold) lab[k] = li;
+        if (lane == 0) csz[li] = merged_size;
+        __syncwarp();
     }
-    // Clusters in ascending label order (std::map, :209-222).  A live label L always labels element L itself,
-    // so "label L exists" <=> lab[L] == L.  Processed members are re-tagged -1-c to carry the renumbered label.
-    int ncl = 0;
-    for (int L = 0; L < n; ++L) {
-        if (lab[L] != L) continue;
-        double sxx = 0, syy = 0, cntd = 0;
-        for (int k = lane; k < n; k += 32) if (lab[k] == L) { sxx += sx[k]; syy += sy[k]; cntd += 1.0; }
-        warp_sum3(sxx, syy, cntd);
-        const double cx = sxx / cntd, cy = syy / cntd;
+    // Gaussian-weighted centre of every cluster (:43-117).  A live label L always labels element L itself, so "label L
+    // exists" <=> lab[L] == L.  The transcendental work (sqrt, exp) is done by one lane per MEMBER; the sums are done
+    // by one lane per CLUSTER walking its members in index order, i.e. in the reference's summation order.
+    for (int L = lane; L < n; L += 32) if (lab[L] == L) {          // centroid (:55-74), label-indexed scratch in ox/oy
+        double sxx = 0, syy = 0;
+        for (int k = 0; k < n; ++k) if (lab[k] == L) { sxx += sx[k]; syy += sy[k]; }
+        ox[L] = sxx / csz[L]; oy[L] = syy / csz[L];
+    }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) { const int L = lab[k]; const double dx = sx[k] - ox[L], dy = sy[k] - oy[L]; dk[k] = sqrt(dx * dx + dy * dy); }
+    __syncwarp();
+    for (int L = lane; L < n; L += 32) if (lab[L] == L) {          // mean distance from the centroid (:77-88)
         double tot = 0;
-        for (int k = lane; k < n; k += 32) if (lab[k] == L) { const double dx = sx[k] - cx, dy = sy[k] - cy; tot += sqrt(dx * dx + dy * dy); }
-        tot = warp_sum(tot);
-        const double md = tot / cntd;
-        double wx = 0, wy = 0, wt = 0, ww = 0;
-        for (int k = lane; k < n; k += 32) if (lab[k] == L) {
-            const double dx = sx[k] - cx, dy = sy[k] - cy, d = sqrt(dx * dx + dy * dy);
-            const double z = (d - md) / p.clus_sigma;
-            const double g = exp(-0.5 * (z * z));
-            wx += g * sx[k]; wy += g * sy[k]; wt += g * sth[k]; ww += g;
-        }
-        warp_sum2(wx, wy);
-        warp_sum2(wt, ww);
-        if (lane == 0) { ox[ncl] = wx / ww; oy[ncl] = wy / ww; oth[ncl] = wt / ww; }
-        __syncwarp();
-        for (int k = lane; k < n; k += 32) if (lab[k] == L) lab[k] = -1 - ncl;
-        __syncwarp();
-        ++ncl;
+        for (int k = 0; k < n; ++k) if (lab[k] == L) tot += dk[k];
+        oth[L] = tot / csz[L];
     }
-    for (int k = lane; k < n; k += 32) lab[k] = -1 - lab[k];
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) { const double z = (dk[k] - oth[lab[k]]) / p.clus_sigma; gk[k] = exp(-0.5 * (z * z)); }   // :103
+    __syncwarp();
+    for (int L = lane; L < n; L += 32) if (lab[L] == L) {          // weighted means (:105-114)
+        double wx = 0, wy = 0, wt = 0, ww = 0;
+        for (int k = 0; k < n; ++k) if (lab[k] == L) { const double g = gk[k]; wx += g * sx[k]; wy += g * sy[k]; wt += g * sth[k]; ww += g; }
+        ox[L] = wx / ww; oy[L] = wy / ww; oth[L] = wt / ww;
+    }
+    __syncwarp();
+    // clusters in ascending label order (std::map, :209-222): ordered compaction label index -> cluster index
+    int ncl = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int L = c0 + lane;
+        const bool live = L < n && lab[L] == L;
+        const unsigned m = __ballot_sync(FULL, live);
+        const int c = ncl + __popc(m & ((1u << lane) - 1));
+        double vx = 0, vy = 0, vt = 0;
+        if (live) { vx = ox[L]; vy = oy[L]; vt = oth[L]; }
+        __syncwarp();
+        if (live) { ox[c] = vx; oy[c] = vy; oth[c] = vt; csz[L] = -1 - c; }
+        __syncwarp();
+        ncl += __popc(m);
+    }
+    for (int k = lane; k < n; k += 32) { const int L = lab[k]; lab[k] = -1 - csz[L]; }
     __syncwarp();
     return ncl;
 }
@@ -1062,7 +1077,8 @@ __global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams
 {
     __shared__ double s_x[WPB][MAXC], s_y[WPB][MAXC], s_t[WPB][MAXC];
     __shared__ double s_ox[WPB][MAXC], s_oy[WPB][MAXC], s_ot[WPB][MAXC];
-    __shared__ int s_lab[WPB][MAXC];
+    __shared__ int s_lab[WPB][MAXC], s_csz[WPB][MAXC];
+    __shared__ double s_dk[WPB][MAXC], s_gk[WPB][MAXC];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nL = b.nE[2 * f];
     const int* cstart = b.cstart + (size_t)f * b.E;
@@ -1076,7 +1092,7 @@ __global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams
         if (n > MAXC) { if (lane == 0) atomicExch(b.errFlag, 4); n = MAXC; }
         for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
         __syncwarp();
-        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_ox[w], s_oy[w], s_ot[w]);
+        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_csz[w], s_dk[w], s_gk[w], s_ox[w], s_oy[w], s_ot[w]);
         __syncwarp();
         for (int k = lane; k < ncl; k += 32) {
             c_x[st + k] = s_ox[w][k]; c_y[st + k] = s_oy[w][k]; c_th[st + k] = s_ot[w][k];
@@ -1343,11 +1359,12 @@ __global__ void cluster_one_kernel(const double* x, const double* y, const doubl
                                    double* cx, double* cy, double* cth, int* labels, int* nclusters)
 {
     __shared__ double s_x[MAXC], s_y[MAXC], s_t[MAXC], s_ox[MAXC], s_oy[MAXC], s_ot[MAXC];
-    __shared__ int s_lab[MAXC];
+    __shared__ int s_lab[MAXC], s_csz[MAXC];
+    __shared__ double s_dk[MAXC], s_gk[MAXC];
     const int lane = threadIdx.x;
     for (int k = lane; k < n; k += 32) { s_x[k] = x[k]; s_y[k] = y[k]; s_t[k] = th[k]; }
     __syncwarp();
-    const int ncl = warp_cluster(s_x, s_y, s_t, n, by_orient != 0, p, lane, s_lab, s_ox, s_oy, s_ot);
+    const int ncl = warp_cluster(s_x, s_y, s_t, n, by_orient != 0, p, lane, s_lab, s_csz, s_dk, s_gk, s_ox, s_oy, s_ot);
     __syncwarp();
     for (int k = lane; k < ncl; k += 32) { cx[k] = s_ox[k]; cy[k] = s_oy[k]; cth[k] = s_ot[k]; }
     for (int k = lane; k < n; k += 32) labels[k] = s_lab[k];

@@ -163,6 +163,9 @@ class StereoResult:
         L.so_get_stats(C.c_void_p(h), _p(t), cnt)
         self.stage_seconds = dict(zip(STAGES, t.tolist()))
         self.counts = dict(zip(["s1_total", "ncc_pairs1", "ncc_pairs2", "gn_pairs", "gn_iters"], list(cnt)))
+        self.gn_iters = np.zeros(self.counts['gn_pairs'], np.int32)
+        if len(self.gn_iters):
+            L.so_get_gn_iters(C.c_void_p(h), _p(self.gn_iters))
         self.stages = {}
         if want_dumps:
             for k, name in enumerate(STAGES):

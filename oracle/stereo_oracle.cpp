@@ -71,6 +71,7 @@ struct Cl {  // Stereo_Matching_Edge_Clusters (Dataset.h:169-179)
     std::vector<Cand> c;
     std::vector<double> score, conf;
     std::vector<char> valid;
+    std::vector<int> iters;   // diagnostics: GN iterations per candidate
 };
 
 struct Img {
@@ -354,6 +355,7 @@ struct Result {
     std::vector<double> lines;      // nL*3
     std::vector<double> t_stage;    // seconds per stage
     long gn_pairs = 0, gn_iters = 0, ncc_pairs1 = 0, ncc_pairs2 = 0, s1_total = 0;
+    std::vector<int> gn_iter_list;   // per GN candidate, in stage order
 };
 
 enum { ST_EPI = 0, ST_DISP, ST_ORIENT, ST_SIFT, ST_NCC, ST_BNB_NCC, ST_BNB_SIFT, ST_SHIFT, ST_GN, ST_CLUSTER, ST_NCC2, ST_BEST, ST_COUNT };
@@ -623,19 +625,20 @@ void *so_run(const uint8_t *Lraw, const uint8_t *Rraw, const uint8_t *Lund, cons
     for (int i = 0; i < nL; ++i) {
         Cl &c = cl[i];
         if (c.c.empty()) continue;
-        c.score.clear(); c.conf.clear(); c.valid.clear();
+        c.score.clear(); c.conf.clear(); c.valid.clear(); c.iters.clear();
         const double *l = &res->lines[3 * (size_t)i];
         double dx = -l[1], dy = l[0], nn = std::sqrt(dx * dx + dy * dy);
         dx /= nn; dy /= nn;
         for (auto &k : c.c) {
             double a, s, cf; bool v; int iters;
             gn_refine(L[i], k.e, dx, dy, ILu, IRu, gxR, gyR, p, a, s, cf, v, iters);
-            c.score.push_back(s); c.conf.push_back(cf); c.valid.push_back(v);
+            c.score.push_back(s); c.conf.push_back(cf); c.valid.push_back(v); c.iters.push_back(iters);
             k.e.x += a * dx; k.e.y += a * dy;
             gnp++; gni += iters;
         }
     }
     res->gn_pairs = gnp; res->gn_iters = gni;
+    for (int i = 0; i < nL; ++i) for (int it : cl[i].iters) res->gn_iter_list.push_back(it);
     t1 = now(); res->t_stage[ST_GN] = t1 - t0;
     dump(*res, ST_GN, cl, want_dumps);
     t0 = now();
@@ -704,6 +707,7 @@ void so_get_stats(void *h, double *t_stage /*ST_COUNT*/, long *counts /*5: s1_to
     for (int k = 0; k < ST_COUNT; ++k) t_stage[k] = r->t_stage[k];
     counts[0] = r->s1_total; counts[1] = r->ncc_pairs1; counts[2] = r->ncc_pairs2; counts[3] = r->gn_pairs; counts[4] = r->gn_iters;
 }
+void so_get_gn_iters(void *h, int *out) { Result *r = (Result *)h; std::memcpy(out, r->gn_iter_list.data(), r->gn_iter_list.size() * 4); }
 void so_free(void *h) { delete (Result *)h; }
 int so_stage_count() { return ST_COUNT; }
 
