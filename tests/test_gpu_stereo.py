@@ -160,3 +160,61 @@ def test_gn_fp32_variant_within_documented_tolerance(kitti_case):
     assert len(common) >= 0.999 * len(res.mate_left)
     d = np.hypot(res.mate_right[io, 0] - mates["rx"][ig], res.mate_right[io, 1] - mates["ry"][ig])
     assert (d > 1e-3).mean() <= 1e-3
+
+
+def _sift_descriptors(img, xyt):
+    """augment_Edge_Data / apply_SIFT_filtering keypoints (Stereo_Matches.cpp:668-677,720-727): two keypoints per edge
+    at +-8 px along the normal, size 1, angle = deg(theta); one batched cv2 compute per image."""
+    cv2 = pytest.importorskip("cv2")
+    kps = []
+    for x, y, t in xyt:
+        for s in (1, -1):
+            kps.append(cv2.KeyPoint(float(x + s * 8 * np.sin(t)), float(y - s * 8 * np.cos(t)), 1, float(180 / np.pi * t)))
+    k2, d = cv2.SIFT_create().compute(img, kps)
+    assert len(k2) == len(kps)
+    return d.reshape(len(xyt), 2, 128).astype(np.float32)
+
+
+def test_sift_gate_and_bnb_sift_with_injected_descriptors(gpu_ctx):
+    """S4 + S7' on the GPU with caller-supplied descriptors (cv2 4.x SIFT), against the oracle in the same mode."""
+    cal = synth.kitti_calib(640, 240)
+    L, R = synth.stereo_pair(cal, 1)
+    eL, _ = oracle.toed(L)
+    eR, _ = oracle.toed(R)
+    dL, dR = _sift_descriptors(L, eL), _sift_descriptors(R, eR)
+    F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    res = oracle.stereo(L, R, eL, eR, F21, descL=dL, descR=dR)
+    off = oracle.stereo(L, R, eL, eR, F21)
+    assert res.stages["sift"]["off"][-1] < off.stages["sift"]["off"][-1]          # the gate is not a no-op
+    gpu_ctx.set_stage_dumps(True)
+    mates = gpu_ctx.stereo_match(_calib(cal), L, R, _lib.edges_from_xyt(eL), _lib.edges_from_xyt(eR), descL=dL, descR=dR)
+    frac_bad = _check_stages(gpu_ctx, res)
+    gpu_ctx.set_stage_dumps(False)
+    assert frac_bad <= 2e-3
+    common, io, ig = np.intersect1d(res.mate_left, mates["left_index"], return_indices=True)
+    assert len(common) >= (1 - 2e-3) * len(res.mate_left) and len(mates) <= (1 + 2e-3) * len(res.mate_left) + 1
+    d = np.hypot(res.mate_right[io, 0] - mates["rx"][ig], res.mate_right[io, 1] - mates["ry"][ig])
+    assert (d > 1e-3).mean() <= 2e-3
+
+
+def test_4k_stress_shape_properties():
+    """BASELINE config 5 (3840x2160): capacity and size-independent properties (the brute-force oracle is O(N^2)
+    in the edge count and is not run at this size): TOED vs oracle, determinism, mates on their epipolar lines,
+    NCC scores above the gate, left-edge order kept."""
+    cal = synth.kitti4k_calib()
+    L, R = synth.stereo_pair(cal, 0, density=0.5)
+    ctx = _lib.Context(0, cal.width, cal.height, max_batch=1, max_edges=1 << 20)
+    eo, nto = oracle.toed(L)
+    eg, ntg = ctx.toed(L)
+    assert abs(len(eg) - len(eo)) <= 1e-3 * len(eo) and abs(ntg - nto) <= 1e-3 * nto
+    if len(eg) == len(eo):
+        assert np.abs(eg["x"] - eo[:, 0]).max() < 1e-3 and np.abs(eg["y"] - eo[:, 1]).max() < 1e-3
+    calib = _calib(cal)
+    m1, Le, Re = ctx.stereo_frame(calib, L, R)
+    m2 = ctx.stereo_frame(calib, L, R, want_edges=False)
+    ctx.close()
+    assert len(m1) > 10000 and np.array_equal(m1, m2)
+    assert (np.diff(m1["left_index"]) > 0).all() and (m1["score"] > 0.6).all()
+    dy = np.abs(m1["ry"] - m1["ly"])                       # rectified: the shifts project onto y = y_L unless the
+    assert dy.max() < 0.5 and (dy < 1e-6).mean() > 0.95    # tangency test fails (edge kept, within the 0.5 px gate)
+    assert np.array_equal(m1["lx"], Le["x"][m1["left_index"]])
