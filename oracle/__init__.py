@@ -34,7 +34,8 @@ def build(force: bool = False) -> None:
     if need:
         subprocess.check_call(["make", "-C", _DIR, "libebvo_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/toed/cpu_toed.cpp") and (
-            force or not os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))):
+            force or not os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))
+            or not os.path.exists(os.path.join(_DIR, "_ref", "libstereo_ref.so"))):
         subprocess.check_call(["make", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -55,6 +56,28 @@ def lib():
 
 def have_ref() -> bool:
     return os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))
+
+
+def have_stereo_ref() -> bool:
+    return os.path.exists(os.path.join(_DIR, "_ref", "libstereo_ref.so"))
+
+
+_SREF = None
+
+
+def stereo_ref_lib():
+    """oracle/_ref/libstereo_ref.so: the UNMODIFIED reference stereo sources compiled in place against oracle/ref_shim."""
+    global _SREF
+    if _SREF is None:
+        build()
+        R = C.CDLL(os.path.join(_DIR, "_ref", "libstereo_ref.so"))
+        R.rs_run.restype = C.c_void_p
+        R.rs_num_mates.restype = C.c_int
+        R.rs_stage_total.restype = C.c_int
+        R.rs_patch_similarity.restype = C.c_double
+        R.rs_cluster.restype = C.c_int
+        _SREF = R
+    return _SREF
 
 
 def ref():
@@ -199,3 +222,67 @@ def stereo(Lraw, Rraw, Ledges, Redges, F21, Lund=None, Rund=None, descL=None, de
     h = lib().so_run(_p(Lraw), _p(Rraw), _p(Lund), _p(Rund), H, W, _p(Le), len(Le), _p(Re), len(Re), _p(F),
                      mode, _p(descL), _p(descR), int(want_dumps), threads)
     return StereoResult(h, len(Le), want_dumps)
+
+
+class ReferenceStereoResult:
+    """Stage dumps + mates produced by the reference's own stereo code (oracle/ref_stereo_harness.cpp)."""
+
+    def __init__(self, h, nL):
+        R = stereo_ref_lib()
+        hp = C.c_void_p(h)
+        n = R.rs_num_mates(hp)
+        self.mate_left = np.zeros(n, np.int32)
+        rx, ry, rth = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.mate_score = np.zeros(n)
+        R.rs_get_mates(hp, _p(self.mate_left), _p(rx), _p(ry), _p(rth), _p(self.mate_score))
+        self.mate_right = np.stack([rx, ry, rth], 1) if n else np.zeros((0, 3))
+        self.lines = np.zeros((nL, 3))
+        self.F21 = np.zeros((3, 3))
+        R.rs_get_lines(hp, _p(self.lines), _p(self.F21))
+        self.stages = {}
+        for k, name in enumerate(STAGES):
+            tot = R.rs_stage_total(hp, k)
+            if tot < 0:
+                continue
+            off = np.zeros(nL + 1, np.int32)
+            ridx = np.zeros(tot, np.int32)
+            x, y, th, sc = (np.zeros(tot) for _ in range(4))
+            R.rs_get_stage(hp, k, _p(off), _p(ridx), _p(x), _p(y), _p(th), _p(sc))
+            self.stages[name] = dict(off=off, ridx=ridx, x=x, y=y, th=th, score=sc)
+        R.rs_free(hp)
+
+
+def stereo_reference(Lraw, Rraw, Ledges, Redges, Kl, Kr, R21, T21, Lund=None, Rund=None) -> ReferenceStereoResult:
+    """Run the reference's own stage functions (SIFT-off, see oracle/ref_stereo_harness.cpp) on one pair."""
+    Lraw = np.ascontiguousarray(Lraw, dtype=np.uint8)
+    Rraw = np.ascontiguousarray(Rraw, dtype=np.uint8)
+    Lund = Lraw if Lund is None else np.ascontiguousarray(Lund, dtype=np.uint8)
+    Rund = Rraw if Rund is None else np.ascontiguousarray(Rund, dtype=np.uint8)
+    H, W = Lraw.shape
+    Le = np.ascontiguousarray(Ledges, dtype=np.float64).reshape(-1, 3)
+    Re = np.ascontiguousarray(Redges, dtype=np.float64).reshape(-1, 3)
+    a = [np.ascontiguousarray(m, dtype=np.float64) for m in (Kl, Kr, R21, T21)]
+    h = stereo_ref_lib().rs_run(_p(Lraw), _p(Rraw), _p(Lund), _p(Rund), H, W, _p(Le), len(Le), _p(Re), len(Re), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]))
+    return ReferenceStereoResult(h, len(Le))
+
+
+def ref_edge_patches(img, x, y, th):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    p, m = np.zeros(49, np.float32), np.zeros(49, np.float32)
+    stereo_ref_lib().rs_edge_patches(_p(img), H, W, C.c_double(x), C.c_double(y), C.c_double(th), _p(p), _p(m))
+    return p.reshape(7, 7), m.reshape(7, 7)
+
+
+def ref_patch_similarity(a, b) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+    b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+    return stereo_ref_lib().rs_patch_similarity(_p(a), _p(b))
+
+
+def ref_cluster(xyt, by_orientation=True):
+    xyt = np.ascontiguousarray(xyt, dtype=np.float64).reshape(-1, 3)
+    n = len(xyt)
+    cen, cnt = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.int32)
+    k = stereo_ref_lib().rs_cluster(_p(xyt), n, int(by_orientation), _p(cen), _p(cnt))
+    return cen[:k].copy(), cnt[:k].copy()

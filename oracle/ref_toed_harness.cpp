@@ -22,7 +22,7 @@ int toed_ref_run(const unsigned char* img, int H, int W, int stride,
 {
     ThirdOrderEdgeDetectionCPU det(H, W);
     if (omp_threads > 0) det.omp_threads = omp_threads;
-    cv::Mat m(H, W, img, (size_t)stride);
+    cv::Mat m(H, W, CV_8UC1, (void*)img, (size_t)stride);
     det.get_Third_Order_Edges(m);
     int n = (int)det.toed_edges.size();
     for (int k = 0; k < n && k < capacity; ++k) {
@@ -52,7 +52,7 @@ int toed_ref_detect(void* h, const unsigned char* img, int H, int W, int stride,
                     double* time_conv, double* time_nms)
 {
     auto* d = static_cast<ThirdOrderEdgeDetectionCPU*>(h);
-    cv::Mat m(H, W, img, (size_t)stride);
+    cv::Mat m(H, W, CV_8UC1, (void*)img, (size_t)stride);
     d->get_Third_Order_Edges(m);
     if (time_conv) *time_conv = d->time_conv;
     if (time_nms) *time_nms = d->time_nms;

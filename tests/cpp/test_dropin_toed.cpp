@@ -16,7 +16,7 @@ int main(int argc, char** argv)
     FILE* f = std::fopen(argv[1], "rb");
     if (!f || std::fread(buf.data(), 1, buf.size(), f) != buf.size()) return 3;
     std::fclose(f);
-    cv::Mat image(H, W, buf.data(), (size_t)W);
+    cv::Mat image(H, W, CV_8UC1, buf.data(), (size_t)W);
     ThirdOrderEdgeDetectionCPU::Ptr TOED = ThirdOrderEdgeDetectionCPU::Ptr(new ThirdOrderEdgeDetectionCPU(H, W));
     std::vector<Edge> edges;
     for (int rep = 0; rep < 2; ++rep) {          // the pipeline reuses one detector for the left and right image

@@ -6,6 +6,9 @@
                          (oracle/_ref/libtoed_ref.so = /root/reference/src/toed/cpu_toed.cpp compiled in place).
 * stereo_small.npz     : a 320x200 KITTI-calibrated synthetic pair, its reference TOED edges (both views) and
                          the oracle's stage counts + final mates (regression pin of the restatement itself).
+* stereo_ref_small.npz : the same pair through the REFERENCE'S OWN stereo code (oracle/_ref/libstereo_ref.so =
+                         Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in place against oracle/ref_shim,
+                         driven by oracle/ref_stereo_harness.cpp): per-stage candidate lists and final mates.
 """
 import os, sys
 import numpy as np
@@ -33,3 +36,17 @@ np.savez_compressed(os.path.join(HERE, "stereo_small.npz"), L=L, R=R, eL=eL, eR=
                     stage_names=np.array(list(counts.keys())), stage_totals=np.array(list(counts.values())),
                     mate_left=res.mate_left, mate_right=res.mate_right, mate_score=res.mate_score)
 print("stereo_small", len(eL), len(eR), counts, len(res.mate_left))
+
+assert oracle.have_stereo_ref(), "needs oracle/_ref/libstereo_ref.so (build container only)"
+ref = oracle.stereo_reference(L, R, eL, eR, cal.Kl, cal.Kr, cal.R21, cal.T21)
+out = dict(mate_left=ref.mate_left, mate_right=ref.mate_right, mate_score=ref.mate_score, F21=ref.F21)
+for k, v in ref.stages.items():
+    out[f"{k}_off"] = v["off"]
+    if k in ("epi", "disp", "orient", "ncc", "bnb_ncc"):      # index stages: positions are those of the right edges
+        out[f"{k}_ridx"] = v["ridx"]
+    if k in ("shift", "gn", "cluster", "ncc2", "best"):
+        out[f"{k}_xyt"] = np.stack([v["x"], v["y"], v["th"]], 1).astype(np.float64)
+    if k in ("ncc", "bnb_ncc", "ncc2", "best"):
+        out[f"{k}_score"] = v["score"]
+np.savez_compressed(os.path.join(HERE, "stereo_ref_small.npz"), **out)
+print("stereo_ref_small", {k: int(v["off"][-1]) for k, v in ref.stages.items()}, len(ref.mate_left))

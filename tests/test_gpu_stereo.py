@@ -218,3 +218,27 @@ def test_4k_stress_shape_properties():
     dy = np.abs(m1["ry"] - m1["ly"])                       # rectified: the shifts project onto y = y_L unless the
     assert dy.max() < 0.5 and (dy < 1e-6).mean() > 0.95    # tangency test fails (edge kept, within the 0.5 px gate)
     assert np.array_equal(m1["lx"], Le["x"][m1["left_index"]])
+
+
+def test_against_reference_stereo_golden(gpu_ctx, golden_stereo):
+    """CUDA path against output of the reference's OWN stereo code (tests/golden/stereo_ref_small.npz, produced by
+    Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in place; see tests/golden/make_golden.py)."""
+    import os
+    g = golden_stereo
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stereo_ref_small.npz"))
+    cal = synth.kitti_calib(320, 200)
+    gpu_ctx.set_stage_dumps(True)
+    mates = gpu_ctx.stereo_match(_calib(cal), g["L"], g["R"], _lib.edges_from_xyt(g["eL"]), _lib.edges_from_xyt(g["eR"]))
+    stages = {n: gpu_ctx.stage(n) for n in _lib.STAGES}
+    gpu_ctx.set_stage_dumps(False)
+    for n in _lib.STAGES:
+        assert np.array_equal(stages[n]["off"], ref[f"{n}_off"]), n
+    for n in ("epi", "disp", "orient", "ncc"):
+        assert np.array_equal(stages[n]["ridx"], ref[f"{n}_ridx"]), n
+    assert np.abs(stages["ncc"]["score"] - ref["ncc_score"]).max() < 1e-5
+    for n in ("cluster", "ncc2", "best"):
+        xyt = np.stack([stages[n]["x"], stages[n]["y"], stages[n]["th"]], 1)
+        assert np.abs(xyt[:, :2] - ref[f"{n}_xyt"][:, :2]).max() < 1e-3 and np.abs(xyt[:, 2] - ref[f"{n}_xyt"][:, 2]).max() < 1e-4, n
+    assert np.array_equal(mates["left_index"], ref["mate_left"])
+    assert np.abs(mates["rx"] - ref["mate_right"][:, 0]).max() < 1e-3 and np.abs(mates["ry"] - ref["mate_right"][:, 1]).max() < 1e-3
+    assert np.abs(mates["rtheta"] - ref["mate_right"][:, 2]).max() < 1e-4 and np.abs(mates["score"] - ref["mate_score"]).max() < 1e-5
