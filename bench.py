@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (cycled to fill the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton arithmetic: 0 mixed (default), 1 FP64, 2 FP32")
+    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -280,7 +280,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(2 * B * W * H), "d2h_bytes_per_step": int(64 * nM.sum() + 4 * B)},
                 "gpu_launches": int(sum(v[1] for v in ktimes.values())),
                 "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
-                "work_per_step": {"s3_pairs": int(c[0]), "bnb_pairs": int(c[1]), "gn_pairs": int(c[2]), "gn_iterations": int(c[3]), "ncc2_pairs": int(c[4])}}
+                "work_per_step": {"s3_pairs": int(c[0]), "bnb_pairs": int(c[1]), "gn_pairs": int(c[2]), "gn_iterations": int(c[3]), "ncc2_pairs": int(c[4]), "gn_tile_builds": int(c[5])}}
         if world == 1 and not args.no_cpu_baseline:
             secs, ttoed, tst, kind, nm = cpu_reference_frame(cal, *base[0])
             secs2, ttoed2, tst2, _, _ = cpu_reference_frame(cal, *base[1 % len(base)])

@@ -19,6 +19,7 @@
 #include "ebvo_internal.cuh"
 #include <math_constants.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace ebvo {
 
@@ -604,14 +605,16 @@ __global__ void __launch_bounds__(128) shift_kernel(DevBatch b, DevParams p, int
 }
 
 // ------------------------------------------------------------------------------------------------------
-// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  One warp per live pool slot.
-// Lane l owns samples s = l + 32 m (m < 4, s < 98): s < 49 -> "+" patch cell s, else "-" patch cell s - 49
-// (cell (i,j) = (t/7-3, t%7-3)).  Three arithmetic variants share this structure:
-//   gn_mixed_kernel (default)  image channel + residuals exactly as the reference (FP64 blend rounded to float,
-//                              FP64 residual and sums); the two Sobel channels, Huber weights and per-lane partial
-//                              products in FP32 (they only scale the step: measured effect < 1e-6 px)
-//   gn64_kernel                everything as the reference (FP64), for strict comparisons
-//   gn32_kernel                everything FP32: fastest, 0.02 % of the mates move by > 1e-3 px (non-converging GN)
+// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  Three kernels (ebvo_params.gn_mode):
+//   gn_tile64_kernel (0, default)  reference arithmetic (FP64 blends rounded to float, FP64 residuals / weights /
+//                              normal equations); one warp per LEFT EDGE, right-view samples served from
+//                              warp-private shared-memory tiles
+//   gn64_kernel (1)            the same arithmetic, one warp per candidate, samples gathered from global memory
+//                              (the simple form; kept as the cross-check of the tiled kernel)
+//   gn32_kernel (2)            everything FP32: 0.02 % of the mates move by > 1e-3 px (non-converging GN); opt-in
+// Gauss-Newton sequences that do not converge amplify last-bit differences by up to ~1e8, and the clusterer that
+// follows decides nearest-neighbour merges among candidates that converged to the same point within ~1e-6 px, so
+// anything less than double precision in ANY channel changes 0.05 % of the final mates' orientations.
 // ------------------------------------------------------------------------------------------------------
 // include/utility.h:159-172 on an 8-bit image viewed as CV_32F (convertTo is exact): clamped sampler, FP32 blend
 __device__ __forceinline__ void cell_of(double x, int n, int& x0, int& x1, float& a)
@@ -715,82 +718,210 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
     b.c_score[o] = score; b.c_conf[o] = conf;
 }
 
-__global__ void __launch_bounds__(32 * WPB, 6) gn_mixed_kernel(DevBatch b, DevParams p)
+// ------------------------------------------------------------------------------------------------------
+// gn_tile64_kernel (default).  One warp per LEFT EDGE (dynamic chunks of the frame's left-edge list), looping over
+// that edge's surviving candidates: the left patches are sampled once per left edge, not once per candidate.
+// Lanes 0-15 own the "+" patch, lanes 16-31 the "-" patch (cell t = hl + 16 m, m < 4, t < 49), so the two patch
+// means reduce inside half-warps.  Per candidate each half-warp stages the pixels its patch can reach while alpha
+// stays within +-R px of the build position into a warp-private tile: a double2 plane {gx, gy} and a double plane
+// I (no conversion instructions inside the iteration).  Coordinates beyond the image read the clamped border
+// pixel, which is what util_bilinear_Sample_F's coordinate clamp produces (utility.h:161-166).  The four corners
+// of a sample are then 4 LDS.128 + 4 LDS.64 instead of 12 scattered global loads (the gather kernel is bound by
+// L1 wavefronts: ~10 cache lines per load instruction).  The tile is rebuilt when alpha leaves the +-R window
+// (3 % of the candidates).  Arithmetic: FP64 four-corner blends of I, gx and gy, each rounded to float
+// (util_bilinear_Sample_F returns float); FP64 residuals, Huber weights and normal equations; the divisions by
+// 49, by |r| and by H are evaluated by reciprocal + FMA correction (within 1 ulp; same class as the summation
+// order).  Measured against the reference: identical to gn64_kernel (max 9e-7 px at the GN stage on 128 913
+// candidates, 6e-8 px on the final mates).
+// ------------------------------------------------------------------------------------------------------
+constexpr int GN_CHUNK = 2;        // left edges fetched per atomic
+constexpr int GN_R = 5;            // tile reach along the epipolar direction (px) before a rebuild
+
+__device__ __forceinline__ double half_sum(double v)   // sum over the 16 lanes of a half-warp, result in every lane
 {
-    const int f = blockIdx.y, lane = threadIdx.x & 31;
-    const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy, 0}
-    const int* c_owner = b.c_owner + (size_t)f * b.P;
-    const int used = min(b.poolUsed[f], b.P);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// a / 49 correctly rounded without the division sequence (Markstein: q = a*y, r = a - 49 q exactly, q + r*y)
+__device__ __forceinline__ double div49(double a)
+{
+    const double y = 1.0 / 49.0;
+    const double q = a * y;
+    const double r = fma(-49.0, q, a);
+    return fma(r, y, q);
+}
+// 1 / x to ~1 ulp: MUFU.RCP64H seed (about 20 bits) + two Newton steps; x is a finite positive normal number here
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// a / b (b finite, positive, normal) correctly rounded in all but pathological cases, without the division sequence
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    const double y = rcp_fast(b);
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+template <int GT64_MAXPX, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, DevParams p, int Rmax)
+{
+    __shared__ double2 s_tile[WPB][2][GT64_MAXPX + GT64_MAXPX / 2];   // per sub-tile: {gx, gy} plane, then the I plane
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hw = lane >> 4, hl = lane & 15;
+    double2* tG = s_tile[w][hw];
+    double* tI = reinterpret_cast<double*>(tG + GT64_MAXPX);
+    const int imgL = 2 * f;
+    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
+    const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy}
+    const int nL = b.nE[imgL];
     const int W = b.W, H = b.H;
-    const float huber = (float)p.gn_huber;
-    unsigned long long npairs = 0, niters = 0;
-    for (int q = blockIdx.x * WPB + (threadIdx.x >> 5); q < used; q += gridDim.x * WPB) {
-        const int i = c_owner[q];
-        if (i < 0) continue;
-        GnSetup g;
-        gn_setup(b, f, i, q, lane, g);
-        const float fdx = (float)g.dirx, fdy = (float)g.diry;
-        double alpha = 0.0, score = 0.0, conf = 0.0;
-        for (int it = 0; it < p.gn_max_iter; ++it) {
-            const double sx = alpha * g.dirx, sy = alpha * g.diry;
-            double vi[4];
-            float vg[4];
-            double sRp = 0, sRm = 0;
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    const int* ccount = b.ccount + (size_t)f * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
+    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+    unsigned long long* cursor = b.counters + (size_t)f * 8 + 7;
+    const double huber = p.gn_huber;
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
+    unsigned long long npairs = 0, niters = 0, nbuilds = 0;
+    for (;;) {
+        int i0 = 0;
+        if (lane == 0) i0 = (int)atomicAdd(cursor, (unsigned long long)GN_CHUNK);
+        i0 = __shfl_sync(FULL, i0, 0);
+        if (i0 >= nL) break;
+        const int i1 = min(i0 + GN_CHUNK, nL);
+        for (int i = i0; i < i1; ++i) {
+            const int n = ccount[i];
+            if (n == 0) continue;
+            const int st = cstart[i];
+            // ---- per left edge: geometry, centred left samples, tile shape ----
+            const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+            const double dirx = ln[3], diry = ln[4], st_ = ln[5], ct_ = ln[6];
+            const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
+            const double side = 7 / 2.0 + 1.0;                               // :1171
+            const double cx = hw ? st_ * side : -st_ * side;                 // +-n*side, n = (-t.y, t.x) (:1169-1170)
+            const double cy = hw ? -ct_ * side : ct_ * side;
+            double rx[4], ry[4], Lc[4];
+            double sumL = 0;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                vi[m] = 0.0; vg[m] = 0.f;
-                const int s = lane + 32 * m;
-                if (s < 98) {
-                    int x0, y0, dx1, dy1;
-                    double a, bb;
-                    cell_magic(g.Bx[m] + sx, W, 1, x0, dx1, a);
-                    cell_magic(g.By[m] + sy, H, W, y0, dy1, bb);
-                    const uint2* c00 = PK + (y0 * W + x0);
-                    const uint2 u00 = __ldg(c00), u10 = __ldg(c00 + dx1), u01 = __ldg(c00 + dy1), u11 = __ldg(c00 + dy1 + dx1);
-                    // image channel: FP64 blend rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172)
-                    const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
-                    vi[m] = round_to_float(w00 * pk_i(u00) + w10 * pk_i(u10) + w01 * pk_i(u01) + w11 * pk_i(u11));
-                    // Sobel channels: FP32 blend of the exact half-precision samples
-                    const float af = (float)a, bf = (float)bb;
-                    const float f00 = (1.f - af) * (1.f - bf), f10 = af * (1.f - bf), f01 = (1.f - af) * bf, f11 = af * bf;
-                    const float2 g00 = __half22float2(*reinterpret_cast<const __half2*>(&u00.y)), g10 = __half22float2(*reinterpret_cast<const __half2*>(&u10.y));
-                    const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&u01.y)), g11 = __half22float2(*reinterpret_cast<const __half2*>(&u11.y));
-                    const float gx = f00 * g00.x + f10 * g10.x + f01 * g01.x + f11 * g11.x;
-                    const float gy = f00 * g00.y + f10 * g10.y + f01 * g01.y + f11 * g11.y;
-                    vg[m] = -gx * fdx + gy * fdy;                                    // :1240
-                    if (s >= 49) sRm += vi[m]; else sRp += vi[m];
-                }
+                const int t = hl + 16 * m;
+                const int ii = t / 7 - 3, jj = t % 7 - 3;
+                rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
+                Lc[m] = 0.0;
+                if (t < 49) { Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m]; }
             }
-            warp_sum2(sRp, sRm);
-            const double mRp = sRp / 49.0, mRm = sRm / 49.0;
-            float Hf = 0.f, bf_ = 0.f, cf = 0.f;
+            sumL = half_sum(sumL);
+            const double mL = sumL / 49.0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int s = lane + 32 * m;
-                if (s < 98) {
-                    const float r = (float)(g.Lc[m] - (vi[m] - ((s >= 49) ? mRm : mRp)));   // FP64 residual, then float
-                    const float ar = fabsf(r);
-                    const float wgt = (ar <= huber) ? 1.f : __fdividef(huber, ar);
-                    const float wg = wgt * vg[m];
-                    Hf = fmaf(wg, vg[m], Hf); bf_ = fmaf(wg, r, bf_); cf = fmaf(wgt * r, r, cf);
-                }
+            for (int m = 0; m < 4; ++m) if (hl + 16 * m < 49) Lc[m] -= mL;
+            // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
+            const double hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
+            int R = Rmax, TWp, THp;
+            for (;;) {
+                TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
+                THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
+                // row pitch in 8-byte words: residues 0, +-1, +-2 and 8 (mod 16 banks) fold neighbouring rows onto the same banks
+                while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
+                if (TWp * THp <= GT64_MAXPX || R == 0) break;
+                --R;
             }
-            double Hh = (double)Hf, bb_ = (double)bf_, cost = (double)cf;   // per-lane partials (<= 4 terms) -> FP64 reduction
-            warp_sum3(Hh, bb_, cost);
-            ++niters;
-            if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
-            const double delta = -bb_ / Hh;
-            alpha += delta;
-            if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
-                const double rms = sqrt(cost / 98.0);
-                score = rms; conf = exp(-rms / p.gn_huber);
-                break;
+            const double ex = R * fabs(dirx) + hext, ey = R * fabs(diry) + hext;
+            const int npx = TWp * THp;
+            const float invTW = 1.0f / (float)TWp;
+            const double Rv = (double)R - 1e-6;
+
+            for (int k = 0; k < n; ++k) {
+                const int q = st + k;
+                const double xr = c_x[q], yr = c_y[q];
+                const double xc = xr + cx, yc = yr + cy;      // patch centre at alpha = 0 (:1203-1204)
+                double alpha = 0.0, score = 0.0, conf = 0.0, alpha0 = CUDART_NAN;
+                int ox = 0, oy = 0;
+                for (int it = 0; it < p.gn_max_iter; ++it) {
+                    const double sx = alpha * dirx, sy = alpha * diry;
+                    if (!(fabs(alpha - alpha0) <= Rv)) {
+                        // ---- (re)build this half-warp's sub-tile around the current position ----
+                        alpha0 = alpha;
+                        ox = __double2int_rd((xc + sx) - ex);
+                        oy = __double2int_rd((yc + sy) - ey);
+                        ++nbuilds;
+                        __syncwarp();
+                        for (int e = hl; e < npx; e += 16) {
+                            const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
+                            const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
+                            const uint2 u = __ldg(PK + (Y * W + X));
+                            const float2 gg = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                            tI[e] = (double)(int)(u.x & 0xffffu); tG[e] = make_double2((double)gg.x, (double)gg.y);
+                        }
+                        __syncwarp();
+                    }
+                    double vi[4], vg[4];
+                    double sR = 0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        vi[m] = 0.0; vg[m] = 0.0;
+                        if (hl + 16 * m < 49) {
+                            const double x = (xc + rx[m]) + sx, y = (yc + ry[m]) + sy;
+                            const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
+                            const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
+                            const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
+                            const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
+                            const int o = yi * TWp + xi;
+                            // FP64 blends rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172) per channel
+                            const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
+                            const double2 g00 = tG[o], g10 = tG[o + 1], g01 = tG[o + TWp], g11 = tG[o + TWp + 1];
+                            vi[m] = round_to_float(w00 * tI[o] + w10 * tI[o + 1] + w01 * tI[o + TWp] + w11 * tI[o + TWp + 1]);
+                            const double gx = round_to_float(w00 * g00.x + w10 * g10.x + w01 * g01.x + w11 * g11.x);
+                            const double gy = round_to_float(w00 * g00.y + w10 * g10.y + w01 * g01.y + w11 * g11.y);
+                            vg[m] = -gx * dirx + gy * diry;                                   // :1240
+                            sR += vi[m];
+                        }
+                    }
+                    sR = half_sum(sR);
+                    const double mR = div49(sR);
+                    double Hh = 0, bb_ = 0, cost = 0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        if (hl + 16 * m < 49) {
+                            const double r = Lc[m] - (vi[m] - mR);
+                            const double gg = vg[m];
+                            const double ar = fabs(r);
+                            const double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
+                            const double wg = wgt * gg;
+                            Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
+                        }
+                    }
+                    warp_sum2(Hh, bb_);
+                    ++niters;
+                    if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+                    const double delta = -div_fast(bb_, Hh);
+                    alpha += delta;
+                    if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+                        cost = warp_sum(cost);
+                        const double rms = sqrt(cost / 98.0);
+                        score = rms; conf = exp(-rms / p.gn_huber);
+                        break;
+                    }
+                }
+                ++npairs;
+                if (lane == 0) {
+                    c_x[q] = xr + alpha * dirx;          // :1350-1352 (moved regardless of validity)
+                    c_y[q] = yr + alpha * diry;
+                    c_score[q] = score; c_conf[q] = conf;
+                }
             }
         }
-        ++npairs;
-        if (lane == 0) gn_store(b, f, q, g, alpha, score, conf);
     }
-    if (lane == 0 && npairs) { atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters); }
+    if (lane == 0 && npairs) {
+        atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters);
+        atomicAdd(&b.counters[(size_t)f * 8 + 5], nbuilds);
+    }
 }
 
 __global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams p)
@@ -1270,7 +1401,14 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
     EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 0)));
     if (p.gn_mode == 2) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
-    else EBVO_KERNEL(prof, "gn", st, (gn_mixed_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    else {
+        static bool attr = false;
+        if (!attr) {   // 48 KB of tiles per CTA: ask for the large shared-memory carve-out so that 4 CTAs fit per SM
+            cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr = true;
+        }
+        EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, GN_R)));
+    }
 }
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {

@@ -62,8 +62,8 @@ typedef struct ebvo_params {
     double gn_huber_delta;            /* 3.0 */
     double toed_mag_thresh;           /* "I_grad_mag <= 2" cpu_toed.cpp:406 */
     int32_t toed_border;              /* 10, cpu_toed.cpp:401-403,553 */
-    int32_t gn_mode;                  /* Gauss-Newton arithmetic: 0 (default) image channel + residuals as the reference (FP64),
-                                         Sobel channels/weights FP32; 1: all FP64; 2: all FP32 (fastest, looser parity) */
+    int32_t gn_mode;                  /* Gauss-Newton kernel: 0 (default) reference arithmetic (FP64), shared-memory tiles;
+                                         1: the same arithmetic, global-memory gathers (cross-check); 2: all FP32 (looser parity) */
 } ebvo_params;
 
 /* One finalised stereo mate: final_stereo_edge_pair.left_edge / right_edge, include/Dataset.h:291-309. */
