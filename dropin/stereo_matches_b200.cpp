@@ -1,0 +1,208 @@
+// Drop-in replacement for the two heavy members of the reference class Stereo_Matches
+//   Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr, Stereo_Edge_Pairs&, size_t, Timing_Statistics&)
+//   void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs&, std::vector<final_stereo_edge_pair>&)
+// (reference src/Stereo_Matches.cpp:1360-1540 and :1578-1653), compiled against the reference's OWN headers
+// (include/Stereo_Matches.h, Dataset.h, Stereo_Iterator.h, toed/cpu_toed.hpp - unmodified), so the call sites in
+// Pipeline::get_Stereo_Edge_Correspondences (src/Pipeline.cpp:116-131) compile and behave unchanged.  The work is
+// done on the GPU through the C ABI (include/ebvo_b200.h: ebvo_stereo_match, ebvo_edge_patches).  No CPU fallback.
+//
+// How a maintainer links it (no reference source is edited):
+//   * add this file and libebvo_b200.so to the library;
+//   * compile src/Stereo_Matches.cpp with
+//       -Dget_Stereo_Edge_Pairs=get_Stereo_Edge_Pairs_cpu -Dfinalize_stereo_edge_mates=finalize_stereo_edge_mates_cpu
+//     (CMake: set_source_files_properties(Stereo_Matches.cpp PROPERTIES COMPILE_DEFINITIONS "...")), which keeps the
+//     CPU bodies under other names and leaves every other member (Find_Stereo_GT_Locations, get_Stereo_Edge_GT_Pairs,
+//     the writers, the individual apply_* filters) exactly as it is.
+// dropin/Makefile does precisely this with the reference sources in place and tests/test_gpu_dropin.py runs the result.
+//
+// Scope: the no-GT branch (KITTI, EuRoC, ETH3D-SLAM: Dataset.cpp:120-148), SIFT-off: the SIFT
+// gate, BNB-SIFT and the finalisation descriptors are not computed (descriptor pairs are left empty).  With has_gt()
+// the per-stage Evaluate_Stereo_Edge_Correspondences metrics (diagnostics) are not produced: the returned
+// Frame_Evaluation_Metrics is empty, the mates are the same.
+//
+// State left in Stereo_Edge_Pairs, as after the reference's remove_empty_clusters (:1543-1576): only matched left
+// edges remain; per remaining edge one EdgeCluster whose center_edge is the mate, refine_final_scores = {NCC}.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <random>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+#include <opencv2/opencv.hpp>
+#include <Eigen/Dense>
+
+#include "Stereo_Matches.h"      // the reference header
+#include "ebvo_b200.h"
+#include "ebvo_dropin_common.hpp"
+
+namespace {
+
+void log_error(const char* what, ebvo_ctx* c, int rc)
+{
+    std::printf("\033[1;31m[ERROR] %s failed (%d): %s\033[0m\n", what, rc, c ? ebvo_last_error(c) : "");
+}
+
+ebvo_calib calib_of(Dataset& d)
+{
+    ebvo_calib c;
+    const Eigen::Matrix3d Kl = d.get_left_calib_matrix(), Kr = d.get_right_calib_matrix(), R = d.get_relative_rot_left_to_right();
+    const Eigen::Vector3d T = d.get_relative_transl_left_to_right();
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) { c.Kl[3 * i + j] = Kl(i, j); c.Kr[3 * i + j] = Kr(i, j); c.R21[3 * i + j] = R(i, j); }
+        c.T21[i] = T(i);
+    }
+    return c;    // F21 is derived inside the library exactly as Dataset.cpp:102-112 does
+}
+
+std::pair<cv::Mat, cv::Mat> patch_pair(const float* plus49, const float* minus49)
+{
+    cv::Mat p(PATCH_SIZE, PATCH_SIZE, CV_32F), m(PATCH_SIZE, PATCH_SIZE, CV_32F);       // utility.cpp:190-191
+    for (int i = 0; i < PATCH_SIZE; ++i)
+        for (int j = 0; j < PATCH_SIZE; ++j) { p.at<float>(i, j) = plus49[i * PATCH_SIZE + j]; m.at<float>(i, j) = minus49[i * PATCH_SIZE + j]; }
+    return {p, m};
+}
+
+}  // namespace
+
+Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr dataset, Stereo_Edge_Pairs& pairs, size_t frame_idx, Timing_Statistics& timing_statistics)
+{
+    (void)frame_idx; (void)timing_statistics;
+    Frame_Evaluation_Metrics frame_metrics;
+    const StereoFrame& f = *pairs.stereo_frame;
+    const int W = f.left_image.cols, H = f.left_image.rows;
+    const size_t nF = pairs.focused_edge_indices.size();
+    const int nR = (int)f.right_edges.size();
+    const int cap = (int)std::max<size_t>(std::max<size_t>(nF, (size_t)nR), 1);
+    ebvo_ctx* ctx = ebvo_dropin::context(W, H, cap);
+
+    // what the reference's stages leave behind even when nothing survives
+    auto fail_empty = [&]() {
+        pairs.focused_edge_indices.clear(); pairs.GT_locations_from_left_edges.clear(); pairs.veridical_right_edges_indices.clear();
+        pairs.Gamma_in_left_cam_coord.clear(); pairs.Gamma_in_right_cam_coord.clear(); pairs.left_edge_descriptors.clear();
+        pairs.epip_line_coeffs_of_left_edges.clear(); pairs.left_edge_patches.clear(); pairs.matching_edge_clusters.clear();
+        return frame_metrics;
+    };
+    if (!ctx) return fail_empty();
+
+    // inputs: raw images for the NCC stages (:562-563), undistorted ones for Gauss-Newton and finalisation (:1293, :1580)
+    const std::vector<unsigned char> Lraw = ebvo_dropin::packed_u8(f.left_image.data, H, W, f.left_image.step);
+    const std::vector<unsigned char> Rraw = ebvo_dropin::packed_u8(f.right_image.data, H, W, f.right_image.step);
+    const std::vector<unsigned char> Lund = ebvo_dropin::packed_u8(f.left_image_undistorted.data, H, W, f.left_image_undistorted.step);
+    const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(f.right_image_undistorted.data, H, W, f.right_image_undistorted.step);
+    std::vector<ebvo_edge> L(nF), R((size_t)nR);
+    for (size_t i = 0; i < nF; ++i) {                      // the focused left edges, in Stereo_Edge_Pairs order (:192-198)
+        const Edge& e = f.left_edges[pairs.focused_edge_indices[i]];
+        L[i] = ebvo_edge{e.location.x, e.location.y, e.orientation, pairs.focused_edge_indices[i], e.frame_source};
+    }
+    for (int k = 0; k < nR; ++k) {
+        const Edge& e = f.right_edges[k];
+        R[k] = ebvo_edge{e.location.x, e.location.y, e.orientation, k, e.frame_source};
+    }
+    const ebvo_calib calib = calib_of(*dataset);
+    std::vector<ebvo_mate> mates(std::max<size_t>(nF, 1));
+    int n = 0;
+    int rc = ebvo_stereo_match(ctx, &calib, Lraw.data(), Rraw.data(), Lund.data(), Rund.data(), W, H, W, L.data(), (int)nF, R.data(), nR,
+                               nullptr, nullptr, mates.data(), (int)mates.size(), &n);
+    if (rc != EBVO_OK) { log_error("ebvo_stereo_match", ctx, rc); return fail_empty(); }
+
+    // left patches of the matched edges from the RAW left image (apply_NCC_Filtering, :570-576)
+    std::vector<ebvo_edge> Lm((size_t)n);
+    for (int k = 0; k < n; ++k) Lm[k] = L[mates[k].left_index];
+    std::vector<float> pp((size_t)n * 49), pm((size_t)n * 49);
+    if (n > 0) {
+        rc = ebvo_edge_patches(ctx, Lraw.data(), W, H, W, Lm.data(), n, pp.data(), pm.data());
+        if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); return fail_empty(); }
+    }
+
+    // rebuild the per-left-edge containers for the survivors, in left-edge order (the order remove_empty_clusters keeps)
+    const Eigen::Matrix3d F21 = dataset->get_fund_mat_21();
+    std::vector<int> focused((size_t)n);
+    std::vector<cv::Point2d> gt_loc((size_t)n);
+    std::vector<std::vector<int>> veridical((size_t)n);
+    std::vector<Eigen::Vector3d> g_left((size_t)n), g_right((size_t)n), lines((size_t)n);
+    std::vector<std::pair<cv::Mat, cv::Mat>> desc((size_t)n), patches((size_t)n);
+    std::vector<Stereo_Matching_Edge_Clusters> clusters((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        const int i = mates[k].left_index;                 // position in the focused list handed to the matcher
+        focused[k] = pairs.focused_edge_indices[i];
+        if ((size_t)i < pairs.GT_locations_from_left_edges.size()) gt_loc[k] = pairs.GT_locations_from_left_edges[i];
+        if ((size_t)i < pairs.veridical_right_edges_indices.size()) veridical[k] = pairs.veridical_right_edges_indices[i];
+        if ((size_t)i < pairs.Gamma_in_left_cam_coord.size()) g_left[k] = pairs.Gamma_in_left_cam_coord[i];
+        if ((size_t)i < pairs.Gamma_in_right_cam_coord.size()) g_right[k] = pairs.Gamma_in_right_cam_coord[i];
+        const Eigen::Vector3d x(L[i].x, L[i].y, 1.0);     // CalculateEpipolarLine (:10-20)
+        lines[k] = F21 * x;
+        patches[k] = patch_pair(&pp[(size_t)k * 49], &pm[(size_t)k * 49]);
+        EdgeCluster ec;
+        ec.center_edge = Edge(cv::Point2d(mates[k].rx, mates[k].ry), mates[k].rtheta, false, 0);   // :39 / EdgeClusterer.cpp:243
+        ec.center_edge.index = -1;                         // uninitialised in the reference (cpu_toed.hpp:35)
+        ec.contributing_edges.push_back(ec.center_edge);
+        ec.paired_left_edge_index = focused[k];
+        clusters[k].edge_clusters.push_back(ec);
+        clusters[k].refine_final_scores.push_back(mates[k].score);
+        clusters[k].refine_confidences.push_back(0.0);
+        clusters[k].refine_validities.push_back(true);
+    }
+    pairs.focused_edge_indices.swap(focused);
+    pairs.GT_locations_from_left_edges.swap(gt_loc);
+    pairs.veridical_right_edges_indices.swap(veridical);
+    pairs.Gamma_in_left_cam_coord.swap(g_left);
+    pairs.Gamma_in_right_cam_coord.swap(g_right);
+    pairs.left_edge_descriptors.swap(desc);                // SIFT-off: empty descriptor pairs, sized like the reference (:657-658)
+    pairs.epip_line_coeffs_of_left_edges.swap(lines);
+    pairs.left_edge_patches.swap(patches);
+    pairs.matching_edge_clusters.swap(clusters);
+    return frame_metrics;
+}
+
+void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::vector<final_stereo_edge_pair>& final_stereo_edge_pairs)
+{
+    const size_t n = pairs.focused_edge_indices.size();
+    // the reference's consistency check (:1585-1603)
+    if (n != pairs.matching_edge_clusters.size() || n != pairs.Gamma_in_left_cam_coord.size() || n != pairs.Gamma_in_right_cam_coord.size() ||
+        n != pairs.left_edge_patches.size() || n != pairs.left_edge_descriptors.size() || n != pairs.GT_locations_from_left_edges.size()) {
+        std::printf("\033[1;31m[ERROR] Vector sizes are not consistent in finalize_stereo_edge_mates\033[0m\n");
+        return;
+    }
+    final_stereo_edge_pairs.clear();
+    final_stereo_edge_pairs.resize(n);
+    if (n == 0) { std::cout << "Size of finalized stereo edge pairs = 0" << std::endl; return; }
+
+    // right patches of every mate from the UNDISTORTED right image (:1580-1582, :1622), one batched call
+    const cv::Mat& Rimg = pairs.stereo_frame->right_image_undistorted;
+    const int W = Rimg.cols, H = Rimg.rows;
+    std::vector<ebvo_edge> Rm(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Edge& e = pairs.matching_edge_clusters[i].edge_clusters[0].center_edge;
+        Rm[i] = ebvo_edge{e.location.x, e.location.y, e.orientation, (int)i, 0};
+    }
+    std::vector<float> pp(n * 49), pm(n * 49);
+    ebvo_ctx* ctx = ebvo_dropin::context(W, H, (int)n);
+    if (!ctx) { final_stereo_edge_pairs.clear(); return; }
+    const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(Rimg.data, H, W, Rimg.step);
+    const int rc = ebvo_edge_patches(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, pp.data(), pm.data());
+    if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+
+    for (size_t i = 0; i < n; ++i) {
+        final_stereo_edge_pair mate;
+        mate.left_edge = pairs.get_focused_edge_by_Stereo_Edge_Pairs_index(i);
+        mate.right_edge = pairs.matching_edge_clusters[i].edge_clusters[0].center_edge;
+        mate.left_edge_patches = pairs.left_edge_patches[i];
+        mate.right_edge_patches = patch_pair(&pp[i * 49], &pm[i * 49]);
+        mate.left_edge_descriptors = pairs.left_edge_descriptors[i];
+        // right_edge_descriptors: SIFT-off (cv::SIFT is third-party code outside this path) - left empty
+        mate.Gamma_in_left_cam_coord = pairs.Gamma_in_left_cam_coord[i];
+        mate.Gamma_in_right_cam_coord = pairs.Gamma_in_right_cam_coord[i];
+        mate.gt_right_location = pairs.GT_locations_from_left_edges[i];
+        mate.b_is_TP = cv::norm(mate.right_edge.location - pairs.GT_locations_from_left_edges[i]) <= DIST_TO_GT_THRESH;   // :1645
+        final_stereo_edge_pairs[i] = mate;
+    }
+    std::cout << "Size of finalized stereo edge pairs = " << final_stereo_edge_pairs.size() << std::endl;
+}
