@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 
 FP32_LANES_PER_SM = 128
 TOED_FLOP_PER_PX = 1636.0      # 818 MAC per input pixel, separable form
+GN_FLOP_PER_ITER = 5300.0      # 98 samples x 54 FP64 flop per Gauss-Newton iteration
+GN_DRAM_BYTES_PER_FRAME = 78.9e6 / 8   # ncu dram__bytes_{read,write}.sum of one gn launch over 8 frames (profiles/r01_ncu_gn_tile64.txt)
 
 
 def read_peaks():
@@ -230,22 +232,25 @@ def main():
         value = frames_total / (ms_total / 1e3)
         e2e_value = frames_total / (e2e_ms / 1e3)
         # dominant kernel + roofline.  Algorithmic work per unit (DESIGN.md section 5 / SURVEY.md 8(d)):
-        #   TOED        1636 flop per input pixel (818 MAC, separable dense form) x W*H x 2 views
-        #   GN          4.5 kflop per Gauss-Newton iteration (98 samples x 3 channels bilinear + residual/normal equations)
-        #   NCC         2.3 kflop per scored pair
-        # Bound = FP32 pipe (no dense contraction on this path, tensor cores unused); HBM traffic is far below the
-        # compute time for every kernel (the per-frame working set is L2-resident), see `hbm` for the byte side.
+        #   GN    5.3 kflop FP64 per Gauss-Newton iteration (98 samples x 54 flop: 3 four-corner blends, weights, residual,
+        #         Huber-weighted normal equations), all in double as the reference computes it -> bound = FP64 pipe
+        #   TOED  1636 flop FP32 per input pixel (818 MAC, separable dense form) x W*H x 2 views      -> bound = FP32 pipe
+        #   NCC   2.3 kflop per scored pair
+        # No step is a dense contraction (tensor cores unused) and HBM traffic is far below the compute time of every
+        # kernel (the per-frame working set is L2-resident): `hbm` gives the byte side, `traffic` the DRAM bytes ncu measured.
         ksum = sum(v[0] for v in ktimes.values())
         dom = max(ktimes.items(), key=lambda kv: kv[1][0])
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         fp32_peak = sms * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12      # TFLOP/s, nominal FP32 FMA peak at max clock
+        fp64_peak = fp32_peak / 2                                          # 64 FP64 lanes per SM per clock (measured: ncu pipe_fp64)
         c = counters.sum(axis=0)
         toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_orient", (0, 1))[0]
         toed_flops = TOED_FLOP_PER_PX * W * H * 2 * B * args.steps
         gn_name = next((k for k in ("gn", "gn64", "gn32") if k in ktimes), None)
         gn_ms = ktimes[gn_name][0] if gn_name else 0.0
-        gn_flops = 4500.0 * float(c[3]) * args.steps
+        gn_flops = GN_FLOP_PER_ITER * float(c[3]) * args.steps
+        gn_peak = fp32_peak if gn_name == "gn32" else fp64_peak
         ncc_ms = ktimes.get("patch", (0, 1))[0] + ktimes.get("ncc_bnb", (0, 1))[0]
         ncc_flops = 2300.0 * float(c[0]) * args.steps
 
@@ -257,22 +262,29 @@ def main():
         match_bytes = (2 * W * H * 2 + 2 * 4 * W * H) * B + 24.0 * (nL.sum() + nR.sum()) + 4.0 * c[0] + 64.0 * nM.sum()
         dom_is_gn = dom[0] == gn_name
         ach = tf(gn_flops, gn_ms) if dom_is_gn else tf(toed_flops, toed_ms)
-        roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach / fp32_peak if ach else None, "traffic": None,
-                "peak_source": f"nominal FP32 FMA peak = {sms} SM x 128 lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock); "
-                               "tensor cores unused (no dense contraction on this path)",
+        peak = gn_peak if dom_is_gn else fp32_peak
+        roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": ("fp64" if gn_peak == fp64_peak else "fp32") if dom_is_gn else "fp32",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
+                # DRAM bytes of one launch of the dominant kernel: ncu --set full capture profiles/r01_ncu_gn_tile64.txt
+                # (dram__bytes_read.sum + dram__bytes_write.sum = 78.9 MB for 8 frames), scaled to this batch
+                "traffic": GN_DRAM_BYTES_PER_FRAME * B if dom_is_gn else None,
+                "algorithmic_flop_per_launch": gn_flops / args.steps if dom_is_gn else toed_flops / args.steps,
+                "avg_launch_ms": (gn_ms if dom_is_gn else toed_ms) / args.steps,
+                "peak_source": f"nominal {'FP64' if peak == fp64_peak else 'FP32'} FMA peak = {sms} SM x {64 if peak == fp64_peak else 128} lanes x 2 x sm_max_mhz "
+                               f"({peak_src} MEASURED_PEAKS.json clock); neither HBM nor tensor bound: no dense contraction on this path (tensor cores "
+                               "unused) and the kernel's DRAM traffic is 0.1 % of HBM peak",
                 "dominant_kernel_by_time": dom[0], "dominant_kernel_share": dom[1][0] / ksum if ksum else None,
-                "per_stage": {"toed": {"algorithmic_flop_per_px": TOED_FLOP_PER_PX, "achieved_tflops": tf(toed_flops, toed_ms),
+                "per_stage": {"toed": {"bound": "fp32", "algorithmic_flop_per_px": TOED_FLOP_PER_PX, "achieved_tflops": tf(toed_flops, toed_ms),
                                        "frac": (tf(toed_flops, toed_ms) or 0) / fp32_peak},
-                              "gauss_newton": {"algorithmic_flop_per_iteration": 4500.0, "achieved_tflops": tf(gn_flops, gn_ms),
-                                               "frac": (tf(gn_flops, gn_ms) or 0) / fp32_peak},
-                              "ncc": {"algorithmic_flop_per_pair": 2300.0, "achieved_tflops": tf(ncc_flops, ncc_ms),
+                              "gauss_newton": {"bound": "fp64" if gn_peak == fp64_peak else "fp32", "algorithmic_flop_per_iteration": GN_FLOP_PER_ITER,
+                                               "achieved_tflops": tf(gn_flops, gn_ms), "frac": (tf(gn_flops, gn_ms) or 0) / gn_peak},
+                              "ncc": {"bound": "fp32", "algorithmic_flop_per_pair": 2300.0, "achieved_tflops": tf(ncc_flops, ncc_ms),
                                       "frac": (tf(ncc_flops, ncc_ms) or 0) / fp32_peak}},
                 "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "matching_algorithmic_bytes_per_step": float(match_bytes),
                         "matching_algorithmic_gbs": float(match_bytes) / ((ksum - toed_ms) / args.steps / 1e3) / 1e9 if ksum > toed_ms else None}}
         line = {"metric": "stereo frames/s (TOED+NCC stereo match) at KITTI 1241x376", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 mixed", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TOED) / f64 (matching)", "data": "synthetic",
                 "config": {"workload": "configs[2]: KITTI-shape 1241x376 synthetic stereo batch, TOED x2 + stereo match S1-S13 (SIFT-off)",
                            "frames_per_gpu_per_step": B, "distinct_frames": len(base), "l2": "batch inputs (%.0f MB u8 images + per-frame "
                            "intermediates) exceed the 126 MB L2" % (2 * B * W * H / 1e6),

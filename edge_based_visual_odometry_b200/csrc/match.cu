@@ -734,7 +734,7 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 // order).  Measured against the reference: identical to gn64_kernel (max 9e-7 px at the GN stage on 128 913
 // candidates, 6e-8 px on the final mates).
 // ------------------------------------------------------------------------------------------------------
-constexpr int GN_CHUNK = 2;        // left edges fetched per atomic
+constexpr int GN_CHUNK = 8;        // pool slots fetched per atomic
 constexpr int GN_R = 5;            // tile reach along the epipolar direction (px) before a rebuild
 
 __device__ __forceinline__ double half_sum(double v)   // sum over the 16 lanes of a half-warp, result in every lane
@@ -770,75 +770,86 @@ __device__ __forceinline__ double div_fast(double a, double b)
     return fma(r, y, q);
 }
 template <int GT64_MAXPX, int MINB>
-__global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, DevParams p, int Rmax)
+__global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
 {
     __shared__ double2 s_tile[WPB][2][GT64_MAXPX + GT64_MAXPX / 2];   // per sub-tile: {gx, gy} plane, then the I plane
-    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int hw = lane >> 4, hl = lane & 15;
     double2* tG = s_tile[w][hw];
     double* tI = reinterpret_cast<double*>(tG + GT64_MAXPX);
-    const int imgL = 2 * f;
-    const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
-    const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy}
-    const int nL = b.nE[imgL];
     const int W = b.W, H = b.H;
-    const int* cstart = b.cstart + (size_t)f * b.E;
-    const int* ccount = b.ccount + (size_t)f * b.E;
-    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
-    double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
-    unsigned long long* cursor = b.counters + (size_t)f * 8 + 7;
     const double huber = p.gn_huber;
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
-    unsigned long long npairs = 0, niters = 0, nbuilds = 0;
-    for (;;) {
-        int i0 = 0;
-        if (lane == 0) i0 = (int)atomicAdd(cursor, (unsigned long long)GN_CHUNK);
-        i0 = __shfl_sync(FULL, i0, 0);
-        if (i0 >= nL) break;
-        const int i1 = min(i0 + GN_CHUNK, nL);
-        for (int i = i0; i < i1; ++i) {
-            const int n = ccount[i];
-            if (n == 0) continue;
-            const int st = cstart[i];
-            // ---- per left edge: geometry, centred left samples, tile shape ----
-            const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
-            const double dirx = ln[3], diry = ln[4], st_ = ln[5], ct_ = ln[6];
-            const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
-            const double side = 7 / 2.0 + 1.0;                               // :1171
-            const double cx = hw ? st_ * side : -st_ * side;                 // +-n*side, n = (-t.y, t.x) (:1169-1170)
-            const double cy = hw ? -ct_ * side : ct_ * side;
+    // Persistent CTAs: every warp walks all frames (starting at a CTA-dependent one) and pulls chunks of GN_CHUNK
+    // consecutive pool slots from the frame's cursor, so the only tail is at the very end of the launch; a left edge
+    // with 40 candidates is spread over several warps instead of serialising 800 iterations on one.
+    const int f0 = (int)(((long long)blockIdx.x * nFrames) / gridDim.x);
+    for (int ff = 0; ff < nFrames; ++ff) {
+        const int f = (f0 + ff) % nFrames;
+        const int imgL = 2 * f;
+        const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
+        const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy}
+        const int* c_owner = b.c_owner + (size_t)f * b.P;
+        double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
+        double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+        unsigned long long* cursor = b.counters + (size_t)f * 8 + 7;
+        const int used = min(b.poolUsed[f], b.P);
+        unsigned long long npairs = 0, niters = 0, nbuilds = 0;
+        for (;;) {
+            int q0 = 0;
+            if (lane == 0) q0 = (int)atomicAdd(cursor, (unsigned long long)GN_CHUNK);
+            q0 = __shfl_sync(FULL, q0, 0);
+            if (q0 >= used) break;
+            const int q1 = min(q0 + GN_CHUNK, used);
+            // per-left-edge state, recomputed when the owner of the slot changes (slots of one left edge are contiguous)
+            int owner = -1;
+            double dirx = 0, diry = 0, cx = 0, cy = 0, ex = 0, ey = 0, Rv = 0;
             double rx[4], ry[4], Lc[4];
-            double sumL = 0;
+            int TWp = 0, THp = 0, npx = 0;
+            float invTW = 0.f;
+            for (int q = q0; q < q1; ++q) {
+                const int i = c_owner[q];
+                if (i < 0) continue;          // dead slot (dropped by NCC / best-nearly-best)
+                if (i != owner) {
+                    owner = i;
+                    // ---- per left edge: geometry, centred left samples, tile shape ----
+                    const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+                    dirx = ln[3]; diry = ln[4];
+                    const double st_ = ln[5], ct_ = ln[6];
+                    const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
+                    const double side = 7 / 2.0 + 1.0;                               // :1171
+                    cx = hw ? st_ * side : -st_ * side;                              // +-n*side, n = (-t.y, t.x) (:1169-1170)
+                    cy = hw ? -ct_ * side : ct_ * side;
+                    double sumL = 0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int t = hl + 16 * m;
-                const int ii = t / 7 - 3, jj = t % 7 - 3;
-                rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
-                Lc[m] = 0.0;
-                if (t < 49) { Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m]; }
-            }
-            sumL = half_sum(sumL);
-            const double mL = sumL / 49.0;
+                    for (int m = 0; m < 4; ++m) {
+                        const int t = hl + 16 * m;
+                        const int ii = t / 7 - 3, jj = t % 7 - 3;
+                        rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
+                        Lc[m] = 0.0;
+                        if (t < 49) { Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m]; }
+                    }
+                    sumL = half_sum(sumL);
+                    const double mL = sumL / 49.0;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) if (hl + 16 * m < 49) Lc[m] -= mL;
-            // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
-            const double hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
-            int R = Rmax, TWp, THp;
-            for (;;) {
-                TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
-                THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
-                // row pitch in 8-byte words: residues 0, +-1, +-2 and 8 (mod 16 banks) fold neighbouring rows onto the same banks
-                while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
-                if (TWp * THp <= GT64_MAXPX || R == 0) break;
-                --R;
-            }
-            const double ex = R * fabs(dirx) + hext, ey = R * fabs(diry) + hext;
-            const int npx = TWp * THp;
-            const float invTW = 1.0f / (float)TWp;
-            const double Rv = (double)R - 1e-6;
-
-            for (int k = 0; k < n; ++k) {
-                const int q = st + k;
+                    for (int m = 0; m < 4; ++m) if (hl + 16 * m < 49) Lc[m] -= mL;
+                    // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
+                    const double hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
+                    int R = Rmax;
+                    for (;;) {
+                        TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
+                        THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
+                        // row pitch in 8-byte words: residues 0, +-1, +-2 and 8 (mod 16 banks) fold neighbouring rows onto the same banks
+                        while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
+                        if (TWp * THp <= GT64_MAXPX || R == 0) break;
+                        --R;
+                    }
+                    ex = R * fabs(dirx) + hext; ey = R * fabs(diry) + hext;
+                    npx = TWp * THp;
+                    invTW = 1.0f / (float)TWp;
+                    Rv = (double)R - 1e-6;
+                }
+                {
                 const double xr = c_x[q], yr = c_y[q];
                 const double xc = xr + cx, yc = yr + cy;      // patch centre at alpha = 0 (:1203-1204)
                 double alpha = 0.0, score = 0.0, conf = 0.0, alpha0 = CUDART_NAN;
@@ -915,12 +926,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
                     c_y[q] = yr + alpha * diry;
                     c_score[q] = score; c_conf[q] = conf;
                 }
+                }
             }
         }
-    }
-    if (lane == 0 && npairs) {
-        atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters);
-        atomicAdd(&b.counters[(size_t)f * 8 + 5], nbuilds);
+        if (lane == 0 && npairs) {
+            atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters);
+            atomicAdd(&b.counters[(size_t)f * 8 + 5], nbuilds);
+        }
     }
 }
 
@@ -1407,7 +1419,8 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
             cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr = true;
         }
-        EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, GN_R)));
+        if (!g_sms) warp_grid(1);
+        EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<g_sms * 4, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
     }
 }
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
