@@ -72,6 +72,9 @@ struct ebvo_ctx {
     int stageNL = 0;
     int curFrames = 0;
     std::vector<int> h_counts;
+    // pipelined batch call: copy-in / copy-out streams and per-sub-batch events
+    cudaStream_t stIn = nullptr, stOut = nullptr;
+    std::vector<cudaEvent_t> evIn, evDone;
 };
 
 namespace {
@@ -374,6 +377,10 @@ void ebvo_destroy(ebvo_ctx* ctx)
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->d_descL) cudaFree(ctx->d_descL);
     if (ctx->d_descR) cudaFree(ctx->d_descR);
+    for (cudaEvent_t e : ctx->evIn) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->evDone) cudaEventDestroy(e);
+    if (ctx->stIn) cudaStreamDestroy(ctx->stIn);
+    if (ctx->stOut) cudaStreamDestroy(ctx->stOut);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -502,6 +509,29 @@ int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_r
     return download_mates(ctx, 1, out, cap, n_mates);
 }
 
+// The same device view restricted to frames [f0, f0 + n): every per-image / per-frame base pointer advanced, so that
+// the kernels (which index frames from 0) work on a sub-batch while copies of other sub-batches are in flight.
+static DevBatch frame_view(const DevBatch& b, int f0, int n)
+{
+    DevBatch v = b;
+    const size_t i0 = 2 * (size_t)f0, F0 = (size_t)f0, E = (size_t)b.E, P = (size_t)b.P;
+    v.nFrames = n; v.nImages = 2 * n;
+    v.raw += i0 * b.imgStride; v.und += i0 * b.imgStride;
+    v.mask += i0 * b.maskStride; v.sp += i0 * b.spStride; v.rowcnt += i0 * b.rowStride; v.rowoff += i0 * b.rowStride;
+    v.coords += i0 * E; v.ex += i0 * E; v.ey += i0 * E; v.eth += i0 * E; v.nE += i0; v.nTot += i0;
+    if (v.pkh) v.pkh += F0 * b.gStride;
+    if (v.pk16) v.pk16 += F0 * b.gStride;
+    if (v.pk) v.pk += F0 * b.gStride;
+    v.npatch += i0 * E * 98; v.pflag += i0 * E;
+    v.blk += F0 * b.NB; v.pmax += F0 * b.NB; v.smin += F0 * b.NB;
+    v.lines += F0 * E * 8;
+    v.cstart += F0 * E; v.ccount += F0 * E; v.poolUsed += F0;
+    v.c_ridx += F0 * P; v.c_x += F0 * P; v.c_y += F0 * P; v.c_th += F0 * P; v.c_score += F0 * P; v.c_conf += F0 * P; v.c_owner += F0 * P;
+    v.mates += F0 * E; v.nMates += F0; v.mateFlag += F0 * E;
+    v.counters += F0 * 8;
+    return v;
+}
+
 static int run_frames(ebvo_ctx* ctx, const ebvo_calib* calib, int nFrames, int do_match)
 {
     launch_toed(ctx->b, ctx->dp, 2 * nFrames, ctx->st, &ctx->prof);
@@ -585,14 +615,66 @@ int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* 
 int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
                       int h, int stride, ebvo_mate* out, int cap, int* n_mates)
 {
-    if (!ctx || !calib) return EBVO_ERR_INVALID;
+    if (!ctx || !calib || !L_imgs || !R_imgs) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
     ctx->prof.reset();
-    int rc = ebvo_batch_upload(ctx, n_frames, L_imgs, R_imgs, w, h, stride);
+    int rc = configure(ctx, w, h, n_frames);
     if (rc) return rc;
-    if ((rc = run_frames(ctx, calib, n_frames, 1))) return rc;
+    // Software pipeline over sub-batches of SB frames: the images of sub-batch k+1 are copied in and the mates of
+    // sub-batch k-1 copied out while the kernels of sub-batch k run (three streams, events in between).
+    const int SB = 32, nsb = (n_frames + SB - 1) / SB;
+    if (!ctx->stIn) { CK(cudaStreamCreateWithFlags(&ctx->stIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->stOut, cudaStreamNonBlocking)); }
+    while ((int)ctx->evIn.size() < nsb) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ctx->evIn.push_back(a); ctx->evDone.push_back(b);
+    }
+    const DevBatch& b = ctx->b;
+    double F21[9];
+    ebvo_fundamental(calib, F21, nullptr);
+    ctx->h_counts.assign(n_frames, 0);
+    auto upload = [&](int k) -> int {
+        const int f0 = k * SB, f1 = std::min(n_frames, f0 + SB);
+        for (int f = f0; f < f1; ++f) {
+            CK(cudaMemcpy2DAsync(ctx->d_raw + (size_t)(2 * f) * b.imgStride, b.pitch, L_imgs[f], stride, b.W, b.H, cudaMemcpyHostToDevice, ctx->stIn));
+            CK(cudaMemcpy2DAsync(ctx->d_raw + (size_t)(2 * f + 1) * b.imgStride, b.pitch, R_imgs[f], stride, b.W, b.H, cudaMemcpyHostToDevice, ctx->stIn));
+        }
+        CK(cudaEventRecord(ctx->evIn[k], ctx->stIn));
+        return EBVO_OK;
+    };
+    int over = EBVO_OK;
+    auto download = [&](int k) -> int {
+        const int f0 = k * SB, f1 = std::min(n_frames, f0 + SB);
+        CK(cudaStreamWaitEvent(ctx->stOut, ctx->evDone[k], 0));
+        CK(cudaMemcpyAsync(ctx->h_counts.data() + f0, b.nMates + f0, sizeof(int) * (f1 - f0), cudaMemcpyDeviceToHost, ctx->stOut));
+        CK(cudaStreamSynchronize(ctx->stOut));
+        for (int f = f0; f < f1; ++f) {
+            const int n = ctx->h_counts[f], m = std::min(n, cap);
+            if (n_mates) n_mates[f] = n;
+            if (n > cap) { ctx->err = "output mate buffer too small"; over = EBVO_ERR_CAPACITY; }
+            if (out && m) CK(cudaMemcpyAsync(out + (size_t)f * cap, ctx->d_out + (size_t)f * b.E, sizeof(ebvo_mate) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stOut));
+        }
+        return EBVO_OK;
+    };
+    // the copy-in stream must not overwrite images a previous call's kernels may still read: calls are synchronous at return
+    if ((rc = upload(0))) return rc;
+    for (int k = 0; k < nsb; ++k) {
+        if (k + 1 < nsb && (rc = upload(k + 1))) return rc;
+        const int f0 = k * SB, n = std::min(n_frames, f0 + SB) - f0;
+        const DevBatch v = frame_view(b, f0, n);
+        CK(cudaStreamWaitEvent(ctx->st, ctx->evIn[k], 0));
+        launch_toed(v, ctx->dp, 2 * n, ctx->st, &ctx->prof);
+        launch_match(v, ctx->dp, F21, n, false, ctx->st, &ctx->prof);
+        launch_compact(v, n, ctx->d_out + (size_t)f0 * b.E, b.E, ctx->st, &ctx->prof);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->evDone[k], ctx->st));
+        if (k >= 1 && (rc = download(k - 1))) return rc;
+    }
+    if ((rc = download(nsb - 1))) return rc;
+    CK(cudaStreamSynchronize(ctx->stOut));
     if ((rc = check_err_flag(ctx))) return rc;
     ctx->prof.collect();
-    return download_mates(ctx, n_frames, out, cap, n_mates);
+    return over;
 }
 
 int ebvo_edge_patches(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* plus49, float* minus49)

@@ -262,3 +262,23 @@ def test_against_reference_stereo_golden(gpu_ctx, golden_stereo):
     assert np.array_equal(mates["left_index"], ref["mate_left"])
     assert np.abs(mates["rx"] - ref["mate_right"][:, 0]).max() < 1e-3 and np.abs(mates["ry"] - ref["mate_right"][:, 1]).max() < 1e-3
     assert np.abs(mates["rtheta"] - ref["mate_right"][:, 2]).max() < 1e-4 and np.abs(mates["score"] - ref["mate_score"]).max() < 1e-5
+
+
+def test_pipelined_batch_call_equals_the_resident_batch_path():
+    """ebvo_stereo_batch overlaps copies and kernels over sub-batches of 32 frames (three streams); 70 frames = three
+    sub-batches, the last one ragged.  Same mates, bit for bit, as upload-all / run / download-all on one stream."""
+    cal = synth.kitti_calib(320, 200)
+    pairs = [synth.stereo_pair(cal, f) for f in range(5)]
+    Ls = [pairs[f % 5][0] for f in range(70)]
+    Rs = [pairs[f % 5][1] for f in range(70)]
+    ctx = _lib.Context(0, 320, 200, max_batch=70, max_edges=16384)
+    out, n = ctx.stereo_batch(_calib(cal), Ls, Rs, cap=8000)
+    ctx.batch_upload(Ls, Rs)
+    ctx.batch_run(_calib(cal), True)
+    ctx.batch_sync()
+    out2, n2 = ctx.batch_download(8000)
+    ctx.close()
+    assert np.array_equal(n, n2) and n.min() > 500
+    for f in range(70):
+        assert np.array_equal(out[f, :n[f]], out2[f, :n2[f]])
+        assert np.array_equal(out[f, :n[f]], out[f % 5, :n[f % 5]])
