@@ -5,7 +5,7 @@
 // members run.  TEST INFRASTRUCTURE: Dataset.cpp (yaml-cpp, file I/O) is not built, its calibration part is restated
 // below as in oracle/ref_stereo_harness.cpp.
 //
-// usage: test_dropin_stereo <in.bin> <out.bin>
+// usage: test_dropin_stereo <in.bin> <out.bin> [output dir for the reference's own text writer]
 //   in : int32 W, H, nL, nR; double Kl[9], Kr[9], R21[9], T21[3]; u8 L[H*W], R[H*W]; double Lxyt[3*nL], Rxyt[3*nR]
 //   out: int32 n; n x 14 doubles {left index, lx, ly, lth, rx, ry, rth, score, sum(L+), sum(L-), sum(R+), sum(R-), b_is_TP, line c}
 #include <algorithm>
@@ -106,6 +106,10 @@ int main(int argc, char** argv)
     std::vector<final_stereo_edge_pair> mates;
     engine->finalize_stereo_edge_mates(pairs, mates);                                      // GPU drop-in
     if (!metrics.stages.empty() || mates.size() != pairs.focused_edge_indices.size()) return 5;
+    if (argc > 3) {   // the on-disk format: the REFERENCE'S OWN writer (Stereo_Matches.cpp:1656-1699) consumes the GPU mates unchanged
+        dataset->file_info.output_path = argv[3];
+        engine->write_finalized_stereo_edge_pairs_to_file(dataset, mates, 0);              // Pipeline.cpp:131
+    }
 
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return 6;

@@ -36,14 +36,14 @@ EXE_UNITS = os.path.join(ROOT, "dropin", "_build", "test_dropin_units")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def _run_stereo_dropin(tmp_path, cal, L, R, eL, eR):
+def _run_stereo_dropin(tmp_path, cal, L, R, eL, eR, writer_dir=None):
     inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
         np.array([L.shape[1], L.shape[0], len(eL), len(eR)], np.int32).tofile(f)
         np.concatenate([np.ravel(cal.Kl), np.ravel(cal.Kr), np.ravel(cal.R21), np.ravel(cal.T21)]).astype(np.float64).tofile(f)
         np.ascontiguousarray(L).tofile(f); np.ascontiguousarray(R).tofile(f)
         np.ascontiguousarray(eL[:, :3], np.float64).tofile(f); np.ascontiguousarray(eR[:, :3], np.float64).tofile(f)
-    out = subprocess.run([EXE_STEREO, str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([EXE_STEREO, str(inp), str(outp)] + ([str(writer_dir)] if writer_dir else []), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, (out.returncode, out.stdout[-2000:], out.stderr[-2000:])
     raw = np.fromfile(outp, np.uint8)
     n = int(raw[:4].view(np.int32)[0])
@@ -58,7 +58,14 @@ def test_stereo_matches_members_backed_by_the_gpu_against_reference_output(tmp_p
     g = np.load(os.path.join(GOLDEN, "stereo_small.npz"))
     ref = np.load(os.path.join(GOLDEN, "stereo_ref_small.npz"))
     cal = synth.kitti_calib(320, 200)
-    rows = _run_stereo_dropin(tmp_path, cal, g["L"], g["R"], g["eL"], g["eR"])
+    rows = _run_stereo_dropin(tmp_path, cal, g["L"], g["R"], g["eL"], g["eR"], writer_dir=tmp_path)
+    # on-disk format: the reference's own writer ran on the GPU mates - header + 16 columns per mate, the
+    # first six being the left / right edges (default ostream precision: 6 significant digits)
+    txt = (tmp_path / "finalized_stereo_edge_pairs_frame_0.txt").read_text().splitlines()
+    assert txt[0].startswith("left_edge_location, left_edge_orientation, right_edge_location") and len(txt) == len(rows) + 1
+    tab = np.array([[float(v) for v in l.split()] for l in txt[1:]])
+    assert tab.shape == (len(rows), 16) and np.isfinite(tab[:, :6]).all()
+    assert np.abs(tab[:, :6] - rows[:, 1:7]).max() < 5e-4 * max(1.0, np.abs(rows[:, 1:7]).max())
     assert np.array_equal(rows[:, 0].astype(int), ref["mate_left"])                       # focused_edge_indices after the stage
     assert np.array_equal(rows[:, 1:4], g["eL"][ref["mate_left"], :3])                     # left_edge copied from the frame
     assert np.abs(rows[:, 4:6] - ref["mate_right"][:, :2]).max() < 1e-3                    # right_edge location
