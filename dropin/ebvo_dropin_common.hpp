@@ -6,6 +6,7 @@
 // error the reference way (a LOG_ERROR-style print) and returns an empty result.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -25,6 +26,14 @@ inline Shared& shared()
     return s;
 }
 
+// SIFT gate / BNB-SIFT / finalisation descriptors (Stereo_Matches.cpp:655-787,1452,1627-1635) run on the device as in the
+// reference's default flow; EBVO_DROPIN_SIFT=0 in the environment selects the "SIFT-off" parity configuration.
+inline bool sift_enabled()
+{
+    const char* e = std::getenv("EBVO_DROPIN_SIFT");
+    return !(e && e[0] == '0');
+}
+
 // Returns a context able to hold w x h images and `edges` edges per image (nullptr + message on failure).
 inline ebvo_ctx* context(int w, int h, int edges)
 {
@@ -36,7 +45,10 @@ inline ebvo_ctx* context(int w, int h, int edges)
     int E = edges > s.edges ? edges : s.edges;
     if (E < 1 << 16) E = 1 << 16;
     ebvo_ctx* c = nullptr;
-    const int rc = ebvo_create(&c, 0, W, H, 1, E, nullptr);
+    ebvo_params prm;
+    ebvo_params_default(&prm);
+    prm.sift_mode = sift_enabled() ? 1 : 0;
+    const int rc = ebvo_create(&c, 0, W, H, 1, E, &prm);
     if (rc != EBVO_OK) {
         std::printf("\033[1;31m[ERROR] ebvo_create failed (%d): %s\033[0m\n", rc, c ? ebvo_last_error(c) : "no CUDA device");
         if (c) ebvo_destroy(c);

@@ -15,10 +15,11 @@
 //     the writers, the individual apply_* filters) exactly as it is.
 // dropin/Makefile does precisely this with the reference sources in place and tests/test_gpu_dropin.py runs the result.
 //
-// Scope: the no-GT branch (KITTI, EuRoC, ETH3D-SLAM: Dataset.cpp:120-148), SIFT-off: the SIFT
-// gate, BNB-SIFT and the finalisation descriptors are not computed (descriptor pairs are left empty).  With has_gt()
-// the per-stage Evaluate_Stereo_Edge_Correspondences metrics (diagnostics) are not produced: the returned
-// Frame_Evaluation_Metrics is empty, the mates are the same.
+// Scope: the no-GT branch (KITTI, EuRoC, ETH3D-SLAM: Dataset.cpp:120-148).  The SIFT gate, BNB-SIFT and the
+// descriptors of the finalised mates are computed on the device (cv::SIFT::compute at the reference's keypoints,
+// restated in csrc/sift.cu) as in the reference's default flow; EBVO_DROPIN_SIFT=0 selects the SIFT-off parity
+// configuration (descriptor pairs stay empty).  With has_gt() the per-stage Evaluate_Stereo_Edge_Correspondences
+// metrics (diagnostics) are not produced: the returned Frame_Evaluation_Metrics is empty, the mates are the same.
 //
 // State left in Stereo_Edge_Pairs, as after the reference's remove_empty_clusters (:1543-1576): only matched left
 // edges remain; per remaining edge one EdgeCluster whose center_edge is the mate, refine_final_scores = {NCC}.
@@ -60,6 +61,14 @@ ebvo_calib calib_of(Dataset& d)
         c.T21[i] = T(i);
     }
     return c;    // F21 is derived inside the library exactly as Dataset.cpp:102-112 does
+}
+
+// two 1 x 128 CV_32F rows, as cv::SIFT::compute returns them (descriptors.row(0), descriptors.row(1))
+std::pair<cv::Mat, cv::Mat> descriptor_pair(const float* d256)
+{
+    cv::Mat a(1, 128, CV_32F), b(1, 128, CV_32F);
+    for (int k = 0; k < 128; ++k) { a.at<float>(0, k) = d256[k]; b.at<float>(0, k) = d256[128 + k]; }
+    return {a, b};
 }
 
 std::pair<cv::Mat, cv::Mat> patch_pair(const float* plus49, const float* minus49)
@@ -122,6 +131,14 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
         if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); return fail_empty(); }
     }
 
+    // SIFT descriptors of the matched left edges from the undistorted left image (augment_Edge_Data, :655-689)
+    std::vector<float> dl;
+    if (ebvo_dropin::sift_enabled() && n > 0) {
+        dl.resize((size_t)n * 256);
+        rc = ebvo_sift_descriptors(ctx, Lund.data(), W, H, W, Lm.data(), n, dl.data());
+        if (rc != EBVO_OK) { log_error("ebvo_sift_descriptors", ctx, rc); return fail_empty(); }
+    }
+
     // rebuild the per-left-edge containers for the survivors, in left-edge order (the order remove_empty_clusters keeps)
     const Eigen::Matrix3d F21 = dataset->get_fund_mat_21();
     std::vector<int> focused((size_t)n);
@@ -140,6 +157,7 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
         const Eigen::Vector3d x(L[i].x, L[i].y, 1.0);     // CalculateEpipolarLine (:10-20)
         lines[k] = F21 * x;
         patches[k] = patch_pair(&pp[(size_t)k * 49], &pm[(size_t)k * 49]);
+        if (!dl.empty()) desc[k] = descriptor_pair(&dl[(size_t)k * 256]);
         EdgeCluster ec;
         ec.center_edge = Edge(cv::Point2d(mates[k].rx, mates[k].ry), mates[k].rtheta, false, 0);   // :39 / EdgeClusterer.cpp:243
         ec.center_edge.index = -1;                         // uninitialised in the reference (cpu_toed.hpp:35)
@@ -155,7 +173,7 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     pairs.veridical_right_edges_indices.swap(veridical);
     pairs.Gamma_in_left_cam_coord.swap(g_left);
     pairs.Gamma_in_right_cam_coord.swap(g_right);
-    pairs.left_edge_descriptors.swap(desc);                // SIFT-off: empty descriptor pairs, sized like the reference (:657-658)
+    pairs.left_edge_descriptors.swap(desc);                // sized like the reference (:657-658); empty pairs when SIFT is off
     pairs.epip_line_coeffs_of_left_edges.swap(lines);
     pairs.left_edge_patches.swap(patches);
     pairs.matching_edge_clusters.swap(clusters);
@@ -187,8 +205,14 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
     ebvo_ctx* ctx = ebvo_dropin::context(W, H, (int)n);
     if (!ctx) { final_stereo_edge_pairs.clear(); return; }
     const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(Rimg.data, H, W, Rimg.step);
-    const int rc = ebvo_edge_patches(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, pp.data(), pm.data());
+    int rc = ebvo_edge_patches(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, pp.data(), pm.data());
     if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+    std::vector<float> dr;                                 // right descriptors of the mates (:1627-1635)
+    if (ebvo_dropin::sift_enabled()) {
+        dr.resize(n * 256);
+        rc = ebvo_sift_descriptors(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, dr.data());
+        if (rc != EBVO_OK) { log_error("ebvo_sift_descriptors", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+    }
 
     for (size_t i = 0; i < n; ++i) {
         final_stereo_edge_pair mate;
@@ -197,7 +221,7 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         mate.left_edge_patches = pairs.left_edge_patches[i];
         mate.right_edge_patches = patch_pair(&pp[i * 49], &pm[i * 49]);
         mate.left_edge_descriptors = pairs.left_edge_descriptors[i];
-        // right_edge_descriptors: SIFT-off (cv::SIFT is third-party code outside this path) - left empty
+        if (!dr.empty()) mate.right_edge_descriptors = descriptor_pair(&dr[i * 256]);
         mate.Gamma_in_left_cam_coord = pairs.Gamma_in_left_cam_coord[i];
         mate.Gamma_in_right_cam_coord = pairs.Gamma_in_right_cam_coord[i];
         mate.gt_right_location = pairs.GT_locations_from_left_edges[i];

@@ -19,7 +19,7 @@ EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
     "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
-    "ebvo_cluster", "ebvo_sobel", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
+    "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
 ]
 
@@ -44,7 +44,7 @@ class Params(C.Structure):
         "bnb_ncc", "bnb_sift", "sift_threshold", "location_perturbation", "epip_tangency_displ_thresh",
         "orient_perturbation", "cluster_dist_thresh", "cluster_orient_thresh_deg", "cluster_orient_gauss_sigma")] + [
         ("max_cluster_size", C.c_int32), ("gn_max_iter", C.c_int32), ("gn_tol", C.c_double), ("gn_huber_delta", C.c_double),
-        ("toed_mag_thresh", C.c_double), ("toed_border", C.c_int32), ("gn_mode", C.c_int32)]
+        ("toed_mag_thresh", C.c_double), ("toed_border", C.c_int32), ("gn_mode", C.c_int32), ("sift_mode", C.c_int32)]
 
 
 class Mate(C.Structure):
@@ -264,6 +264,15 @@ class Context:
         gx, gy = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
         self._ck(self.L.ebvo_sobel(self.h, _p(img), w, h, img.strides[0], _p(gx), _p(gy)))
         return gx, gy
+
+    def sift_descriptors(self, img, edges):
+        """augment_Edge_Data: (n, 2, 128) float32 descriptors (needs a context created with params.sift_mode = 1)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        e = np.ascontiguousarray(edges, EDGE_DTYPE)
+        out = np.zeros((len(e), 2, 128), np.float32)
+        self._ck(self.L.ebvo_sift_descriptors(self.h, _p(img), w, h, img.strides[0], _p(e), len(e), _p(out)))
+        return out
 
     def set_stage_dumps(self, enable=True):
         self._ck(self.L.ebvo_set_stage_dumps(self.h, int(enable)))

@@ -112,7 +112,7 @@ void set_devparams(ebvo_ctx* ctx)
     d.clus_orient_rad = q.cluster_orient_thresh_deg * (M_PI / 180.0);   // deg_to_rad, include/utility.h:293-297
     d.clus_sigma = q.cluster_orient_gauss_sigma; d.clus_max = q.max_cluster_size; d.gn_max_iter = q.gn_max_iter;
     d.gn_tol = q.gn_tol; d.gn_huber = q.gn_huber_delta; d.toed_mag_thresh = (float)q.toed_mag_thresh; d.toed_border = q.toed_border;
-    d.gn_mode = q.gn_mode;
+    d.gn_mode = q.gn_mode; d.sift_mode = q.sift_mode;
 }
 
 // geometry-dependent fields of the device view
@@ -128,6 +128,7 @@ int configure(ebvo_ctx* ctx, int w, int h, int nFrames)
     b.nFrames = nFrames; b.nImages = 2 * nFrames;
     b.raw = ctx->d_raw; b.und = ctx->d_raw;
     b.descL = nullptr; b.descR = nullptr;
+    b.siftDev = ctx->params.sift_mode == 1 ? 1 : 0;
     b.dumps = 0;
     ctx->curFrames = nFrames;
     return EBVO_OK;
@@ -306,7 +307,7 @@ int ebvo_params_default(ebvo_params* p)
     p->ncc_thresh = 0.6; p->bnb_ncc = 0.9; p->bnb_sift = 0.4; p->sift_threshold = 500.0; p->location_perturbation = 0.4;
     p->epip_tangency_displ_thresh = 3.0; p->orient_perturbation = 0.174533; p->cluster_dist_thresh = 1.0;
     p->cluster_orient_thresh_deg = 20.0; p->cluster_orient_gauss_sigma = 2.0; p->max_cluster_size = 10; p->gn_max_iter = 20;
-    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->gn_mode = 0;
+    p->gn_tol = 1e-3; p->gn_huber_delta = 3.0; p->toed_mag_thresh = 2.0; p->toed_border = 10; p->gn_mode = 0; p->sift_mode = 0;
     return EBVO_OK;
 }
 
@@ -360,6 +361,11 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     CK(dalloc(ctx, &b.mates, (size_t)b.E * B)); CK(dalloc(ctx, &b.nMates, (size_t)B)); CK(dalloc(ctx, &b.mateFlag, (size_t)b.E * B));
     CK(dalloc(ctx, &b.errFlag, (size_t)4)); CK(dalloc(ctx, &b.counters, (size_t)8 * B));
     CK(dalloc(ctx, &ctx->d_out, (size_t)b.E * B));
+    if (ctx->params.sift_mode == 1) {
+        b.blurStride = align_up((size_t)max_w * max_h, 64);
+        CK(dalloc(ctx, &b.blur, b.blurStride * nImg));
+        CK(dalloc(ctx, &b.desc8, (size_t)b.E * 256 * nImg));
+    }
     CK(dalloc(ctx, &b.dF, (size_t)16));
     CK(cudaMemsetAsync(b.errFlag, 0, 16, ctx->st));
     CK(cudaMemsetAsync(b.nE, 0, sizeof(int) * nImg, ctx->st));
@@ -442,6 +448,7 @@ static int run_match_with_dumps(ebvo_ctx* ctx, const double* F21, bool sift, int
     if ((rc = gate_stage(ctx, EBVO_STAGE_ORIENT, 2, F21, nL, rx, ry, rth))) return rc;
     match_gate(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
     if (sift) {
+        if (ctx->b.siftDev) launch_sift(ctx->b, 2, ctx->st, &ctx->prof);
         match_sift(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
         // positions are not materialised before the NCC kernel: take them from the right-edge list
         if ((rc = snapshot_stage(ctx, EBVO_STAGE_SIFT, -1, nL))) return rc;
@@ -484,8 +491,10 @@ int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_r
     std::vector<double> rx, ry, rth;
     if ((rc = upload_edges(ctx, 0, L, nL))) return rc;
     if ((rc = upload_edges(ctx, 1, R, nR, &rx, &ry, &rth))) return rc;
-    const bool sift = descL && descR;
-    if (sift) {
+    const bool injected = descL && descR;
+    const bool sift = injected || ctx->params.sift_mode == 1;
+    ctx->b.siftDev = (!injected && ctx->params.sift_mode == 1) ? 1 : 0;
+    if (injected) {
         size_t need = (size_t)std::max(nL, nR) * 256;
         if (need > ctx->descCap) {
             if (ctx->d_descL) cudaFree(ctx->d_descL);
@@ -529,6 +538,8 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     v.c_ridx += F0 * P; v.c_x += F0 * P; v.c_y += F0 * P; v.c_th += F0 * P; v.c_score += F0 * P; v.c_conf += F0 * P; v.c_owner += F0 * P;
     v.mates += F0 * E; v.nMates += F0; v.mateFlag += F0 * E;
     v.counters += F0 * 8;
+    if (v.blur) v.blur += i0 * b.blurStride;
+    if (v.desc8) v.desc8 += i0 * E * 256;
     return v;
 }
 
@@ -538,7 +549,7 @@ static int run_frames(ebvo_ctx* ctx, const ebvo_calib* calib, int nFrames, int d
     if (do_match) {
         double F21[9];
         ebvo_fundamental(calib, F21, nullptr);
-        launch_match(ctx->b, ctx->dp, F21, nFrames, false, ctx->st, &ctx->prof);
+        launch_match(ctx->b, ctx->dp, F21, nFrames, ctx->params.sift_mode == 1, ctx->st, &ctx->prof);
         launch_compact(ctx->b, nFrames, ctx->d_out, ctx->b.E, ctx->st, &ctx->prof);
     }
     CK(cudaGetLastError());
@@ -664,7 +675,7 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         const DevBatch v = frame_view(b, f0, n);
         CK(cudaStreamWaitEvent(ctx->st, ctx->evIn[k], 0));
         launch_toed(v, ctx->dp, 2 * n, ctx->st, &ctx->prof);
-        launch_match(v, ctx->dp, F21, n, false, ctx->st, &ctx->prof);
+        launch_match(v, ctx->dp, F21, n, ctx->params.sift_mode == 1, ctx->st, &ctx->prof);
         launch_compact(v, n, ctx->d_out + (size_t)f0 * b.E, b.E, ctx->st, &ctx->prof);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->evDone[k], ctx->st));
@@ -675,6 +686,33 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
     if ((rc = check_err_flag(ctx))) return rc;
     ctx->prof.collect();
     return over;
+}
+
+int ebvo_sift_descriptors(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* out)
+{
+    if (!ctx || !img || (n && !edges) || n < 0 || (n && !out)) return EBVO_ERR_INVALID;
+    if (ctx->params.sift_mode != 1) { ctx->err = "ebvo_sift_descriptors needs a context created with sift_mode = 1"; return EBVO_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    if (n > ctx->E) { ctx->err = "more edges than the context's max_edges"; return EBVO_ERR_CAPACITY; }
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, img, stride))) return rc;
+    std::vector<double> x(n), y(n), t(n);
+    for (int k = 0; k < n; ++k) { x[k] = edges[k].x; y[k] = edges[k].y; t[k] = edges[k].theta; }
+    const DevBatch& b = ctx->b;
+    if (n) {
+        CK(cudaMemcpyAsync(b.ex, x.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.ey, y.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.eth, t.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->st));
+    }
+    CK(cudaMemcpyAsync(b.nE, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+    launch_sift(b, 1, ctx->st, nullptr);
+    CK(cudaGetLastError());
+    std::vector<uint8_t> d8((size_t)n * 256);
+    if (n) CK(cudaMemcpyAsync(d8.data(), b.desc8, d8.size(), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (size_t k = 0; k < d8.size(); ++k) out[k] = (float)d8[k];
+    return EBVO_OK;
 }
 
 int ebvo_edge_patches(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* plus49, float* minus49)

@@ -60,7 +60,10 @@ struct DevBatch {
     int* mateFlag;                        // [frame][E]
     int* errFlag;                         // single int: capacity overflows
     unsigned long long* counters;         // [frame][8] work counters (s3 pairs, ncc pairs, gn pairs, gn iters, ncc2 pairs ...)
-    const float* descL; const float* descR; // optional SIFT descriptors (frame 0 only), may be null
+    const float* descL; const float* descR; // optional caller-supplied SIFT descriptors (frame 0 only), may be null
+    float* blur; size_t blurStride;         // sift_mode 1: Gaussian-blurred float images [img][H*W] (descriptor image of cv::SIFT)
+    uint8_t* desc8;                         // sift_mode 1: descriptors computed on the device [img][E][2][128]
+    int siftDev;                            // != 0: use desc8 (all frames) instead of descL/descR
     double* dF;                           // device copy of F21 (9 doubles, row-major)
     int dumps;                            // != 0: fill dump[] for frame 0
     DumpBuf dump[DUMP_COUNT];
@@ -72,13 +75,15 @@ struct DevParams {
     int clus_max, gn_max_iter;
     double gn_tol, gn_huber;
     float toed_mag_thresh; int toed_border;
-    int gn_mode;   // 0 mixed (default), 1 FP64, 2 FP32
+    int gn_mode;   // 0 FP64 tiled (default), 1 FP64 gather, 2 FP32
+    int sift_mode; // 0: SIFT stages only with caller-supplied descriptors; 1: descriptors computed on the device
 };
 
 // kernel launchers (defined in toed.cu / match.cu); all asynchronous on `st`
 void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_t st, struct Prof* prof);
 void launch_match(const DevBatch& b, const DevParams& p, const double* F21 /*host 9*/, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
 void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* prof);
+void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);   // blur + descriptors of every edge (sift.cu)
 void upload_toed_tables();
 
 // stage-dump support (debug): gate lists for stages 0..2 on frame 0

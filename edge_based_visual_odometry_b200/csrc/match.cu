@@ -553,6 +553,44 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate_kernel(DevBatch b, DevPara
     }
 }
 
+// The same gate on descriptors computed on the device (sift.cu; every frame): 8-bit entries, so the four squared
+// distances are exact integer sums (cv::norm accumulates the float entries in double: the same value).
+__global__ void __launch_bounds__(32 * WPB) sift_gate8_kernel(DevBatch b, DevParams p)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nL = b.nE[2 * f];
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    int* c_ridx = b.c_ridx + (size_t)f * b.P;
+    double* c_conf = b.c_conf + (size_t)f * b.P;
+    const uint8_t* dL = b.desc8 + (size_t)(2 * f) * b.E * 256;
+    const uint8_t* dR = b.desc8 + (size_t)(2 * f + 1) * b.E * 256;
+    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+        const int n = ccount[i];
+        if (n == 0) continue;
+        const int st = cstart[i];
+        const uchar4 a1 = reinterpret_cast<const uchar4*>(dL + (size_t)i * 256)[lane], a2 = reinterpret_cast<const uchar4*>(dL + (size_t)i * 256 + 128)[lane];
+        int ns = 0;
+        for (int j = 0; j < n; ++j) {
+            const int r = c_ridx[st + j];
+            const uchar4 b1 = reinterpret_cast<const uchar4*>(dR + (size_t)r * 256)[lane], b2 = reinterpret_cast<const uchar4*>(dR + (size_t)r * 256 + 128)[lane];
+            auto d2 = [](uchar4 u, uchar4 v) {
+                const int x = (int)u.x - (int)v.x, y = (int)u.y - (int)v.y, z = (int)u.z - (int)v.z, q = (int)u.w - (int)v.w;
+                return x * x + y * y + z * z + q * q;
+            };
+            const int d11 = __reduce_add_sync(FULL, d2(a1, b1)), d21 = __reduce_add_sync(FULL, d2(a2, b1));
+            const int d12 = __reduce_add_sync(FULL, d2(a1, b2)), d22 = __reduce_add_sync(FULL, d2(a2, b2));
+            const double d = fmin(fmin(sqrt((double)d11), sqrt((double)d21)), fmin(sqrt((double)d12), sqrt((double)d22)));   // :736-740
+            if (d < p.sift_thresh) {
+                if (lane == 0) { c_ridx[st + ns] = r; c_conf[st + ns] = d; }
+                ++ns;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) ccount[i] = ns;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // S8 epipolar shift (Stereo_Matches.cpp:26-89; utility.cpp:46-74).  One THREAD per live pool slot: scalar FP64
 // trigonometry is 32x cheaper here than replicated across the lanes of a warp-per-candidate kernel.
@@ -1394,7 +1432,8 @@ void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t
 }
 void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
-    EBVO_KERNEL(prof, "sift_gate", st, (sift_gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    if (b.siftDev) EBVO_KERNEL(prof, "sift_gate", st, (sift_gate8_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    else EBVO_KERNEL(prof, "sift_gate", st, (sift_gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cudaStream_t st, Prof* prof)
 {
@@ -1433,6 +1472,7 @@ void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStrea
 void launch_match(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, bool sift, cudaStream_t st, Prof* prof)
 {
     match_prologue(b, p, F21, nFrames, st, prof);
+    if (sift && b.siftDev) launch_sift(b, 2 * nFrames, st, prof);
     match_gate(b, p, nFrames, st, prof);
     if (sift) match_sift(b, p, nFrames, st, prof);
     match_ncc(b, p, nFrames, sift, st, prof);

@@ -1,0 +1,199 @@
+// SIFT descriptors at edge-derived keypoints on sm_100a (S4 / S7' / S13 of the stereo path, "SIFT-on").
+//
+// The reference calls cv::SIFT::compute(image, {kp+, kp-}, desc) once per edge with two hand-made keypoints
+// (size 1, angle = deg(theta), octave 0) at p +- 8 (sin theta, -cos theta): augment_Edge_Data and apply_SIFT_filtering,
+// src/Stereo_Matches.cpp:655-787, and finalize_stereo_edge_mates :1627-1635.  The arithmetic lives in OpenCV
+// (modules/features2d/src/sift.dispatch.cpp / sift.simd.hpp, 4.x), not in the reference repository; it is restated
+// here from its published algorithm and pinned against cv2 4.13 in tests/test_gpu_sift.py (99.97 % of the descriptor
+// entries identical, the rest off by one: OpenCV's SIMD summation orders are not reproducible bit for bit):
+//   * provided keypoints with octave 0 => firstOctave = 0: no image doubling; the descriptor image is
+//     GaussianBlur(float(image), sigma = sqrt(1.6^2 - 0.5^2)), 13 taps, BORDER_REFLECT_101        (createInitialImage)
+//   * calcSIFTDescriptor(img, pt, ori = 360 - angle, scl = size/2 = 0.5, d = 4, n = 8): radius 5 => 11 x 11 samples
+//     around cvRound(pt), central-difference gradients, fastAtan2 polynomial, Gaussian weight exp(-(r'^2+c'^2)/8),
+//     trilinear vote into a (d+2) x (d+2) x (n+2) histogram, circular fold of the orientation axis, clip at 0.2 |h|,
+//     scale to 512 / |h|, saturate to 8 bits
+//   * quirk kept: ori = 360 - angle exceeds 360 for negative angles, so floor(obin) can be below -n and the single
+//     "o0 += n" wrap leaves a negative orientation index; the vote then lands 1..4 slots BEFORE the cell's first
+//     bin in the flat histogram (the previous cell's upper slots), exactly as OpenCV's pointer arithmetic does;
+//     votes that fall outside the array are dropped.
+// Votes are accumulated as 64-bit fixed point with shared-memory atomics, so the result does not depend on the order
+// of the lanes (deterministic run to run).
+#include "ebvo_internal.cuh"
+#include <cfloat>
+#include <cmath>
+
+namespace ebvo {
+
+constexpr int SK = 13, SR = 6;            // Gaussian taps / radius
+__constant__ float c_sift_k[SK];
+
+void upload_sift_tables()
+{
+    // cv::getGaussianKernel(13, sigma, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, stored as float
+    const double sigma = std::sqrt(std::max(1.6 * 1.6 - 0.5 * 0.5, 0.01));
+    double k[SK], sum = 0;
+    for (int i = 0; i < SK; ++i) { const double x = i - (SK - 1) * 0.5; k[i] = std::exp(-(x * x) / (2.0 * sigma * sigma)); sum += k[i]; }
+    float kf[SK];
+    for (int i = 0; i < SK; ++i) kf[i] = (float)(k[i] / sum);
+    cudaMemcpyToSymbol(c_sift_k, kf, sizeof kf);
+}
+
+__device__ __forceinline__ int reflect101(int i, int n)   // BORDER_REFLECT_101; the clamp only matters for pixels that are never stored
+{
+    const int r = n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i));
+    return min(max(r, 0), n - 1);
+}
+
+// 32 x 32 output tile per CTA (256 threads): u8 tile + 6 px halo -> row pass -> column pass, symmetric summation
+// k[6] s[6] + sum_j k[6+j] (s[6+j] + s[6-j]) with fused multiply-adds (the order closest to OpenCV's: <= 3 float ulps)
+__global__ void __launch_bounds__(256) sift_blur_kernel(DevBatch b)
+{
+    __shared__ float s_in[32 + 2 * SR][32 + 2 * SR + 1];
+    __shared__ float s_row[32 + 2 * SR][33];
+    const int img = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.x;
+    const uint8_t* I = b.und + (size_t)img * b.imgStride;
+    for (int e = tid; e < (32 + 2 * SR) * (32 + 2 * SR); e += 256) {
+        const int r = e / (32 + 2 * SR), c = e - r * (32 + 2 * SR);
+        const int gy = reflect101(y0 - SR + r, b.H), gx = reflect101(x0 - SR + c, b.W);
+        s_in[r][c] = (float)I[(size_t)gy * b.pitch + gx];
+    }
+    __syncthreads();
+    for (int e = tid; e < (32 + 2 * SR) * 32; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        const float* v = &s_in[r][c];
+        float a = v[SR] * c_sift_k[SR];
+#pragma unroll
+        for (int j = 1; j <= SR; ++j) a = fmaf(v[SR + j] + v[SR - j], c_sift_k[SR + j], a);
+        s_row[r][c] = a;
+    }
+    __syncthreads();
+    float* out = b.blur + (size_t)img * b.blurStride;
+    for (int e = tid; e < 32 * 32; e += 256) {
+        const int r = e >> 5, c = e & 31;
+        float a = s_row[r + SR][c] * c_sift_k[SR];
+#pragma unroll
+        for (int j = 1; j <= SR; ++j) a = fmaf(s_row[r + SR + j][c] + s_row[r + SR - j][c], c_sift_k[SR + j], a);
+        if (y0 + r < b.H && x0 + c < b.W) out[(size_t)(y0 + r) * b.W + x0 + c] = a;
+    }
+}
+
+// cv::hal::fastAtan2 (degrees), modules/core/src/mathfuncs_core.simd.hpp
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float p1 = 0.9997878412794807f * (float)(180 / 3.14159265358979323846), p3 = -0.3258083974640975f * (float)(180 / 3.14159265358979323846);
+    const float p5 = 0.1555786518463281f * (float)(180 / 3.14159265358979323846), p7 = -0.04432655554792128f * (float)(180 / 3.14159265358979323846);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = ay / (ax + (float)DBL_EPSILON), c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        const float c = ax / (ay + (float)DBL_EPSILON), c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+constexpr int SD = 4, SN = 8;                                  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS
+constexpr int SHIST = (SD + 2) * (SD + 2) * (SN + 2);          // 360
+constexpr float FIX = 4294967296.f;                            // 2^32 fixed-point scale of the votes
+
+// One warp per keypoint; keypoint 2e + s of an image = edge e, side s (0: p + 8 (sin, -cos), 1: p - 8 (sin, -cos)).
+__global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
+{
+    __shared__ unsigned long long s_h[4][SHIST];
+    const int img = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = b.nE[img];
+    const float* I = b.blur + (size_t)img * b.blurStride;
+    const int rows = b.H, cols = b.W;
+    unsigned long long* h = s_h[w];
+    for (int kp = blockIdx.x * 4 + w; kp < 2 * n; kp += gridDim.x * 4) {
+        const int e = kp >> 1, side = kp & 1;
+        const size_t eo = (size_t)img * b.E + e;
+        const double x = b.ex[eo], y = b.ey[eo], th = b.eth[eo];
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        // utility.cpp:128-139 and the cv::KeyPoint(Point2d, 1, 180 / M_PI * theta) constructor (narrowing to float)
+        const float px = (float)(side ? x + 8.0 * (-sn) : x + 8.0 * sn), py = (float)(side ? y + 8.0 * cs : y + 8.0 * (-cs));
+        const float angle = (float)(180 / 3.14159265358979323846 * th);
+        for (int k = lane; k < SHIST; k += 32) h[k] = 0ull;
+        __syncwarp();
+        const int ptx = __float2int_rn(px), pty = __float2int_rn(py);       // cvRound
+        float ori = 360.f - angle;
+        if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
+        float cos_t = cosf(ori * (float)(3.14159265358979323846 / 180)), sin_t = sinf(ori * (float)(3.14159265358979323846 / 180));
+        const float bins_per_rad = SN / 360.f, exp_scale = -1.f / (SD * SD * 0.5f), hist_width = 3.f * 0.5f;
+        cos_t /= hist_width; sin_t /= hist_width;
+        for (int k = lane; k < 121; k += 32) {
+            const int i = k / 11 - 5, j = k % 11 - 5;
+            const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
+            float rbin = r_rot + SD / 2 - 0.5f, cbin = c_rot + SD / 2 - 0.5f;
+            const int r = pty + i, c = ptx + j;
+            if (rbin > -1 && rbin < SD && cbin > -1 && cbin < SD && r > 0 && r < rows - 1 && c > 0 && c < cols - 1) {
+                const float dx = I[(size_t)r * cols + c + 1] - I[(size_t)r * cols + c - 1];
+                const float dy = I[(size_t)(r - 1) * cols + c] - I[(size_t)(r + 1) * cols + c];
+                const float wgt = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                float obin = (fast_atan2_deg(dy, dx) - ori) * bins_per_rad;
+                const float mag = sqrtf(dx * dx + dy * dy) * wgt;
+                const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin);
+                int o0 = (int)floorf(obin);
+                rbin -= r0; cbin -= c0; obin -= o0;
+                if (o0 < 0) o0 += SN;
+                if (o0 >= SN) o0 -= SN;
+                const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
+                const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
+                const int idx = ((r0 + 1) * (SD + 2) + c0 + 1) * (SN + 2) + o0;
+                auto vote = [&](int o, float v) { if (o >= 0 && o < SHIST && v > 0.f) atomicAdd(&h[o], (unsigned long long)(v * FIX)); };
+                vote(idx, v000); vote(idx + 1, v001);
+                vote(idx + (SN + 2), v010); vote(idx + (SN + 3), v011);
+                vote(idx + (SD + 2) * (SN + 2), v100); vote(idx + (SD + 2) * (SN + 2) + 1, v101);
+                vote(idx + (SD + 3) * (SN + 2), v110); vote(idx + (SD + 3) * (SN + 2) + 1, v111);
+            }
+        }
+        __syncwarp();
+        // circular fold + copy: lane owns descriptor entries q = lane + 32 t (cell q / 8, orientation q % 8)
+        float val[4];
+        float nrm2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int q = lane + 32 * t, cell = q >> 3, o = q & 7;
+            const int idx = ((cell / SD + 1) * (SD + 2) + (cell % SD + 1)) * (SN + 2);
+            unsigned long long s = h[idx + o];
+            if (o < 2) s += h[idx + SN + o];
+            val[t] = (float)((double)s * (1.0 / 4294967296.0));
+            nrm2 += val[t] * val[t];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+        const float thr = sqrtf(nrm2) * 0.2f;                                   // SIFT_DESCR_MAG_THR
+        float n2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { val[t] = fminf(val[t], thr); n2 += val[t] * val[t]; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        const float scale = 512.f / fmaxf(sqrtf(n2), FLT_EPSILON);              // SIFT_INT_DESCR_FCTR
+        uint8_t* d = b.desc8 + (eo * 2 + side) * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) d[lane + 32 * t] = (uint8_t)min(max(__float2int_rn(val[t] * scale), 0), 255);   // saturate_cast<uchar>
+        __syncwarp();
+    }
+}
+
+void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, Prof* prof)
+{
+    static bool tables = false;
+    if (!tables) { upload_sift_tables(); tables = true; }
+    dim3 gB((b.W + 31) / 32, (b.H + 31) / 32, nImages);
+    EBVO_KERNEL(prof, "sift_blur", st, (sift_blur_kernel<<<gB, 256, 0, st>>>(b)));
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int gx = (sms * 16 + nImages - 1) / nImages;
+    if (gx < 1) gx = 1;
+    EBVO_KERNEL(prof, "sift_desc", st, (sift_desc_kernel<<<dim3(gx, nImages), 128, 0, st>>>(b)));
+}
+
+}  // namespace ebvo

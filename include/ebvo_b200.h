@@ -64,6 +64,9 @@ typedef struct ebvo_params {
     int32_t toed_border;              /* 10, cpu_toed.cpp:401-403,553 */
     int32_t gn_mode;                  /* Gauss-Newton kernel: 0 (default) reference arithmetic (FP64), shared-memory tiles;
                                          1: the same arithmetic, global-memory gathers (cross-check); 2: all FP32 (looser parity) */
+    int32_t sift_mode;                /* 0 (default): the SIFT gate / BNB-SIFT run only with caller-supplied descriptors ("SIFT-off" otherwise);
+                                         1: descriptors computed on the device (cv::SIFT::compute at the reference's keypoints, restated),
+                                            S4 and S7' always run (Stereo_Matches.cpp:655-787,1452) */
 } ebvo_params;
 
 /* One finalised stereo mate: final_stereo_edge_pair.left_edge / right_edge, include/Dataset.h:291-309. */
@@ -148,6 +151,9 @@ int ebvo_ncc_patch_pair(ebvo_ctx* ctx, const float* p1, const float* p2, int n_p
 /* EdgeClusterer::performClustering (src/EdgeClusterer.cpp:119-302) on one candidate set. */
 int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientation, ebvo_edge* centers, int* labels,
                  int* n_clusters);
+/* augment_Edge_Data (src/Stereo_Matches.cpp:655-689): the two SIFT descriptors of n edges of one image, keypoints at
+ * p +- 8 (sin theta, -cos theta), size 1, angle deg(theta); out = n*2*128 floats (values 0..255).  Needs sift_mode 1. */
+int ebvo_sift_descriptors(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* out);
 /* util_compute_Img_Gradients (include/utility.h:131-141): Sobel 3x3 * 1/8, reflect-101 border. */
 int ebvo_sobel(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* gx, float* gy);
 

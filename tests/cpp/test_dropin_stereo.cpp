@@ -7,7 +7,8 @@
 //
 // usage: test_dropin_stereo <in.bin> <out.bin> [output dir for the reference's own text writer]
 //   in : int32 W, H, nL, nR; double Kl[9], Kr[9], R21[9], T21[3]; u8 L[H*W], R[H*W]; double Lxyt[3*nL], Rxyt[3*nR]
-//   out: int32 n; n x 14 doubles {left index, lx, ly, lth, rx, ry, rth, score, sum(L+), sum(L-), sum(R+), sum(R-), b_is_TP, line c}
+//   out: int32 n; n x 16 doubles {left index, lx, ly, lth, rx, ry, rth, score, sum(L+), sum(L-), sum(R+), sum(R-), b_is_TP, line c,
+//        sum(left descriptor 1) or -1 when empty, sum(right descriptor 2) or -1}
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -117,13 +118,15 @@ int main(int argc, char** argv)
     std::fwrite(&n, 4, 1, o);
     for (int i = 0; i < n; ++i) {
         const final_stereo_edge_pair& m = mates[i];
-        const double row[14] = {(double)pairs.focused_edge_indices[i], m.left_edge.location.x, m.left_edge.location.y, m.left_edge.orientation,
+        const double dsl = m.left_edge_descriptors.first.empty() ? -1.0 : patch_sum(m.left_edge_descriptors.first);
+        const double dsr = m.right_edge_descriptors.second.empty() ? -1.0 : patch_sum(m.right_edge_descriptors.second);
+        const double row[16] = {(double)pairs.focused_edge_indices[i], m.left_edge.location.x, m.left_edge.location.y, m.left_edge.orientation,
                                 m.right_edge.location.x, m.right_edge.location.y, m.right_edge.orientation,
                                 pairs.matching_edge_clusters[i].refine_final_scores[0],
                                 patch_sum(m.left_edge_patches.first), patch_sum(m.left_edge_patches.second),
                                 patch_sum(m.right_edge_patches.first), patch_sum(m.right_edge_patches.second),
-                                m.b_is_TP ? 1.0 : 0.0, pairs.epip_line_coeffs_of_left_edges[i](2)};
-        std::fwrite(row, 8, 14, o);
+                                m.b_is_TP ? 1.0 : 0.0, pairs.epip_line_coeffs_of_left_edges[i](2), dsl, dsr};
+        std::fwrite(row, 8, 16, o);
     }
     std::fclose(o);
     return 0;

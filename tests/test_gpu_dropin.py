@@ -36,18 +36,19 @@ EXE_UNITS = os.path.join(ROOT, "dropin", "_build", "test_dropin_units")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def _run_stereo_dropin(tmp_path, cal, L, R, eL, eR, writer_dir=None):
+def _run_stereo_dropin(tmp_path, cal, L, R, eL, eR, writer_dir=None, sift=False):
     inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
         np.array([L.shape[1], L.shape[0], len(eL), len(eR)], np.int32).tofile(f)
         np.concatenate([np.ravel(cal.Kl), np.ravel(cal.Kr), np.ravel(cal.R21), np.ravel(cal.T21)]).astype(np.float64).tofile(f)
         np.ascontiguousarray(L).tofile(f); np.ascontiguousarray(R).tofile(f)
         np.ascontiguousarray(eL[:, :3], np.float64).tofile(f); np.ascontiguousarray(eR[:, :3], np.float64).tofile(f)
-    out = subprocess.run([EXE_STEREO, str(inp), str(outp)] + ([str(writer_dir)] if writer_dir else []), capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, EBVO_DROPIN_SIFT="1" if sift else "0")
+    out = subprocess.run([EXE_STEREO, str(inp), str(outp)] + ([str(writer_dir)] if writer_dir else []), capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, (out.returncode, out.stdout[-2000:], out.stderr[-2000:])
     raw = np.fromfile(outp, np.uint8)
     n = int(raw[:4].view(np.int32)[0])
-    return raw[4:].view(np.float64).reshape(n, 14)
+    return raw[4:].view(np.float64).reshape(n, 16)
 
 
 @pytest.mark.skipif(not os.path.exists(EXE_STEREO), reason="dropin/_build not built (needs the reference headers at build time)")
@@ -141,3 +142,31 @@ def test_utility_clusterer_and_matlab_ncc_adapters(tmp_path):
         assert ncl == len(want_c) and np.array_equal(lab, want_lab)
         assert np.abs(cen[:, :3] - want_c).max() < 1e-9
         assert np.array_equal(cen[:, 3].astype(int), np.bincount(want_lab, minlength=ncl))       # contributing_edges per cluster
+
+
+@pytest.mark.skipif(not os.path.exists(EXE_STEREO), reason="dropin/_build not built (needs the reference headers at build time)")
+def test_stereo_matches_dropin_sift_on(tmp_path):
+    """The reference's default flow (SIFT gate, BNB-SIFT, descriptors of the finalised mates) through the drop-in, against
+    the oracle fed with cv2 descriptors (cv::SIFT is OpenCV code; tests/test_gpu_sift.py pins the descriptor kernel)."""
+    cv2 = pytest.importorskip("cv2")
+
+    def _cv2_descriptors(img, xyt):      # augment_Edge_Data keypoints (Stereo_Matches.cpp:668-677), one batched compute
+        kps = [cv2.KeyPoint(float(x + s * 8 * np.sin(t)), float(y - s * 8 * np.cos(t)), 1, float(180 / np.pi * t)) for x, y, t in xyt for s in (1, -1)]
+        k2, d = cv2.SIFT_create().compute(img, kps)
+        assert len(k2) == len(kps)
+        return d.reshape(len(xyt), 2, 128).astype(np.float32)
+
+    cal = synth.kitti_calib(480, 200)
+    L, R = synth.stereo_pair(cal, 6)
+    eL, _ = oracle.toed(L)
+    eR, _ = oracle.toed(R)
+    F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    dL, dR = _cv2_descriptors(L, eL[:, :3]), _cv2_descriptors(R, eR[:, :3])
+    res = oracle.stereo(L, R, eL, eR, F21, descL=dL, descR=dR, want_dumps=False)
+    rows = _run_stereo_dropin(tmp_path, cal, L, R, eL, eR, sift=True)
+    left = rows[:, 0].astype(int)
+    common = np.intersect1d(res.mate_left, left)
+    assert len(common) >= (1 - 2e-3) * len(res.mate_left) and len(left) <= (1 + 2e-3) * len(res.mate_left)
+    # descriptors handed to the caller: left ones equal cv2's on the same keypoints up to the off-by-one entries
+    want = dL[left, 0].sum(1)
+    assert (rows[:, 14] >= 0).all() and (rows[:, 15] >= 0).all() and np.abs(rows[:, 14] - want).max() <= 8
