@@ -169,4 +169,5 @@ def test_stereo_matches_dropin_sift_on(tmp_path):
     assert len(common) >= (1 - 2e-3) * len(res.mate_left) and len(left) <= (1 + 2e-3) * len(res.mate_left)
     # descriptors handed to the caller: left ones equal cv2's on the same keypoints up to the off-by-one entries
     want = dL[left, 0].sum(1)
-    assert (rows[:, 14] >= 0).all() and (rows[:, 15] >= 0).all() and np.abs(rows[:, 14] - want).max() <= 8
+    dsum = np.abs(rows[:, 14] - want)      # sums of 128 entries: a handful of off-by-one entries per descriptor at most
+    assert (rows[:, 14] >= 0).all() and (rows[:, 15] >= 0).all() and dsum.max() <= 16 and (dsum > 0).mean() < 0.05
