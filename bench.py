@@ -131,10 +131,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=160, help="stereo frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="stereo frames per GPU per step (default 160; 4 for the 4K workload)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (cycled to fill the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="kitti", choices=["kitti", "euroc", "4k"],
+                    help="kitti = the BASELINE.json metric (default); euroc / 4k = BASELINE configs[1] / configs[4] shapes (extra measurements)")
+    ap.add_argument("--density", type=float, default=1.0, help="synthetic scene density (objects per area), the 4K stress sweep varies it")
+    ap.add_argument("--sift", action="store_true", help="SIFT-on: descriptors, SIFT gate and BNB-SIFT on the device (sift_mode 1)")
     ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -145,7 +149,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     from edge_based_visual_odometry_b200 import synth
-    cal = synth.kitti_calib()
+    cal = {"kitti": synth.kitti_calib, "euroc": synth.CALIBS["euroc"], "4k": synth.kitti4k_calib}[args.workload]()
+    if not args.batch:
+        args.batch = 4 if args.workload == "4k" else 160
     if args.impl == "reference":
         run_reference(args, cal, rank)
         return
@@ -171,9 +177,13 @@ def main():
 
     B = args.batch
     H, W = cal.height, cal.width
-    CAP = 49152   # mates per frame returned to the host
+    big = args.workload == "4k"
+    max_edges = (1 << 21) if big else 65536
+    CAP = (1 << 20) if big else 49152   # mates per frame returned to the host
     # distinct frames per rank (different seeds per rank), cycled to fill the batch
-    base = [synth.stereo_pair(cal, rank * 1000 + f) for f in range(min(args.distinct, B))]
+    if args.workload == "4k":
+        args.distinct = min(args.distinct, 2)
+    base = [synth.stereo_pair(cal, rank * 1000 + f, density=args.density) for f in range(min(args.distinct, B))]
     # pinned host staging for the e2e path
     hL = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
     hR = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
@@ -188,7 +198,8 @@ def main():
 
     prm = _lib.default_params()
     prm.gn_mode = args.gn_mode
-    ctx = _lib.Context(local_rank, W, H, max_batch=B, max_edges=65536, params=prm)
+    prm.sift_mode = 1 if args.sift else 0
+    ctx = _lib.Context(local_rank, W, H, max_batch=B, max_edges=max_edges, params=prm)
     calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
@@ -293,10 +304,13 @@ def main():
                                       "frac": (tf(ncc_flops, ncc_ms) or 0) / fp32_peak}},
                 "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "matching_algorithmic_bytes_per_step": float(match_bytes),
                         "matching_algorithmic_gbs": float(match_bytes) / ((ksum - toed_ms) / args.steps / 1e3) / 1e9 if ksum > toed_ms else None}}
-        line = {"metric": "stereo frames/s (TOED+NCC stereo match) at KITTI 1241x376", "value": value, "unit": "frames/s", "n_gpus": world,
+        shape = {"kitti": "KITTI 1241x376", "euroc": "EuRoC 752x480", "4k": "4K 3840x2160"}[args.workload]
+        cfgname = {"kitti": "configs[2]: KITTI-shape 1241x376 synthetic stereo batch", "euroc": "configs[1]: EuRoC-shape 752x480 synthetic stereo sequence (euroc.yaml calibration, general F)",
+                   "4k": "configs[4]: 4K 3840x2160 synthetic stereo stress, density %.2f" % args.density}[args.workload]
+        line = {"metric": "stereo frames/s (TOED+NCC stereo match) at " + shape, "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TOED) / f64 (matching)", "data": "synthetic",
-                "config": {"workload": "configs[2]: KITTI-shape 1241x376 synthetic stereo batch, TOED x2 + stereo match S1-S13 (SIFT-off)",
+                "config": {"workload": cfgname + ", TOED x2 + stereo match S1-S13 (" + ("SIFT-on, device descriptors" if args.sift else "SIFT-off") + ")",
                            "frames_per_gpu_per_step": B, "distinct_frames": len(base), "l2": "batch inputs (%.0f MB u8 images + per-frame "
                            "intermediates) exceed the 126 MB L2" % (2 * B * W * H / 1e6),
                            "edges_per_image": float(nL.mean()), "mates_per_frame": float(nM.mean())},
@@ -304,7 +318,7 @@ def main():
                 "gpu_launches": int(sum(v[1] for v in ktimes.values())),
                 "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
                 "work_per_step": {"s3_pairs": int(c[0]), "bnb_pairs": int(c[1]), "gn_pairs": int(c[2]), "gn_iterations": int(c[3]), "ncc2_pairs": int(c[4]), "gn_tile_builds": int(c[5])}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "kitti" and not args.sift:
             secs, ttoed, tst, kind, nm = cpu_reference_frame(cal, *base[0])
             secs2, ttoed2, tst2, _, _ = cpu_reference_frame(cal, *base[1 % len(base)])
             _, _, tport, _, _ = cpu_reference_frame(cal, *base[0], stereo_ref=False)
