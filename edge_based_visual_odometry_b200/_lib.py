@@ -17,7 +17,7 @@ STAGES = ["epi", "disp", "orient", "sift", "ncc", "bnb_ncc", "bnb_sift", "shift"
 
 EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
-    "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_batch_upload", "ebvo_batch_run",
+    "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
     "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
@@ -111,6 +111,22 @@ def fundamental(calib: Calib):
     F21, F12 = np.zeros((3, 3)), np.zeros((3, 3))
     load().ebvo_fundamental(C.byref(calib), _p(F21), _p(F12))
     return F21, F12
+
+
+def stereo_batch_multi(contexts, calib, L_imgs, R_imgs, cap):
+    """ebvo_stereo_batch_multi: one batch over several contexts (one per GPU), contiguous frame blocks, host threads."""
+    F = len(L_imgs)
+    h, w = L_imgs[0].shape
+    out = np.zeros((F, cap), MATE_DTYPE)
+    n_mates = np.zeros(F, np.int32)
+    handles = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    c0 = contexts[0]
+    rc = c0.L.ebvo_stereo_batch_multi(handles, len(contexts), C.byref(calib), F, c0._ptr_array(L_imgs), c0._ptr_array(R_imgs), w, h,
+                                      L_imgs[0].strides[0], _p(out), cap, _p(n_mates))
+    if rc != 0:
+        msgs = [c.L.ebvo_last_error(c.h).decode() for c in contexts]
+        raise RuntimeError(f"ebvo_stereo_batch_multi failed ({rc}): {msgs}")
+    return out, n_mates
 
 
 class Context:

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 namespace ebvo {
 
@@ -686,6 +687,27 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
     if ((rc = check_err_flag(ctx))) return rc;
     ctx->prof.collect();
     return over;
+}
+
+int ebvo_stereo_batch_multi(ebvo_ctx* const* ctxs, int n_ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
+                            const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates)
+{
+    if (!ctxs || n_ctx < 1 || !calib || n_frames < 0 || (n_frames && (!L_imgs || !R_imgs))) return EBVO_ERR_INVALID;
+    for (int g = 0; g < n_ctx; ++g) if (!ctxs[g]) return EBVO_ERR_INVALID;
+    const int per = (n_frames + n_ctx - 1) / n_ctx;
+    std::vector<int> rcs(n_ctx, EBVO_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_ctx; ++g) {
+        const int f0 = std::min(g * per, n_frames), f1 = std::min(f0 + per, n_frames);
+        if (f1 <= f0) continue;
+        th.emplace_back([=, &rcs]() {
+            rcs[g] = ebvo_stereo_batch(ctxs[g], calib, f1 - f0, L_imgs + f0, R_imgs + f0, w, h, stride, out ? out + (size_t)f0 * cap : nullptr, cap,
+                                       n_mates ? n_mates + f0 : nullptr);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int rc : rcs) if (rc != EBVO_OK) return rc;
+    return EBVO_OK;
 }
 
 int ebvo_sift_descriptors(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* out)

@@ -134,6 +134,13 @@ int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_i
 int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
                       const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates);
 
+/* The same batch over several contexts (normally one per GPU of the box): frames are split into contiguous blocks of
+ * ceil(n_frames / n_ctx), one host thread per context, no exchange between devices (frames are independent:
+ * src/Pipeline.cpp:64-145 reads nothing from other frames); results land in out / n_mates at their global frame index.
+ * Returns the first non-zero status of any block (the message is on that block's context). */
+int ebvo_stereo_batch_multi(ebvo_ctx* const* ctxs, int n_ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
+                            const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates);
+
 /* Device-resident variant used to time the kernels alone: upload once, run many times, download once. */
 int ebvo_batch_upload(ebvo_ctx* ctx, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
                       int h, int stride);

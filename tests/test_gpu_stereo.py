@@ -282,3 +282,25 @@ def test_pipelined_batch_call_equals_the_resident_batch_path():
     for f in range(70):
         assert np.array_equal(out[f, :n[f]], out2[f, :n2[f]])
         assert np.array_equal(out[f, :n[f]], out[f % 5, :n[f % 5]])
+
+
+def test_multi_context_batch_entry_point():
+    """ebvo_stereo_batch_multi splits a batch into contiguous blocks over several contexts (normally one per GPU; here
+    as many devices as the box has, and two contexts on device 0 when there is only one) with one host thread each:
+    the mates land at their global frame index and equal the single-context result."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    cal = synth.kitti_calib(320, 200)
+    pairs = [synth.stereo_pair(cal, f) for f in range(3)]
+    Ls = [pairs[f % 3][0] for f in range(7)]
+    Rs = [pairs[f % 3][1] for f in range(7)]
+    devs = list(range(ndev)) if ndev > 1 else [0, 0]
+    ctxs = [_lib.Context(d, 320, 200, max_batch=4, max_edges=16384) for d in devs]
+    one = _lib.Context(0, 320, 200, max_batch=7, max_edges=16384)
+    ref, nref = one.stereo_batch(_calib(cal), Ls, Rs, cap=8000)
+    out, n = _lib.stereo_batch_multi(ctxs, _calib(cal), Ls, Rs, cap=8000)
+    for c in ctxs + [one]:
+        c.close()
+    assert np.array_equal(n, nref) and n.min() > 500
+    for f in range(7):
+        assert np.array_equal(out[f, :n[f]], ref[f, :n[f]])
