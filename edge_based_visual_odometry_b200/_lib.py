@@ -19,7 +19,7 @@ EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
     "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
-    "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
+    "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
 ]
 
@@ -280,6 +280,15 @@ class Context:
         gx, gy = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
         self._ck(self.L.ebvo_sobel(self.h, _p(img), w, h, img.strides[0], _p(gx), _p(gy)))
         return gx, gy
+
+    def undistort(self, img, K, dist):
+        """cv::undistort(img, K, dist) for one 8-bit image (dist = k1, k2, p1, p2)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        K = np.ascontiguousarray(K, np.float64).ravel(); dist = np.ascontiguousarray(dist, np.float64).ravel()
+        out = np.zeros((h, w), np.uint8)
+        self._ck(self.L.ebvo_undistort(self.h, _p(img), w, h, img.strides[0], _p(K), _p(dist), _p(out), out.strides[0]))
+        return out
 
     def sift_descriptors(self, img, edges):
         """augment_Edge_Data: (n, 2, 128) float32 descriptors (needs a context created with params.sift_mode = 1)."""

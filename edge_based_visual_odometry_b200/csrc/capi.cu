@@ -710,6 +710,22 @@ int ebvo_stereo_batch_multi(ebvo_ctx* const* ctxs, int n_ctx, const ebvo_calib* 
     return EBVO_OK;
 }
 
+int ebvo_undistort(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const double K[9], const double dist[4], uint8_t* out, int out_stride)
+{
+    if (!ctx || !img || !K || !dist || !out) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = configure(ctx, w, h, 1);
+    if (rc) return rc;
+    if ((rc = upload_image(ctx, ctx->d_raw, 0, img, stride))) return rc;
+    const DevBatch& b = ctx->b;
+    uint8_t* d_dst = ctx->d_raw + b.imgStride;      // image slot 1 of the context as the destination
+    launch_undistort(ctx->d_raw, b.pitch, d_dst, b.pitch, w, h, K, dist, ctx->st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(out, out_stride, d_dst, b.pitch, w, h, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return EBVO_OK;
+}
+
 int ebvo_sift_descriptors(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* out)
 {
     if (!ctx || !img || (n && !edges) || n < 0 || (n && !out)) return EBVO_ERR_INVALID;

@@ -83,7 +83,8 @@ struct DevParams {
 void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_t st, struct Prof* prof);
 void launch_match(const DevBatch& b, const DevParams& p, const double* F21 /*host 9*/, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
 void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* prof);
-void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);   // blur + descriptors of every edge (sift.cu)
+void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);
+void launch_undistort(const uint8_t* src, int srcPitch, uint8_t* dst, int dstPitch, int W, int H, const double K[9], const double dist[4], cudaStream_t st);   // undistort.cu   // blur + descriptors of every edge (sift.cu)
 void upload_toed_tables();
 
 // stage-dump support (debug): gate lists for stages 0..2 on frame 0
