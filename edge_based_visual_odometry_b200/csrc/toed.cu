@@ -45,14 +45,20 @@ constexpr int OWP = OW + 1;
 constexpr int IWP = IW + 1;
 constexpr int CR = 5;                           // output rows per thread in the column pass
 constexpr int NSEG = (OH + CR - 1) / CR;        // 7
-constexpr size_t TOED_SMEM = sizeof(float) * (IN_H * IN_WP + 6 * IN_H * OWP + 3 * IH * IWP);
+// Shared memory: the input tile + six row-pass planes are dead once the column pass has its sums in registers, and the
+// three interp-grid planes (Ix, Iy, magnitude) are only written after that point, so the two groups ALIAS (one extra
+// barrier): 56 KB instead of 111 KB per CTA => 4 CTAs (32 warps) per SM instead of 2, which is what hides the barriers
+// between the four stages and the global-load latency of stage 0.
+constexpr size_t TOED_SMEM_A = sizeof(float) * (IN_H * IN_WP + 6 * IN_H * OWP);
+constexpr size_t TOED_SMEM_B = sizeof(float) * (3 * IH * IWP);
+constexpr size_t TOED_SMEM = TOED_SMEM_A > TOED_SMEM_B ? TOED_SMEM_A : TOED_SMEM_B;
 
-__global__ void __launch_bounds__(TOED_THREADS, 2) toed_grad_nms_kernel(DevBatch b, float magThresh, int border)
+__global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch b, float magThresh, int border)
 {
     extern __shared__ float smem[];
     float* s_in = smem;
     float* s_row = s_in + IN_H * IN_WP;  // planes: 0 G17, 1 Gx17, 2 G19, 3 Gx19, 4 Gs, 5 Gxs
-    float* s_ix = s_row + 6 * IN_H * OWP;
+    float* s_ix = smem;                  // aliases s_in / s_row (see TOED_SMEM)
     float* s_iy = s_ix + IH * IWP;
     float* s_mag = s_iy + IH * IWP;
     __shared__ int s_tot;
@@ -102,12 +108,12 @@ __global__ void __launch_bounds__(TOED_THREADS, 2) toed_grad_nms_kernel(DevBatch
     __syncthreads();
 
     // ---- stage 2: column pass for fx, fy on the four sub-grids; CR output rows per thread ----
-    if (tid < OW * NSEG) {
-        const int seg = tid / OW, c = tid - seg * OW;
-        const int o0 = seg * CR;
-        float fx00[CR], fy00[CR], fx01[CR], fy01[CR], fx10[CR], fy10[CR], fx11[CR], fy11[CR];
+    const int seg = tid / OW, c = tid - seg * OW;
+    const int o0 = seg * CR;
+    float fx00[CR], fy00[CR], fx01[CR], fy01[CR], fx10[CR], fy10[CR], fx11[CR], fy11[CR];
 #pragma unroll
-        for (int k = 0; k < CR; ++k) fx00[k] = fy00[k] = fx01[k] = fy01[k] = fx10[k] = fy10[k] = fx11[k] = fy11[k] = 0.f;
+    for (int k = 0; k < CR; ++k) fx00[k] = fy00[k] = fx01[k] = fy01[k] = fx10[k] = fy10[k] = fx11[k] = fy11[k] = 0.f;
+    if (tid < OW * NSEG) {
 #pragma unroll
         for (int rr = 0; rr < CR + 18; ++rr) {
             int row = o0 + rr;
@@ -134,6 +140,9 @@ __global__ void __launch_bounds__(TOED_THREADS, 2) toed_grad_nms_kernel(DevBatch
                 }
             }
         }
+    }
+    __syncthreads();   // every thread is done reading s_row: the interp planes may now overwrite it
+    if (tid < OW * NSEG) {
 #pragma unroll
         for (int oo = 0; oo < CR; ++oo) {
             int o = o0 + oo;
