@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -114,6 +115,8 @@ void set_devparams(ebvo_ctx* ctx)
     d.clus_sigma = q.cluster_orient_gauss_sigma; d.clus_max = q.max_cluster_size; d.gn_max_iter = q.gn_max_iter;
     d.gn_tol = q.gn_tol; d.gn_huber = q.gn_huber_delta; d.toed_mag_thresh = (float)q.toed_mag_thresh; d.toed_border = q.toed_border;
     d.gn_mode = q.gn_mode; d.sift_mode = q.sift_mode;
+    d.clus_small = 48;
+    if (const char* e = getenv("EBVO_CLUSTER_SMALL")) d.clus_small = std::min(48, std::max(1, atoi(e)));
 }
 
 // geometry-dependent fields of the device view

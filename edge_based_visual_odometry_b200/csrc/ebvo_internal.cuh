@@ -73,6 +73,7 @@ struct DevParams {
     double epi, maxdisp, orient_deg, shift_mag, ncc_thresh, bnb_ncc, bnb_sift, sift_thresh;
     double loc_pert, tang_displ, orient_pert, clus_dist, clus_orient_rad, clus_sigma;
     int clus_max, gn_max_iter;
+    int clus_small;   // sets up to this size go to the small-capacity clusterer launch (48; EBVO_CLUSTER_SMALL lowers it for tests)
     double gn_tol, gn_huber;
     float toed_mag_thresh; int toed_border;
     int gn_mode;   // 0 FP64 tiled (default), 1 FP64 gather, 2 FP32

@@ -209,7 +209,7 @@ __device__ __forceinline__ int gate_scan(const GateCtx& g, const DevBatch& b, co
     return count;
 }
 
-__global__ void __launch_bounds__(32 * WPB) gate_kernel(DevBatch b, DevParams p, const double* __restrict__ F)
+__global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams p, const double* __restrict__ F)
 {
     __shared__ int s_buf[WPB][64];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1171,12 +1171,29 @@ __global__ void __launch_bounds__(32 * WPB, 6) gn32_kernel(DevBatch b, DevParams
 // without exceeding MAX_CLUSTER_SIZE triggers a merge and restarts the scan.  Here every lane evaluates "its"
 // point's nearest admissible neighbour at once and a ballot picks the first feasible point: same merges, same
 // order, O(n) work per merge instead of O(n^2).  Distances are compared squared (sqrt is monotone; d < 1 <=> d^2 < 1).
+// adm != nullptr (the launch for big sets, n > 48): the points do not move while clusters merge, so which pairs are
+// admissible (d < 1 px, |dtheta| < 20 deg) is decided once, as a 2 x 64-bit mask per point, and every rescan visits only
+// a point's admissible neighbours in ascending index order (O(degree) instead of O(n) per rescan; for the usual
+// handful of candidates the mask bookkeeping costs more than it saves, so the small launch passes nullptr).
 __device__ int warp_cluster(const double* sx, const double* sy, const double* sth, int n, bool by_orient, const DevParams& p,
-                            int lane, int* lab, int* csz, double* dk, double* gk, double* ox, double* oy, double* oth)
+                            int lane, int* lab, int* csz, double* dk, double* gk, double* ox, double* oy, double* oth,
+                            unsigned long long* adm = nullptr)
 {
-    for (int k = lane; k < n; k += 32) { lab[k] = k; csz[k] = 1; }
-    __syncwarp();
     const double d2max = p.clus_dist * p.clus_dist;
+    for (int i = lane; i < n; i += 32) {
+        lab[i] = i; csz[i] = 1;
+        if (adm) {
+            const double xi = sx[i], yi = sy[i], ti = sth[i];
+            unsigned long long m0 = 0, m1 = 0;
+            for (int j = 0; j < n; ++j) {
+                const double dx = xi - sx[j], dy = yi - sy[j];
+                const double d2 = dx * dx + dy * dy;
+                if (j != i && d2 < d2max && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad)) { if (j < 64) m0 |= 1ull << j; else m1 |= 1ull << (j - 64); }
+            }
+            adm[2 * i] = m0; adm[2 * i + 1] = m1;
+        }
+    }
+    __syncwarp();
     for (;;) {
         int pick_i = -1, pick_j = -1;
         for (int c0 = 0; c0 < n; c0 += 32) {
@@ -1186,11 +1203,26 @@ __device__ int warp_cluster(const double* sx, const double* sy, const double* st
                 const int li = lab[i];
                 const double xi = sx[i], yi = sy[i], ti = sth[i];
                 double best = CUDART_INF;
-                for (int j = 0; j < n; ++j) {
-                    if (lab[j] == li) continue;
-                    const double dx = xi - sx[j], dy = yi - sy[j];
-                    const double d2 = dx * dx + dy * dy;
-                    if (d2 < best && d2 < d2max && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad)) { best = d2; bj = j; }
+                if (adm) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned long long wbits = adm[2 * i + h];
+                        while (wbits) {
+                            const int j = __ffsll((long long)wbits) - 1 + 64 * h;
+                            wbits &= wbits - 1;
+                            if (lab[j] == li) continue;
+                            const double dx = xi - sx[j], dy = yi - sy[j];
+                            const double d2 = dx * dx + dy * dy;
+                            if (d2 < best) { best = d2; bj = j; }
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < n; ++j) {
+                        if (lab[j] == li) continue;
+                        const double dx = xi - sx[j], dy = yi - sy[j];
+                        const double d2 = dx * dx + dy * dy;
+                        if (d2 < best && d2 < d2max && (!by_orient || fabs(ti - sth[j]) < p.clus_orient_rad)) { best = d2; bj = j; }
+                    }
                 }
                 if (bj >= 0 && csz[li] + csz[lab[bj]] > p.clus_max) bj = -1;   // MAX_CLUSTER_SIZE, EdgeClusterer.cpp:179
             }
@@ -1254,26 +1286,40 @@ __device__ int warp_cluster(const double* sx, const double* sy, const double* st
     return ncl;
 }
 
-__global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams p)
+// CAP = shared-memory capacity per warp.  Two instantiations: <48> (3.4 KB per warp, 8 CTAs per SM) takes every set with
+// n <= 48 - all but a handful - and appends the others to a per-frame work list that <MAXC> processes afterwards.
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, DevParams p, int second)
 {
-    __shared__ double s_x[WPB][MAXC], s_y[WPB][MAXC], s_t[WPB][MAXC];
-    __shared__ double s_ox[WPB][MAXC], s_oy[WPB][MAXC], s_ot[WPB][MAXC];
-    __shared__ int s_lab[WPB][MAXC], s_csz[WPB][MAXC];
-    __shared__ double s_dk[WPB][MAXC], s_gk[WPB][MAXC];
+    __shared__ double s_x[WPB][CAP], s_y[WPB][CAP], s_t[WPB][CAP];
+    __shared__ double s_ox[WPB][CAP], s_oy[WPB][CAP], s_ot[WPB][CAP];
+    __shared__ int s_lab[WPB][CAP], s_csz[WPB][CAP];
+    __shared__ double s_dk[WPB][CAP], s_gk[WPB][CAP];
+    __shared__ unsigned long long s_adm[CAP == MAXC ? WPB : 1][CAP == MAXC ? 2 * MAXC : 1];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nL = b.nE[2 * f];
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
     double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
     const bool dumps = b.dumps && f == 0;
-    for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
+    // work list of the sets the first launch could not hold: indices in mateFlag (free until ncc2_best), count in counters[6]
+    int* big = b.mateFlag + (size_t)f * b.E;
+    unsigned long long* nbig = b.counters + (size_t)f * 8 + 6;
+    const int nwork = second ? (int)*nbig : nL;
+    for (int wi = blockIdx.x * WPB + w; wi < nwork; wi += gridDim.x * WPB) {
+        const int i = second ? big[wi] : wi;
         int n = ccount[i];
         if (n == 0) { if (dumps && lane == 0) b.dump[DUMP_S10].n[i] = 0; continue; }
+        if (n > CAP || (CAP < MAXC && n > p.clus_small)) {
+            if (CAP < MAXC) { if (lane == 0) big[(int)atomicAdd(nbig, 1ull)] = i; continue; }   // left for the MAXC instantiation
+            if (lane == 0) atomicExch(b.errFlag, 4);
+            n = CAP;
+        }
         const int st = cstart[i];
-        if (n > MAXC) { if (lane == 0) atomicExch(b.errFlag, 4); n = MAXC; }
         for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
         __syncwarp();
-        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_csz[w], s_dk[w], s_gk[w], s_ox[w], s_oy[w], s_ot[w]);
+        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_csz[w], s_dk[w], s_gk[w], s_ox[w], s_oy[w], s_ot[w],
+                                     CAP == MAXC ? s_adm[CAP == MAXC ? w : 0] : nullptr);
         __syncwarp();
         for (int k = lane; k < ncl; k += 32) {
             c_x[st + k] = s_ox[w][k]; c_y[st + k] = s_oy[w][k]; c_th[st + k] = s_ot[w][k];
@@ -1285,7 +1331,7 @@ __global__ void __launch_bounds__(32 * WPB) cluster_kernel(DevBatch b, DevParams
 }
 
 // S11 NCC of every cluster centre against the left patches (raw images, :1500) + S12 arg-max (first maximum wins, :941-951)
-__global__ void __launch_bounds__(32 * WPB) ncc2_best_kernel(DevBatch b, DevParams p)
+__global__ void __launch_bounds__(32 * WPB, 6) ncc2_best_kernel(DevBatch b, DevParams p)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int imgL = 2 * f, imgR = 2 * f + 1;
@@ -1465,7 +1511,9 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
     EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 1)));
-    EBVO_KERNEL(prof, "cluster", st, (cluster_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    constexpr int CL_SMALL = 48;
+    EBVO_KERNEL(prof, "cluster", st, (cluster_kernel<CL_SMALL, 8><<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, 0)));
+    EBVO_KERNEL(prof, "cluster_big", st, (cluster_kernel<MAXC, 4><<<dim3(16, nFrames), 32 * WPB, 0, st>>>(b, p, 1)));
     EBVO_KERNEL(prof, "ncc2_best", st, (ncc2_best_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 

@@ -304,3 +304,17 @@ def test_multi_context_batch_entry_point():
     assert np.array_equal(n, nref) and n.min() > 500
     for f in range(7):
         assert np.array_equal(out[f, :n[f]], ref[f, :n[f]])
+
+
+def test_clusterer_work_list_path(kitti_case, monkeypatch):
+    """Candidate sets beyond the small-capacity clusterer launch (48) go through a per-frame work list to the MAXC
+    launch; such sets are rare, so EBVO_CLUSTER_SMALL=6 forces a third of all sets onto that path: same result."""
+    k = kitti_case
+    monkeypatch.setenv("EBVO_CLUSTER_SMALL", "6")
+    ctx = _lib.Context(0, 1241, 376, max_batch=1, max_edges=65536)
+    ctx.set_stage_dumps(True)
+    mates = ctx.stereo_match(_calib(k["cal"]), k["L"], k["R"], _lib.edges_from_xyt(k["eL"]), _lib.edges_from_xyt(k["eR"]))
+    assert _check_stages(ctx, k["res"]) == 0
+    ctx.close()
+    assert np.array_equal(mates["left_index"], k["res"].mate_left)
+    assert np.hypot(k["res"].mate_right[:, 0] - mates["rx"], k["res"].mate_right[:, 1] - mates["ry"]).max() < 1e-3
