@@ -61,9 +61,9 @@ __global__ void sobel_kernel(DevBatch b)
     float gy = (at(yp, xm) - at(ym, xm)) * 0.125f + (at(yp, x) - at(ym, x)) * 0.25f + (at(yp, xp) - at(ym, xp)) * 0.125f;
     const size_t o = (size_t)f * b.gStride + (size_t)y * b.W + x;
     if (b.pk) b.pk[o] = make_float4(at(y, x), gx, gy, 0.f);
-    if (b.pkh) {    // {u16 I, half gx, half gy}: Sobel/8 values are k/8 with |k| <= 1020, exact in fp16; 8 bytes per pixel
+    if (b.pkh) {    // {half I, -, half gx, half gy}: 8-bit intensities and Sobel/8 values (k/8, |k| <= 1020) are exact in fp16; 8 bytes per pixel
         const __half2 hg = __floats2half2_rn(gx, gy);
-        b.pkh[o] = make_uint2((uint32_t)(int)at(y, x), *reinterpret_cast<const uint32_t*>(&hg));
+        b.pkh[o] = make_uint2((uint32_t)__half_as_ushort(__float2half_rn(at(y, x))), *reinterpret_cast<const uint32_t*>(&hg));
     }
     if (b.pk16) {   // {I, 8*gx, 8*gy} as exact 16-bit integers (|8*g| <= 1020): 8 bytes per pixel
         const int i8 = (int)at(y, x), gx8 = (int)(gx * 8.f), gy8 = (int)(gy * 8.f);
@@ -796,10 +796,10 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 // that edge's surviving candidates: the left patches are sampled once per left edge, not once per candidate.
 // Lanes 0-15 own the "+" patch, lanes 16-31 the "-" patch (cell t = hl + 16 m, m < 4, t < 49), so the two patch
 // means reduce inside half-warps.  Per candidate each half-warp stages the pixels its patch can reach while alpha
-// stays within +-R px of the build position into a warp-private tile: a double2 plane {gx, gy} and a double plane
-// I (no conversion instructions inside the iteration).  Coordinates beyond the image read the clamped border
+// stays within +-R px of the build position into a warp-private tile of packed {half I, half gx, half gy} pixels
+// (exact values, 8 B each, widened to double per corner).  Coordinates beyond the image read the clamped border
 // pixel, which is what util_bilinear_Sample_F's coordinate clamp produces (utility.h:161-166).  The four corners
-// of a sample are then 4 LDS.128 + 4 LDS.64 instead of 12 scattered global loads (the gather kernel is bound by
+// of a sample are then 4 LDS.64 instead of 12 scattered global loads (the gather kernel is bound by
 // L1 wavefronts: ~10 cache lines per load instruction).  The tile is rebuilt when alpha leaves the +-R window
 // (3 % of the candidates).  Arithmetic: FP64 four-corner blends of I, gx and gy, each rounded to float
 // (util_bilinear_Sample_F returns float); FP64 residuals, Huber weights and normal equations; the divisions by
@@ -842,14 +842,23 @@ __device__ __forceinline__ double div_fast(double a, double b)
     const double r = fma(-b, q, a);
     return fma(r, y, q);
 }
+// exact fp16 -> fp64 (one F2F.F64.F16, the half selected in place from the low 16 bits of the argument)
+__device__ __forceinline__ double h2d(unsigned int lo16)
+{
+    double d;
+    asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"((unsigned short)lo16));
+    return d;
+}
 template <int GT64_MAXPX, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
 {
-    __shared__ double2 s_tile[WPB][2][GT64_MAXPX + GT64_MAXPX / 2];   // per sub-tile: {gx, gy} plane, then the I plane
+    // pixels are staged in the packed global format {half I, -, half gx, half gy} (exact values) and widened to double per
+    // corner (one F2F.F64.F16 each on the XU pipe): 8 B instead of 24 B per corner through the shared-memory pipe, which is
+    // what binds this kernel, and the tile fill is a plain copy
+    __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int hw = lane >> 4, hl = lane & 15;
-    double2* tG = s_tile[w][hw];
-    double* tI = reinterpret_cast<double*>(tG + GT64_MAXPX);
+    uint2* tF = s_tile[w][hw];
     const int W = b.W, H = b.H;
     const double huber = p.gn_huber;
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
@@ -861,7 +870,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
         const int f = (f0 + ff) % nFrames;
         const int imgL = 2 * f;
         const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
-        const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {u16 I, half gx, half gy}
+        const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {half I, -, half gx, half gy}
         const int* c_owner = b.c_owner + (size_t)f * b.P;
         double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
         double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
@@ -912,7 +921,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
                     for (;;) {
                         TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
                         THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
-                        // row pitch in 8-byte words: residues 0, +-1, +-2 and 8 (mod 16 banks) fold neighbouring rows onto the same banks
+                        // row pitch in 8-byte pixels: residues 0, +-1, +-2 and 8 (mod 16 bank pairs) fold neighbouring rows onto the same banks
                         while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
                         if (TWp * THp <= GT64_MAXPX || R == 0) break;
                         --R;
@@ -939,9 +948,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
                         for (int e = hl; e < npx; e += 16) {
                             const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
                             const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
-                            const uint2 u = __ldg(PK + (Y * W + X));
-                            const float2 gg = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                            tI[e] = (double)(int)(u.x & 0xffffu); tG[e] = make_double2((double)gg.x, (double)gg.y);
+                            tF[e] = __ldg(PK + (Y * W + X));
                         }
                         __syncwarp();
                     }
@@ -959,10 +966,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
                             const int o = yi * TWp + xi;
                             // FP64 blends rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172) per channel
                             const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
-                            const double2 g00 = tG[o], g10 = tG[o + 1], g01 = tG[o + TWp], g11 = tG[o + TWp + 1];
-                            vi[m] = round_to_float(w00 * tI[o] + w10 * tI[o + 1] + w01 * tI[o + TWp] + w11 * tI[o + TWp + 1]);
-                            const double gx = round_to_float(w00 * g00.x + w10 * g10.x + w01 * g01.x + w11 * g11.x);
-                            const double gy = round_to_float(w00 * g00.y + w10 * g10.y + w01 * g01.y + w11 * g11.y);
+                            const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
+                            vi[m] = round_to_float(w00 * h2d(p00.x) + w10 * h2d(p10.x) + w01 * h2d(p01.x) + w11 * h2d(p11.x));
+                            const double gx = round_to_float(w00 * h2d(p00.y) + w10 * h2d(p10.y) + w01 * h2d(p01.y) + w11 * h2d(p11.y));
+                            const double gy = round_to_float(w00 * h2d(p00.y >> 16) + w10 * h2d(p10.y >> 16) + w01 * h2d(p01.y >> 16) + w11 * h2d(p11.y >> 16));
                             vg[m] = -gx * dirx + gy * diry;                                   // :1240
                             sR += vi[m];
                         }
@@ -1535,7 +1542,7 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
     else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else {
         static bool attr = false;
-        if (!attr) {   // 48 KB of tiles per CTA: ask for the large shared-memory carve-out so that 4 CTAs fit per SM
+        if (!attr) {   // 16 KB of tiles per CTA
             cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr = true;
         }
