@@ -75,6 +75,8 @@ struct ebvo_ctx {
     int curFrames = 0;
     std::vector<int> h_counts;
     // pipelined batch call: copy-in / copy-out streams and per-sub-batch events
+    alignas(64) unsigned char tmap[128];          // CUtensorMap of the image array for the current geometry
+    int tmapW = 0, tmapH = 0;
     cudaStream_t stIn = nullptr, stOut = nullptr;
     std::vector<cudaEvent_t> evIn, evDone;
 };
@@ -133,6 +135,12 @@ int configure(ebvo_ctx* ctx, int w, int h, int nFrames)
     b.raw = ctx->d_raw; b.und = ctx->d_raw;
     b.descL = nullptr; b.descR = nullptr;
     b.siftDev = ctx->params.sift_mode == 1 ? 1 : 0;
+    b.imgBase = 0; b.tmap = ctx->tmap;
+    if (w != ctx->tmapW || h != ctx->tmapH) {
+        const int r = make_toed_tensor_map(ctx->tmap, ctx->d_raw, w, h, b.pitch, b.imgStride, 2 * ctx->maxB);
+        if (r) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string(r) + ")"; return EBVO_ERR_CUDA; }
+        ctx->tmapW = w; ctx->tmapH = h;
+    }
     b.dumps = 0;
     ctx->curFrames = nFrames;
     return EBVO_OK;
@@ -529,6 +537,7 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     DevBatch v = b;
     const size_t i0 = 2 * (size_t)f0, F0 = (size_t)f0, E = (size_t)b.E, P = (size_t)b.P;
     v.nFrames = n; v.nImages = 2 * n;
+    v.imgBase = b.imgBase + 2 * f0;
     v.raw += i0 * b.imgStride; v.und += i0 * b.imgStride;
     v.mask += i0 * b.maskStride; v.sp += i0 * b.spStride; v.rowcnt += i0 * b.rowStride; v.rowoff += i0 * b.rowStride;
     v.coords += i0 * E; v.ex += i0 * E; v.ey += i0 * E; v.eth += i0 * E; v.nE += i0; v.nTot += i0;

@@ -37,6 +37,8 @@ struct DevBatch {
     int P;                 // candidate pool capacity per frame
     int NB;                // edge blocks per image (= E/32)
     int nImages, nFrames;
+    int imgBase;           // index of this view's first image in the context's image array (sub-batch views; TMA coordinate)
+    const void* tmap;      // host pointer to the 128-byte CUtensorMap of the image array (toed.cu)
     const uint8_t* raw; const uint8_t* und; size_t imgStride;
     uint32_t* mask; size_t maskStride;
     float2* sp; size_t spStride;          // sub-pixel offsets (s*nx, s*ny) at edge samples
@@ -87,6 +89,7 @@ void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* 
 void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);
 void launch_undistort(const uint8_t* src, int srcPitch, uint8_t* dst, int dstPitch, int W, int H, const double K[9], const double dist[4], cudaStream_t st);   // undistort.cu   // blur + descriptors of every edge (sift.cu)
 void upload_toed_tables();
+int make_toed_tensor_map(void* out128, const uint8_t* base, int W, int H, int pitch, size_t imgStride, int nImages);
 
 // stage-dump support (debug): gate lists for stages 0..2 on frame 0
 void launch_gate_count(const DevBatch& b, const DevParams& p, const double* F21, int mode, int* d_counts, cudaStream_t st);

@@ -15,6 +15,7 @@
 //                         are evaluated only at the surviving edge samples (about 2% of the interp grid).
 #include "ebvo_internal.cuh"
 #include <cmath>
+#include <cuda.h>
 
 namespace ebvo {
 
@@ -53,9 +54,23 @@ constexpr size_t TOED_SMEM_A = sizeof(float) * (IN_H * IN_WP + 6 * IN_H * OWP);
 constexpr size_t TOED_SMEM_B = sizeof(float) * (3 * IH * IWP);
 constexpr size_t TOED_SMEM = TOED_SMEM_A > TOED_SMEM_B ? TOED_SMEM_A : TOED_SMEM_B;
 
-__global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch b, float magThresh, int border)
+// ---- TMA plumbing for the input tile -----------------------------------------------------------------------
+// The u8 tile + halo is fetched by ONE bulk tensor copy (cp.async.bulk.tensor.3d, SASS UTMALDG) from a tensor map over
+// the whole image array [image][row][column]: the hardware clips the 64 x 52 box against the image and fills what lies
+// outside with zeros, which is exactly the zero padding of the reference's convolution (cpu_toed.cpp:204-205), so the
+// per-pixel bounds tests and the scalar gather loop disappear.  Completion is signalled on an mbarrier.
+constexpr int TMA_BOX_W = 64;                         // box width in bytes (a multiple of 16 covering IN_W = 52 plus the alignment shift)
+constexpr int TMA_XPAD = 16;                          // the box starts at x0 - 16, not x0 - HALO: its first byte must be 16-byte aligned
+static_assert(TW % 16 == 0 && TMA_XPAD >= HALO && TMA_XPAD - HALO + IN_W <= TMA_BOX_W, "TMA box must cover the tile + halo");
+constexpr int TMA_BYTES = TMA_BOX_W * IN_H;           // 3328
+constexpr size_t TOED_U8_OFF = 11264;                 // 128-byte aligned offset inside the (not yet written) row-pass planes
+static_assert(TOED_U8_OFF >= sizeof(float) * IN_H * IN_WP && TOED_U8_OFF % 128 == 0, "u8 tile must not overlap s_in");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch b, const __grid_constant__ CUtensorMap tmap, float magThresh, int border)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* s_in = smem;
     float* s_row = s_in + IN_H * IN_WP;  // planes: 0 G17, 1 Gx17, 2 G19, 3 Gx19, 4 Gs, 5 Gxs
     float* s_ix = smem;                  // aliases s_in / s_row (see TOED_SMEM)
@@ -63,18 +78,33 @@ __global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch
     float* s_mag = s_iy + IH * IWP;
     __shared__ int s_tot;
 
+    __shared__ __align__(8) unsigned long long s_bar;
     const int tid = threadIdx.x, img = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const uint8_t* src = b.und + (size_t)img * b.imgStride;
     if (tid == 0) s_tot = 0;
 
-    // ---- stage 0: uint8 tile + halo -> float, zero padding outside the image (cpu_toed.cpp:204-205) ----
+    // ---- stage 0: uint8 tile + halo by TMA (zero fill outside the image), then u8 -> float ----
+    const uint8_t* s_u8 = reinterpret_cast<const uint8_t*>(smem) + TOED_U8_OFF;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TMA_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(s_u8)), "l"(&tmap), "r"(x0 - TMA_XPAD), "r"(y0 - HALO), "r"(b.imgBase + img), "r"(bar) : "memory");
+    }
+    {   // wait for the bytes (phase 0); a bounded spin: a mis-programmed copy traps instead of hanging the GPU
+        uint32_t done = 0;
+        for (int spin = 0; !done && spin < (1 << 24); ++spin)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+        if (!done) __trap();
+    }
     for (int it = tid; it < IN_H * IN_W; it += TOED_THREADS) {
-        int r = it / IN_W, c = it - r * IN_W;
-        int gy = y0 - HALO + r, gx = x0 - HALO + c;
-        float v = 0.f;
-        if (gy >= 0 && gy < b.H && gx >= 0 && gx < b.W) v = (float)src[(size_t)gy * b.pitch + gx];
-        s_in[r * IN_WP + c] = v;
+        const int r = it / IN_W, c = it - r * IN_W;
+        s_in[r * IN_WP + c] = (float)s_u8[r * TMA_BOX_W + (TMA_XPAD - HALO) + c];
     }
     __syncthreads();
 
@@ -335,6 +365,26 @@ __global__ void __launch_bounds__(128) toed_orient_kernel(DevBatch b)
     b.eth[o] = (double)th;
 }
 
+// Tensor map over the context's image array: dims (W, H, images) of u8, strides (pitch, imgStride) bytes, box 64 x 52 x 1.
+int make_toed_tensor_map(void* out128, const uint8_t* base, int W, int H, int pitch, size_t imgStride, int nImages)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nImages};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)imgStride};
+    const cuuint32_t box[3] = {(cuuint32_t)TMA_BOX_W, (cuuint32_t)IN_H, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out128), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_t st, Prof* prof)
 {
     static bool attr = false;
@@ -345,7 +395,7 @@ void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_
     cudaMemsetAsync(b.rowcnt, 0, sizeof(int) * b.rowStride * nImages, st);
     cudaMemsetAsync(b.nTot, 0, sizeof(int) * nImages, st);
     dim3 gA(b.tilesX, b.tilesY, nImages);
-    EBVO_KERNEL(prof, "toed_grad_nms", st, (toed_grad_nms_kernel<<<gA, TOED_THREADS, TOED_SMEM, st>>>(b, p.toed_mag_thresh, p.toed_border)));
+    EBVO_KERNEL(prof, "toed_grad_nms", st, (toed_grad_nms_kernel<<<gA, TOED_THREADS, TOED_SMEM, st>>>(b, *reinterpret_cast<const CUtensorMap*>(b.tmap), p.toed_mag_thresh, p.toed_border)));
     EBVO_KERNEL(prof, "toed_scan", st, (toed_scan_kernel<<<nImages, 1024, 0, st>>>(b)));
     dim3 gE((b.H2 + 7) / 8, nImages);
     EBVO_KERNEL(prof, "toed_expand", st, (toed_expand_kernel<<<gE, 256, 0, st>>>(b)));
