@@ -79,3 +79,23 @@ def test_stereo_sift_on_against_oracle_with_cv2_descriptors():
     io = np.searchsorted(res.mate_left, common); ig = np.searchsorted(mates["left_index"], common)
     d = np.hypot(res.mate_right[io, 0] - mates["rx"][ig], res.mate_right[io, 1] - mates["ry"][ig])
     assert (d > 1e-3).mean() <= 2e-3
+
+
+def test_sift_on_batch_equals_single_frames():
+    """sift_mode 1 through the pipelined batch call (descriptor buffers are per frame; sub-batch views shift them)."""
+    cal = synth.kitti_calib(320, 200)
+    pairs = [synth.stereo_pair(cal, f) for f in range(3)]
+    Ls = [pairs[f % 3][0] for f in range(35)]
+    Rs = [pairs[f % 3][1] for f in range(35)]
+    prm = _lib.default_params(); prm.sift_mode = 1
+    ctx = _lib.Context(0, 320, 200, max_batch=35, max_edges=16384, params=prm)
+    calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    out, n = ctx.stereo_batch(calib, Ls, Rs, cap=8000)
+    singles = [ctx.stereo_frame(calib, Ls[f], Rs[f], want_edges=False) for f in range(3)]
+    prm0 = _lib.default_params()
+    ctx0 = _lib.Context(0, 320, 200, max_batch=1, max_edges=16384, params=prm0)
+    off = ctx0.stereo_frame(calib, Ls[0], Rs[0], want_edges=False)
+    ctx.close(); ctx0.close()
+    for f in range(35):
+        assert n[f] == len(singles[f % 3]) and np.array_equal(out[f, :n[f]], singles[f % 3])
+    assert len(off) != len(singles[0])          # SIFT-on really ran (it prunes candidates)
