@@ -52,6 +52,22 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
 
     def run(self):
+        try:      # NVML directly (a few ms per sample); nvidia-smi below as the fallback
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), "%.1f" % pw] + ["Active" if r & bits[k] else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+                time.sleep(0.05)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:

@@ -338,7 +338,9 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     *out = ctx;   // returned even on failure so that ebvo_last_error() can be read; caller destroys it
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-    upload_toed_tables();
+    init_toed_device();
+    init_match_device();
+    if (ctx->params.sift_mode == 1) upload_sift_tables();
     DevBatch& b = ctx->b;
     memset(&b, 0, sizeof b);
     const int B = max_batch, nImg = 2 * B;

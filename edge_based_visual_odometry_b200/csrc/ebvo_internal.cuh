@@ -89,6 +89,9 @@ void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* 
 void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);
 void launch_undistort(const uint8_t* src, int srcPitch, uint8_t* dst, int dstPitch, int W, int H, const double K[9], const double dist[4], cudaStream_t st);   // undistort.cu   // blur + descriptors of every edge (sift.cu)
 void upload_toed_tables();
+void upload_sift_tables();
+void init_toed_device();    // per-device: constant tables + function attributes (call after cudaSetDevice)
+void init_match_device();
 int make_toed_tensor_map(void* out128, const uint8_t* base, int W, int H, int pitch, size_t imgStride, int nImages);
 
 // stage-dump support (debug): gate lists for stages 0..2 on frame 0

@@ -1483,7 +1483,12 @@ __global__ void snapshot_kernel(DevBatch b, int src, const int* offsets, int* ri
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
-static int g_sms = 0;
+static int g_sms = 0;     // SM count (every GPU of a box is the same model)
+
+void init_match_device()   // per-device function attributes, called by ebvo_create after cudaSetDevice
+{
+    cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 static dim3 warp_grid(int nFrames)
 {
@@ -1541,11 +1546,6 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
     if (p.gn_mode == 2) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else {
-        static bool attr = false;
-        if (!attr) {   // 16 KB of tiles per CTA
-            cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr = true;
-        }
         if (!g_sms) warp_grid(1);
         EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<g_sms * 4, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
     }

@@ -185,8 +185,6 @@ __global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
 
 void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, Prof* prof)
 {
-    static bool tables = false;
-    if (!tables) { upload_sift_tables(); tables = true; }
     dim3 gB((b.W + 31) / 32, (b.H + 31) / 32, nImages);
     EBVO_KERNEL(prof, "sift_blur", st, (sift_blur_kernel<<<gB, 256, 0, st>>>(b)));
     int sms = 148;

@@ -385,13 +385,17 @@ int make_toed_tensor_map(void* out128, const uint8_t* base, int W, int H, int pi
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// per-DEVICE initialisation (constant tables, function attributes): called by ebvo_create after cudaSetDevice, so that
+// every GPU a process opens a context on is set up (ebvo_stereo_batch_multi drives several devices from one process)
+void init_toed_device()
+{
+    cudaFuncSetAttribute(toed_grad_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOED_SMEM);
+    cudaFuncSetAttribute(toed_grad_nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    upload_toed_tables();
+}
+
 void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_t st, Prof* prof)
 {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(toed_grad_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOED_SMEM);
-        attr = true;
-    }
     cudaMemsetAsync(b.rowcnt, 0, sizeof(int) * b.rowStride * nImages, st);
     cudaMemsetAsync(b.nTot, 0, sizeof(int) * nImages, st);
     dim3 gA(b.tilesX, b.tilesY, nImages);
