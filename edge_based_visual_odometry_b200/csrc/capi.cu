@@ -77,7 +77,7 @@ struct ebvo_ctx {
     // pipelined batch call: copy-in / copy-out streams and per-sub-batch events
     alignas(64) unsigned char tmap[128];          // CUtensorMap of the image array for the current geometry
     int tmapW = 0, tmapH = 0;
-    cudaStream_t stIn = nullptr, stOut = nullptr;
+    cudaStream_t stIn = nullptr, stOut = nullptr, st2 = nullptr;   // st2: second compute stream (odd sub-batches)
     std::vector<cudaEvent_t> evIn, evDone;
 };
 
@@ -401,6 +401,7 @@ void ebvo_destroy(ebvo_ctx* ctx)
     for (cudaEvent_t e : ctx->evDone) cudaEventDestroy(e);
     if (ctx->stIn) cudaStreamDestroy(ctx->stIn);
     if (ctx->stOut) cudaStreamDestroy(ctx->stOut);
+    if (ctx->st2) cudaStreamDestroy(ctx->st2);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -649,7 +650,10 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
     // Software pipeline over sub-batches of SB frames: the images of sub-batch k+1 are copied in and the mates of
     // sub-batch k-1 copied out while the kernels of sub-batch k run (three streams, events in between).
     const int SB = 32, nsb = (n_frames + SB - 1) / SB;
-    if (!ctx->stIn) { CK(cudaStreamCreateWithFlags(&ctx->stIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->stOut, cudaStreamNonBlocking)); }
+    if (!ctx->stIn) {
+        CK(cudaStreamCreateWithFlags(&ctx->stIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->stOut, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking));
+    }
     while ((int)ctx->evIn.size() < nsb) {
         cudaEvent_t a, b;
         CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -688,12 +692,15 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         if (k + 1 < nsb && (rc = upload(k + 1))) return rc;
         const int f0 = k * SB, n = std::min(n_frames, f0 + SB) - f0;
         const DevBatch v = frame_view(b, f0, n);
-        CK(cudaStreamWaitEvent(ctx->st, ctx->evIn[k], 0));
-        launch_toed(v, ctx->dp, 2 * n, ctx->st, &ctx->prof);
-        launch_match(v, ctx->dp, F21, n, ctx->params.sift_mode == 1, ctx->st, &ctx->prof);
-        launch_compact(v, n, ctx->d_out + (size_t)f0 * b.E, b.E, ctx->st, &ctx->prof);
+        // sub-batches alternate between two compute streams: the tail of one sub-batch's kernels (a persistent kernel waits for
+        // its slowest warp) is filled by the head of the next one's; the sub-batches touch disjoint buffers
+        cudaStream_t cs = (k & 1) ? ctx->st2 : ctx->st;
+        CK(cudaStreamWaitEvent(cs, ctx->evIn[k], 0));
+        launch_toed(v, ctx->dp, 2 * n, cs, &ctx->prof);
+        launch_match(v, ctx->dp, F21, n, ctx->params.sift_mode == 1, cs, &ctx->prof);
+        launch_compact(v, n, ctx->d_out + (size_t)f0 * b.E, b.E, cs, &ctx->prof);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->evDone[k], ctx->st));
+        CK(cudaEventRecord(ctx->evDone[k], cs));
         if (k >= 1 && (rc = download(k - 1))) return rc;
     }
     if ((rc = download(nsb - 1))) return rc;
