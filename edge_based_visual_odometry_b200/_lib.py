@@ -19,7 +19,7 @@ EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
     "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
-    "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
+    "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_launch_count", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
 ]
 
@@ -75,6 +75,8 @@ def load():
         L.ebvo_stream.argtypes = [C.c_void_p]
         L.ebvo_destroy.argtypes = [C.c_void_p]
         L.ebvo_destroy.restype = None
+        L.ebvo_launch_count.restype = C.c_longlong
+        L.ebvo_launch_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -298,6 +300,9 @@ class Context:
         out = np.zeros((len(e), 2, 128), np.float32)
         self._ck(self.L.ebvo_sift_descriptors(self.h, _p(img), w, h, img.strides[0], _p(e), len(e), _p(out)))
         return out
+
+    def launch_count(self):
+        return int(self.L.ebvo_launch_count(self.h))
 
     def set_stage_dumps(self, enable=True):
         self._ck(self.L.ebvo_set_stage_dumps(self.h, int(enable)))

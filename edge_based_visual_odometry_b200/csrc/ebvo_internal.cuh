@@ -119,6 +119,7 @@ void launch_cluster_one(const double* x, const double* y, const double* th, int 
 // per-kernel event profiling
 struct Prof {
     bool enabled = false;
+    long long launchCount = 0;   // kernels launched through EBVO_KERNEL since the context was created (counted even when disabled)
     std::vector<std::string> names;
     std::vector<const char*> cnames;
     std::vector<float> ms;
@@ -134,6 +135,7 @@ struct Prof {
 
 #define EBVO_KERNEL(prof, name, st, ...)            \
     do {                                            \
+        if (prof) ++(prof)->launchCount;            \
         if ((prof) && (prof)->enabled) (prof)->begin(name, st); \
         __VA_ARGS__;                                \
         if ((prof) && (prof)->enabled) (prof)->end(st);         \

@@ -179,6 +179,8 @@ int ebvo_stage_fetch(ebvo_ctx* ctx, int stage, int* offsets, int* ridx, double* 
  * stream when profiling is enabled.  names: array of const char* owned by the library. */
 int ebvo_set_profiling(ebvo_ctx* ctx, int enable);
 int ebvo_get_kernel_times(ebvo_ctx* ctx, const char*** names, const float** ms, const int** launches, int* n);
+/* Number of kernels the context has launched since it was created (monotonic; counted with or without profiling). */
+long long ebvo_launch_count(ebvo_ctx* ctx);
 /* The CUDA stream (cudaStream_t) the context launches on, for external event timing. */
 void* ebvo_stream(ebvo_ctx* ctx);
 
