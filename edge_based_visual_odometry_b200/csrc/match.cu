@@ -678,10 +678,12 @@ __global__ void __launch_bounds__(128) shift_kernel(DevBatch b, DevParams p, int
 }
 
 // ------------------------------------------------------------------------------------------------------
-// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  Three kernels (ebvo_params.gn_mode):
-//   gn_tile64_kernel (0, default)  reference arithmetic (FP64 blends rounded to float, FP64 residuals / weights /
-//                              normal equations); one warp per LEFT EDGE, right-view samples served from
-//                              warp-private shared-memory tiles
+// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  Four kernels (ebvo_params.gn_mode):
+//   gn_lerp64_kernel (0, default)  reference arithmetic (FP64 blends rounded to float, FP64 residuals / weights /
+//                              normal equations); persistent warps pulling pool-slot chunks, right-view samples
+//                              served from warp-private shared-memory tiles that are kept across the candidates
+//                              of a left edge, 3 sample rounds + a cooperative 49th sample
+//   gn_tile64_kernel (3)       the round-1 form of the same kernel (four-weight blend, 4 sample rounds); cross-check
 //   gn64_kernel (1)            the same arithmetic, one warp per candidate, samples gathered from global memory
 //                              (the simple form; kept as the cross-check of the tiled kernel)
 //   gn32_kernel (2)            everything FP32: 0.02 % of the mates move by > 1e-3 px (non-converging GN); opt-in
@@ -807,8 +809,18 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 // order).  Measured against the reference: identical to gn64_kernel (max 9e-7 px at the GN stage on 128 913
 // candidates, 6e-8 px on the final mates).
 // ------------------------------------------------------------------------------------------------------
+#ifndef GNL_MINB
+#define GNL_MINB 4
+#endif
+#ifndef GNL_PXV
+#define GNL_PXV 256
+#endif
+constexpr int GNL_PX = GNL_PXV;
 constexpr int GN_CHUNK = 8;        // pool slots fetched per atomic
-constexpr int GN_R = 5;            // tile reach along the epipolar direction (px) before a rebuild
+#ifndef GN_RV
+#define GN_RV 5
+#endif
+constexpr int GN_R = GN_RV;            // tile reach along the epipolar direction (px) before a rebuild
 
 __device__ __forceinline__ double half_sum(double v)   // sum over the 16 lanes of a half-warp, result in every lane
 {
@@ -987,6 +999,228 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
                             const double wg = wgt * gg;
                             Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
                         }
+                    }
+                    warp_sum2(Hh, bb_);
+                    ++niters;
+                    if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
+                    const double delta = -div_fast(bb_, Hh);
+                    alpha += delta;
+                    if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+                        cost = warp_sum(cost);
+                        const double rms = sqrt(cost / 98.0);
+                        score = rms; conf = exp(-rms / p.gn_huber);
+                        break;
+                    }
+                }
+                ++npairs;
+                if (lane == 0) {
+                    c_x[q] = xr + alpha * dirx;          // :1350-1352 (moved regardless of validity)
+                    c_y[q] = yr + alpha * diry;
+                    c_score[q] = score; c_conf[q] = conf;
+                }
+                }
+            }
+        }
+        if (lane == 0 && npairs) {
+            atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters);
+            atomicAdd(&b.counters[(size_t)f * 8 + 5], nbuilds);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// gn_lerp64_kernel (gn_mode 0, default).  Same decomposition, tiles and arithmetic class as gn_tile64_kernel, with three
+// changes that cut the instruction stream (FP64, XU and issue slots alike):
+//  * the four-corner blend is evaluated as two horizontal interpolations and one vertical one,
+//    top = v00 + a (v10 - v00), bot = v01 + a (v11 - v01), v = top + b (bot - top): 4 FP64 operations per channel
+//    instead of 4 + the shared weight products; the corner differences are exact in fp16 (|dI| <= 255,
+//    |8 dg| <= 2040 < 2^11), taken by HSUB2 on the packed pixels before widening;
+//  * a half-warp owns 49 samples = 3 full rounds + ONE sample.  gn_tile64_kernel spends a whole fourth round on
+//    it (2 active lanes of 32).  Here the two left-over samples of a candidate (cell (3,3) of each patch) are
+//    evaluated cooperatively: lane u < 12 handles (patch, channel, cell row), the pairs meet by one shuffle;
+//  * the patch centre + shift is added once per iteration, the rotated cell offset once per sample.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hsub2_u32(unsigned a, unsigned b)   // a - b on both halves
+{
+    unsigned d;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+template <int GT64_MAXPX, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
+{
+    __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hw = lane >> 4, hl = lane & 15;
+    uint2* tF = s_tile[w][hw];
+    // cooperative lanes of the left-over samples: u = 2 (3 patch + channel) + row
+    const int u = lane % 12;
+    const int cRow = u & 1, cCh = (u >> 1) % 3, cSmp = (u >> 1) / 3;
+    const uint2* tC = s_tile[w][cSmp];
+    const int W = b.W, H = b.H;
+    const double huber = p.gn_huber;
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
+    const int f0 = (int)(((long long)blockIdx.x * nFrames) / gridDim.x);
+    for (int ff = 0; ff < nFrames; ++ff) {
+        const int f = (f0 + ff) % nFrames;
+        const int imgL = 2 * f;
+        const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
+        const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {half I, -, half gx, half gy}
+        const int* c_owner = b.c_owner + (size_t)f * b.P;
+        double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
+        double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
+        unsigned long long* cursor = b.counters + (size_t)f * 8 + 7;
+        const int used = min(b.poolUsed[f], b.P);
+        unsigned long long npairs = 0, niters = 0, nbuilds = 0;
+        for (;;) {
+            int q0 = 0;
+            if (lane == 0) q0 = (int)atomicAdd(cursor, (unsigned long long)GN_CHUNK);
+            q0 = __shfl_sync(FULL, q0, 0);
+            if (q0 >= used) break;
+            const int q1 = min(q0 + GN_CHUNK, used);
+            int owner = -1;
+            double dirx = 0, diry = 0, cx = 0, cy = 0, hext = 0;
+            int Rint = 0;
+            bool tileValid = false;
+            double rx[3], ry[3], Lc[3], rx48 = 0, ry48 = 0, Lc48 = 0;
+            int TWp = 0, THp = 0, npx = 0, ox = 0, oy = 0, oxC = 0, oyC = 0;
+            float invTW = 0.f;
+            for (int q = q0; q < q1; ++q) {
+                const int i = c_owner[q];
+                if (i < 0) continue;          // dead slot (dropped by NCC / best-nearly-best)
+                if (i != owner) {
+                    owner = i;
+                    // ---- per left edge: geometry, centred left samples, tile shape ----
+                    const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
+                    dirx = ln[3]; diry = ln[4];
+                    const double st_ = ln[5], ct_ = ln[6];
+                    const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
+                    const double side = 7 / 2.0 + 1.0;                               // :1171
+                    cx = hw ? st_ * side : -st_ * side;                              // +-n*side, n = (-t.y, t.x) (:1169-1170)
+                    cy = hw ? -ct_ * side : ct_ * side;
+                    double sumL = 0;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const int t = hl + 16 * m;
+                        const int ii = t / 7 - 3, jj = t % 7 - 3;
+                        rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
+                        Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m];
+                    }
+                    rx48 = ct_ * 3 - st_ * 3; ry48 = st_ * 3 + ct_ * 3;              // cell (3, 3), t = 48
+                    Lc48 = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx48, (yL + cy) + ry48);
+                    sumL = half_sum(sumL) + Lc48;
+                    const double mL = sumL / 49.0;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) Lc[m] -= mL;
+                    Lc48 -= mL;
+                    // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
+                    hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
+                    int R = Rmax;
+                    for (;;) {
+                        TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
+                        THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
+                        // row pitch in 8-byte pixels: residues 0, +-1, +-2 and 8 (mod 16 bank pairs) fold neighbouring rows onto the same banks
+                        while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
+                        if (TWp * THp <= GT64_MAXPX || R == 0) break;
+                        --R;
+                    }
+                    Rint = R;
+                    npx = TWp * THp;
+                    invTW = 1.0f / (float)TWp;
+                    tileValid = false;           // the tile shape belongs to the left edge
+                }
+                {
+                const double xr = c_x[q], yr = c_y[q];
+                const double xc = xr + cx, yc = yr + cy;      // patch centre at alpha = 0 (:1203-1204)
+                double alpha = 0.0, score = 0.0, conf = 0.0, alpha0 = CUDART_NAN;
+                double Rv = (double)Rint - 1e-6;
+                if (tileValid) {
+                    // 78 % of the consecutive candidates of a left edge lie within 1 px of each other: keep the tile of the
+                    // previous candidate when this one's patch (at alpha = 0) sits inside it, with the reach the margins leave
+                    const double mx = fmin((xc - hext) - (double)ox, ((double)(ox + TWp - 1) - hext) - xc);
+                    const double my = fmin((yc - hext) - (double)oy, ((double)(oy + THp - 1) - hext) - yc);
+                    double reach = fmin(fmin(mx / fabs(dirx), my / fabs(diry)), (double)Rint);   // x / 0 = inf, 0 / 0 = NaN is ignored by fmin
+                    if (!(mx >= 0.0 && my >= 0.0)) reach = -1.0;
+                    reach = fmin(reach, __shfl_xor_sync(FULL, reach, 16));
+                    if (reach >= 1.0) { alpha0 = 0.0; Rv = reach - 1e-6; }
+                }
+                for (int it = 0; it < p.gn_max_iter; ++it) {
+                    const double xs = xc + alpha * dirx, ys = yc + alpha * diry;     // (location +- n*side) + shift (:1203-1204)
+                    if (!(fabs(alpha - alpha0) <= Rv)) {
+                        // ---- (re)build this half-warp's sub-tile around the current position ----
+                        alpha0 = alpha; Rv = (double)Rint - 1e-6; tileValid = true;
+                        ox = __double2int_rd(xs - (Rint * fabs(dirx) + hext));
+                        oy = __double2int_rd(ys - (Rint * fabs(diry) + hext));
+                        oxC = __shfl_sync(FULL, ox, cSmp << 4); oyC = __shfl_sync(FULL, oy, cSmp << 4);
+                        ++nbuilds;
+                        __syncwarp();
+                        for (int e = hl; e < npx; e += 16) {
+                            const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
+                            const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
+                            tF[e] = __ldg(PK + (Y * W + X));
+                        }
+                        __syncwarp();
+                    }
+                    double vi[3], vg[3];
+                    double sR = 0;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const double x = xs + rx[m], y = ys + ry[m];
+                        const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
+                        const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
+                        const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
+                        const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
+                        const int o = yi * TWp + xi;
+                        const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
+                        const unsigned d0x = hsub2_u32(p10.x, p00.x), d0y = hsub2_u32(p10.y, p00.y);
+                        const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
+                        // FP64 interpolation rounded to float = util_bilinear_Sample_F (utility.h:159-172) per channel
+                        double top = fma(a, h2d(d0x), h2d(p00.x)), bot = fma(a, h2d(d1x), h2d(p01.x));
+                        vi[m] = round_to_float(fma(bb, bot - top, top));
+                        top = fma(a, h2d(d0y), h2d(p00.y)); bot = fma(a, h2d(d1y), h2d(p01.y));
+                        const double gx = round_to_float(fma(bb, bot - top, top));
+                        top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
+                        const double gy = round_to_float(fma(bb, bot - top, top));
+                        vg[m] = -gx * dirx + gy * diry;                                   // :1240
+                        sR += vi[m];
+                    }
+                    // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
+                    double vi48, vg48;
+                    {
+                        const double x = __shfl_sync(FULL, xs, cSmp << 4) + rx48, y = __shfl_sync(FULL, ys, cSmp << 4) + ry48;
+                        const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
+                        const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
+                        const int xi = (int)min((unsigned)(__double2loint(tx) - oxC), (unsigned)(TWp - 2));
+                        const int yi = (int)min((unsigned)(__double2loint(ty) - oyC), (unsigned)(THp - 2));
+                        const int o = (yi + cRow) * TWp + xi;
+                        const uint2 p0 = tC[o], p1 = tC[o + 1];
+                        const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
+                        const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
+                        const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));       // top (row 0) or bottom (row 1)
+                        const double oth = __shfl_xor_sync(FULL, lin, 1);
+                        const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
+                        const double v = round_to_float(fma(bb, bot - top, top));
+                        vi48 = __shfl_sync(FULL, v, 6 * hw);
+                        const double gx = __shfl_sync(FULL, v, 6 * hw + 2), gy = __shfl_sync(FULL, v, 6 * hw + 4);
+                        vg48 = -gx * dirx + gy * diry;
+                    }
+                    sR = half_sum(sR) + vi48;
+                    const double mR = div49(sR);
+                    double Hh = 0, bb_ = 0, cost = 0;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const double r = (m < 3 ? Lc[m] : Lc48) - ((m < 3 ? vi[m] : vi48) - mR);
+                        const double gg = m < 3 ? vg[m] : vg48;
+                        const double ar = fabs(r);
+#ifdef GN_HUBER_BF
+                        double wgt = huber * rcp_fast(fmax(ar, huber));
+                        if (ar <= huber) wgt = 1.0;
+#else
+                        double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
+#endif
+                        if (m == 3 && hl != 0) wgt = 0.0;                                 // sample 48 counts once per patch
+                        const double wg = wgt * gg;
+                        Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
                     }
                     warp_sum2(Hh, bb_);
                     ++niters;
@@ -1488,6 +1722,7 @@ static int g_sms = 0;     // SM count (every GPU of a box is the same model)
 void init_match_device()   // per-device function attributes, called by ebvo_create after cudaSetDevice
 {
     cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_lerp64_kernel<GNL_PX, GNL_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static dim3 warp_grid(int nFrames)
@@ -1545,9 +1780,12 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
     EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 0)));
     if (p.gn_mode == 2) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
-    else {
+    else if (p.gn_mode == 3) {   // the round-1 tiled kernel (weights form, 4 sample rounds), kept as a cross-check
         if (!g_sms) warp_grid(1);
         EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<g_sms * 4, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
+    } else {
+        if (!g_sms) warp_grid(1);
+        EBVO_KERNEL(prof, "gn", st, (gn_lerp64_kernel<GNL_PX, GNL_MINB><<<g_sms * GNL_MINB, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
     }
 }
 void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)

@@ -61,11 +61,13 @@ def test_kitti_stage_by_stage_on_oracle_edges(gpu_ctx, kitti_case):
     assert (np.diff(mates["left_index"]) > 0).all()                     # finalisation keeps left-edge order
 
 
-def test_gn_gather_kernel_cross_checks_the_tiled_kernel(gpu_ctx, kitti_case):
-    """gn_mode 1 (one warp per candidate, global-memory gathers) and the default shared-memory-tiled kernel implement
-    the same FP64 arithmetic with different data paths and lane layouts: their Gauss-Newton outputs agree to 1e-5 px."""
+@pytest.mark.parametrize("mode", [1, 3])
+def test_gn_gather_kernel_cross_checks_the_tiled_kernel(gpu_ctx, kitti_case, mode):
+    """gn_mode 1 (one warp per candidate, global-memory gathers), gn_mode 3 (the four-weight tiled kernel) and the
+    default kernel (interpolation form, cooperative 49th sample, tiles kept across candidates) implement the same
+    FP64 arithmetic with different data paths and lane layouts: their Gauss-Newton outputs agree to 1e-5 px."""
     k = kitti_case
-    prm = _lib.default_params(); prm.gn_mode = 1
+    prm = _lib.default_params(); prm.gn_mode = mode
     ctx = _lib.Context(0, 1241, 376, max_batch=1, max_edges=65536, params=prm)
     out = []
     for c in (ctx, gpu_ctx):
