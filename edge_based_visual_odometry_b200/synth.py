@@ -139,6 +139,7 @@ def _render(cal, layers, bg, view):
                 (Hinv[1, 0] * xx + Hinv[1, 1] * yy + Hinv[1, 2]) / w)
 
     u, v = to_left(bg["Z"])
+    u, v = u + bg.get("ou", 0.0), v + bg.get("ov", 0.0)   # camera translation of a sequence frame (stereo_sequence_pair)
     img = (bg["base"] + bg["ax"] * np.sin(u * bg["fx"] + bg["px"]) + bg["ay"] * np.cos(v * bg["fy"] + bg["py"])
            + bg["gx"] * (u / W - 0.5) + bg["gy"] * (v / H - 0.5))
     for L in layers:  # far -> near
@@ -203,6 +204,35 @@ def stereo_pair(cal: Calibration | str = "kitti", frame: int = 0, density: float
         img = img + noise_sigma * nrng.standard_normal(img.shape)
         out.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
     return out[0], out[1]
+
+
+def stereo_sequence_pair(cal: Calibration | str = "kitti", frame: int = 0, step=(0.35, 0.1), scene_seed: int = SEED0 + 4000,
+                         density: float = 1.0, noise_sigma: float = 1.0, blur_sigma: float = 1.0):
+    """Frame `frame` of a SEQUENCE: one layered scene (seed `scene_seed`) seen by a stereo rig that translates by
+    `frame * step` baselines along (x, y) between frames (BASELINE.json configs[3]: keyframe -> current-frame edge
+    tracking needs temporal correspondences, which independent per-frame scenes do not have).  A fronto-parallel
+    layer of stereo disparity d moves by -d * frame * step pixels in both views; noise is fresh per frame.
+    Returns (left_u8, right_u8, pose) with pose = camera translation in units of the baseline."""
+    if isinstance(cal, str):
+        cal = CALIBS[cal]()
+    layers, bg = make_scene(cal, scene_seed, density)
+    sx, sy = frame * step[0], frame * step[1]
+    moved = []
+    for L in layers:
+        M = dict(L)
+        cx, cy, a, b, phi = L["prm"]
+        M["prm"] = (cx - L["disp"] * sx, cy - L["disp"] * sy, a, b, phi)
+        moved.append(M)
+    bg = dict(bg, ou=2.0 * sx, ov=2.0 * sy)    # the background plane sits at 2 px of disparity (make_scene)
+    out = []
+    for k, view in enumerate(("left", "right")):
+        img = _render(cal, moved, bg, view)
+        if blur_sigma > 0:
+            img = ndimage.gaussian_filter(img, blur_sigma, mode="nearest")
+        nrng = np.random.default_rng([scene_seed, frame, 7919 + k])
+        img = img + noise_sigma * nrng.standard_normal(img.shape)
+        out.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+    return out[0], out[1], (sx, sy)
 
 
 def fundamental_matrices(cal: Calibration):

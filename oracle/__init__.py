@@ -30,12 +30,13 @@ def build(force: bool = False) -> None:
     need = force or not os.path.exists(os.path.join(_DIR, "libebvo_oracle.so"))
     if not need:
         so = os.path.getmtime(os.path.join(_DIR, "libebvo_oracle.so"))
-        need = any(os.path.getmtime(os.path.join(_DIR, f)) > so for f in ("toed_oracle.c", "stereo_oracle.cpp"))
+        need = any(os.path.getmtime(os.path.join(_DIR, f)) > so for f in ("toed_oracle.c", "stereo_oracle.cpp", "temporal_oracle.inl"))
     if need:
         subprocess.check_call(["make", "-C", _DIR, "libebvo_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/src/toed/cpu_toed.cpp") and (
             force or not os.path.exists(os.path.join(_DIR, "_ref", "libtoed_ref.so"))
-            or not os.path.exists(os.path.join(_DIR, "_ref", "libstereo_ref.so"))):
+            or not os.path.exists(os.path.join(_DIR, "_ref", "libstereo_ref.so"))
+            or not os.path.exists(os.path.join(_DIR, "_ref", "libtemporal_ref.so"))):
         subprocess.check_call(["make", "-C", _DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -286,3 +287,77 @@ def ref_cluster(xyt, by_orientation=True):
     cen, cnt = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.int32)
     k = stereo_ref_lib().rs_cluster(_p(xyt), n, int(by_orientation), _p(cen), _p(cnt))
     return cen[:k].copy(), cnt[:k].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# keyframe -> current-frame quad tracking (Temporal_Matches.cpp): restatement (temporal_oracle.inl) and the reference's
+# own source compiled in place (ref_temporal_harness.cpp -> _ref/libtemporal_ref.so)
+# ---------------------------------------------------------------------------------------------------------------
+TQ_STAGES = ["grid", "orient", "ncc", "bnb", "gn", "cluster"]
+_TREF = None
+
+
+def have_temporal_ref() -> bool:
+    return os.path.exists(os.path.join(_DIR, "_ref", "libtemporal_ref.so"))
+
+
+def temporal_ref_lib():
+    global _TREF
+    if _TREF is None:
+        build()
+        R = C.CDLL(os.path.join(_DIR, "_ref", "libtemporal_ref.so"))
+        R.rt_run.restype = C.c_void_p
+        R.rt_stage_total.restype = C.c_int
+        _TREF = R
+    return _TREF
+
+
+class QuadResult:
+    """Per-stage ragged lists of candidate quads, one list per keyframe mate: off[n_kf + 1], cf (index of the
+    current-frame mate), left / right (x, y, theta) of the cluster centres, ncc (left, right), score (left, right), valid."""
+
+    def __init__(self, total, get, n_kf):
+        self.stages = {}
+        for k, name in enumerate(TQ_STAGES):
+            tot = total(k)
+            off, cf, valid = np.zeros(n_kf + 1, np.int32), np.zeros(tot, np.int32), np.zeros(tot, np.int32)
+            l, r, ncc, sc = np.zeros((tot, 3)), np.zeros((tot, 3)), np.zeros((tot, 2)), np.zeros((tot, 2))
+            get(k, _p(off), _p(cf), _p(l), _p(r), _p(ncc), _p(sc), _p(valid))
+            self.stages[name] = dict(off=off, cf=cf, left=l, right=r, ncc=ncc, score=sc, valid=valid)
+        self.seconds = 0.0
+        self.counts = {}
+
+
+def _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask):
+    imgs = [np.ascontiguousarray(a, dtype=np.uint8) for a in (*kf_imgs, *cf_imgs)]   # (L_raw, L_und, R_und) x 2
+    H, W = imgs[0].shape
+    kf = np.ascontiguousarray(kf, dtype=np.float64).reshape(-1, 6)
+    cf = np.ascontiguousarray(cf, dtype=np.float64).reshape(-1, 6)
+    mask = None if kf_mask is None else np.ascontiguousarray(kf_mask, dtype=np.uint8)
+    return imgs, H, W, kf, cf, mask
+
+
+def temporal(kf_imgs, cf_imgs, kf, cf, kf_mask=None, cell=15, radius=30.0, orient_deg=10.0, ncc_thresh=0.8, bnb=0.8) -> QuadResult:
+    """Run the quad-tracking restatement.  kf_imgs / cf_imgs = (L_raw, L_und, R_und); kf / cf = n x 6 (left xyt, right xyt)."""
+    imgs, H, W, kf, cf, mask = _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask)
+    L = lib()
+    L.to_run.restype = C.c_void_p
+    L.to_stage_total.restype = C.c_int
+    h = C.c_void_p(L.to_run(*[_p(a) for a in imgs], H, W, _p(kf), len(kf), _p(mask), _p(cf), len(cf), cell, C.c_double(radius),
+                            C.c_double(orient_deg), C.c_double(ncc_thresh), C.c_double(bnb)))
+    res = QuadResult(lambda k: L.to_stage_total(h, k), lambda k, *a: L.to_get_stage(h, k, *a), len(kf))
+    sec, cnt = C.c_double(), (C.c_long * 2)()
+    L.to_get_stats(h, C.byref(sec), cnt)
+    res.seconds, res.counts = sec.value, dict(gn_pairs=cnt[0], gn_iters=cnt[1])
+    L.to_free(h)
+    return res
+
+
+def temporal_reference(kf_imgs, cf_imgs, kf, cf, kf_mask=None) -> QuadResult:
+    """Run the reference's own quad stages (oracle/ref_temporal_harness.cpp; SIFT-off; thresholds of Temporal_Matches.cpp:185-213)."""
+    imgs, H, W, kf, cf, mask = _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask)
+    R = temporal_ref_lib()
+    h = C.c_void_p(R.rt_run(*[_p(a) for a in imgs], H, W, _p(kf), len(kf), _p(mask), _p(cf), len(cf)))
+    res = QuadResult(lambda k: R.rt_stage_total(h, k), lambda k, *a: R.rt_get_stage(h, k, *a), len(kf))
+    R.rt_free(h)
+    return res

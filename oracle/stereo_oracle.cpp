@@ -49,6 +49,7 @@
 #include <limits>
 #include <map>
 #include <numeric>
+#include <unordered_set>
 #include <vector>
 #include <omp.h>
 
@@ -717,3 +718,6 @@ void so_free(void *h) { delete (Result *)h; }
 int so_stage_count() { return ST_COUNT; }
 
 }  // extern "C"
+
+// keyframe -> current-frame quad tracking (Temporal_Matches.cpp), same translation unit
+#include "temporal_oracle.inl"

@@ -50,3 +50,34 @@ for k, v in ref.stages.items():
         out[f"{k}_score"] = v["score"]
 np.savez_compressed(os.path.join(HERE, "stereo_ref_small.npz"), **out)
 print("stereo_ref_small", {k: int(v["off"][-1]) for k, v in ref.stages.items()}, len(ref.mate_left))
+
+# temporal_ref_small.npz : two frames of a 320x200 synthetic SEQUENCE (synth.stereo_sequence_pair), their stereo mates
+#                          (oracle) and the quad-tracking stages produced by the REFERENCE'S OWN Temporal_Matches.cpp
+#                          (oracle/_ref/libtemporal_ref.so, driven by oracle/ref_temporal_harness.cpp).
+assert oracle.have_temporal_ref(), "needs oracle/_ref/libtemporal_ref.so (build container only)"
+cal = synth.kitti_calib(320, 200)
+F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+fr = []
+for k in (0, 1):
+    L, R, _ = synth.stereo_sequence_pair(cal, k)
+    eL, _ = oracle.toed(L)
+    eR, _ = oracle.toed(R)
+    res = oracle.stereo(L, R, eL, eR, F21, want_dumps=False)
+    fr.append((L, R, np.concatenate([eL[res.mate_left], res.mate_right], 1)))
+(L0, R0, m0), (L1, R1, m1) = fr
+mask = (np.arange(len(m0)) % 3 != 1).astype(np.uint8)          # exercises the keyframe-mate selection
+ref = oracle.temporal_reference((L0, L0, R0), (L1, L1, R1), m0, m1, mask)
+out = dict(kfL=L0, kfR=R0, cfL=L1, cfR=R1, kf=m0, cf=m1, mask=mask)
+for k, v in ref.stages.items():
+    out[f"{k}_off"] = v["off"]
+    if k == "grid":      # 490 k entries: keep the per-keyframe-mate counts and an order-sensitive checksum of the lists
+        out["grid_cfsum"] = np.add.reduceat(np.concatenate([v["cf"].astype(np.int64) * (1 + np.arange(len(v["cf"])) % 7), [0]]), v["off"][:-1].clip(max=len(v["cf"])))
+        out["grid_cfsum"][np.diff(v["off"]) == 0] = 0
+    else:
+        out[f"{k}_cf"] = v["cf"]
+    if k in ("ncc", "bnb", "gn", "cluster"):
+        out[f"{k}_ncc"] = v["ncc"]
+    if k in ("gn", "cluster"):
+        out[f"{k}_left"], out[f"{k}_right"], out[f"{k}_score"], out[f"{k}_valid"] = v["left"], v["right"], v["score"], v["valid"]
+np.savez_compressed(os.path.join(HERE, "temporal_ref_small.npz"), **out)
+print("temporal_ref_small", {k: int(v["off"][-1]) for k, v in ref.stages.items()})
