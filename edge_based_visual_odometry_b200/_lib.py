@@ -21,6 +21,7 @@ EXPORTS = [
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
     "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_launch_count", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
+    "ebvo_temporal_quads", "ebvo_temporal_quads_stage", "ebvo_temporal_counters",
 ]
 
 
@@ -57,6 +58,27 @@ MATE_DTYPE = np.dtype([("left_index", "<i4"), ("reserved", "<i4"), ("lx", "<f8")
                        ("rx", "<f8"), ("ry", "<f8"), ("rtheta", "<f8"), ("score", "<f8")])
 assert EDGE_DTYPE.itemsize == C.sizeof(Edge) == 32
 assert MATE_DTYPE.itemsize == C.sizeof(Mate) == 64
+# ebvo_quad (include/ebvo_b200.h): one surviving quad of the keyframe -> current-frame tracking
+QUAD_DTYPE = np.dtype([("kf_index", "<i4"), ("cf_index", "<i4"), ("lx", "<f8"), ("ly", "<f8"), ("ltheta", "<f8"),
+                       ("rx", "<f8"), ("ry", "<f8"), ("rtheta", "<f8"), ("ncc_left", "<f8"), ("ncc_right", "<f8"),
+                       ("score_left", "<f8"), ("score_right", "<f8"), ("valid", "<i4"), ("reserved", "<i4")])
+assert QUAD_DTYPE.itemsize == 96
+TQ_STAGES = ["grid", "orient", "ncc", "bnb", "gn", "cluster"]
+
+
+class QuadParams(C.Structure):
+    """ebvo_quad_params: knobs of Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (reference values)."""
+    _fields_ = [("cell_size", C.c_int32), ("reserved", C.c_int32), ("grid_radius", C.c_double), ("orient_deg", C.c_double),
+                ("ncc_thresh", C.c_double), ("bnb_thresh", C.c_double)]
+
+
+def mates_from_arrays(left_xyt, right_xyt) -> np.ndarray:
+    """ebvo_mate records from (n, 3) left and right edges."""
+    l = np.asarray(left_xyt, np.float64).reshape(-1, 3); r = np.asarray(right_xyt, np.float64).reshape(-1, 3)
+    m = np.zeros(len(l), MATE_DTYPE)
+    m["left_index"] = np.arange(len(l))
+    m["lx"], m["ly"], m["ltheta"], m["rx"], m["ry"], m["rtheta"] = l[:, 0], l[:, 1], l[:, 2], r[:, 0], r[:, 1], r[:, 2]
+    return m
 
 _lib = None
 
@@ -275,6 +297,31 @@ class Context:
         n = C.c_int()
         self._ck(self.L.ebvo_cluster(self.h, _p(e), len(e), int(by_orientation), _p(cen), _p(lab), C.byref(n)))
         return cen[:n.value].copy(), lab[:len(e)].copy()
+
+    def temporal_quads(self, kf_imgs, cf_imgs, kf, cf, kf_mask=None, stage="cluster", params=None, cap=None):
+        """Keyframe -> current-frame quad tracking (ebvo_temporal_quads_stage).  kf_imgs / cf_imgs = (L_raw, L_und, R_und)
+        uint8 images; kf / cf = MATE_DTYPE arrays.  Returns (off[n_kf + 1], quads) after `stage`."""
+        imgs = [np.ascontiguousarray(a, np.uint8) for a in (*kf_imgs, *cf_imgs)]
+        h, w = imgs[0].shape
+        kf = np.ascontiguousarray(kf, MATE_DTYPE); cf = np.ascontiguousarray(cf, MATE_DTYPE)
+        mask = None if kf_mask is None else np.ascontiguousarray(kf_mask, np.uint8)
+        k = TQ_STAGES.index(stage) if isinstance(stage, str) else int(stage)
+        if cap is None:
+            cap = max(1, len(kf) * 128 if k >= 2 else len(kf) * max(len(cf), 1))
+            if k < 2:
+                cap = min(cap, 64 * 1024 * 1024)
+        off = np.zeros(len(kf) + 1, np.int32)
+        out = np.zeros(cap, QUAD_DTYPE)
+        n = C.c_int()
+        qp = C.byref(params) if params is not None else None
+        self._ck(self.L.ebvo_temporal_quads_stage(self.h, *[_p(a) for a in imgs], w, h, imgs[0].strides[0], _p(kf), len(kf), _p(mask),
+                                                  _p(cf), len(cf), qp, k, _p(off), _p(out), cap, C.byref(n)))
+        return off, out[:n.value].copy()
+
+    def temporal_counters(self):
+        c = (C.c_longlong * 8)()
+        self._ck(self.L.ebvo_temporal_counters(self.h, c))
+        return dict(gate_survivors=c[0], gn_problems=c[1], gn_iterations=c[2], grid_candidates=c[3], orient_survivors=c[4])
 
     def sobel(self, img):
         img = np.ascontiguousarray(img, np.uint8)

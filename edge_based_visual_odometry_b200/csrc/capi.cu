@@ -80,6 +80,7 @@ struct ebvo_ctx {
     cudaStream_t stIn = nullptr, stOut = nullptr, st2 = nullptr;   // st2: second compute stream (odd sub-batches)
     std::vector<cudaEvent_t> evIn, evDone;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    long long tqCounters[8] = {0};   // work counters of the last quad-tracking call
 };
 
 namespace {
@@ -309,6 +310,14 @@ int download_mates(ebvo_ctx* ctx, int nFrames, ebvo_mate* out, int cap, int* n_m
     return rc;
 }
 
+}  // namespace
+
+namespace {
+struct TqScratch {     // device allocations of one call (stream-ordered; the driver's pool makes repeated calls cheap)
+    cudaStream_t st; std::vector<void*> ptrs;
+    template <typename T> cudaError_t get(T** p, size_t n) { cudaError_t e = cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), st); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+    ~TqScratch() { for (void* q : ptrs) cudaFreeAsync(q, st); cudaStreamSynchronize(st); }
+};
 }  // namespace
 
 extern "C" {
@@ -850,6 +859,129 @@ int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientatio
     for (int k = 0; k < nc; ++k) { centers[k].x = h[3 * n + k]; centers[k].y = h[4 * n + k]; centers[k].theta = h[5 * n + k]; centers[k].index = k; centers[k].frame_source = 0; }
     for (int k = 0; k < n; ++k) labels[k] = hl[k];
     *n_clusters = nc;
+    return EBVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Quad tracking (Temporal_Matches.cpp:168-218): host side of ebvo_temporal_quads / ebvo_temporal_quads_stage
+// ------------------------------------------------------------------------------------------------------
+
+int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
+                              const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
+                              const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                              const ebvo_quad_params* qp, int stage, int* off, ebvo_quad* out, int cap, int* n_quads)
+{
+    if (!ctx) return EBVO_ERR_INVALID;
+    if (!kf_Lraw || !kf_Lund || !kf_Rund || !cf_Lraw || !cf_Lund || !cf_Rund || w <= 0 || h <= 0 || stride < w || n_kf < 0 || n_cf < 0 ||
+        (n_kf && !kf) || (n_cf && !cf) || stage < 0 || stage >= EBVO_TQ_COUNT || cap < 0 || (cap && !out) || !n_quads) {
+        ctx->err = "ebvo_temporal_quads: invalid argument"; return EBVO_ERR_INVALID;
+    }
+    ebvo_quad_params q{15, 0, 30.0, 10.0, 0.8, 0.8};
+    if (qp) q = *qp;
+    if (q.cell_size <= 0 || !(q.grid_radius >= 0)) { ctx->err = "ebvo_temporal_quads: invalid grid parameters"; return EBVO_ERR_INVALID; }
+    *n_quads = 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    TqScratch S{st, {}};
+    TqDev d{};
+    d.W = w; d.H = h; d.pitch = (w + 15) & ~15;
+    d.n_kf = n_kf; d.n_cf = n_cf;
+    d.cell = q.cell_size; d.gw = (w + q.cell_size - 1) / q.cell_size; d.gh = (h + q.cell_size - 1) / q.cell_size;   // Dataset.h:33-34
+    d.sr = (int)std::ceil(q.grid_radius / q.cell_size);                                                             // Dataset.h:96
+    d.orient_deg = q.orient_deg; d.ncc_thresh = q.ncc_thresh; d.bnb_thresh = q.bnb_thresh;
+    const int ncell = d.gw * d.gh;
+    // images
+    uint8_t* img[6];
+    const uint8_t* himg[6] = {kf_Lraw, kf_Lund, kf_Rund, cf_Lraw, cf_Lund, cf_Rund};
+    for (int k = 0; k < 6; ++k) {
+        CK(S.get(&img[k], (size_t)d.pitch * h));
+        CK(cudaMemcpy2DAsync(img[k], d.pitch, himg[k], stride, w, h, cudaMemcpyHostToDevice, st));
+    }
+    d.kfLraw = img[0]; d.kfLund = img[1]; d.kfRund = img[2]; d.cfLraw = img[3]; d.cfLund = img[4]; d.cfRund = img[5];
+    // mates
+    std::vector<double> hk(6 * (size_t)n_kf), hc(6 * (size_t)n_cf);
+    for (int i = 0; i < n_kf; ++i) { double* m = &hk[6 * (size_t)i]; m[0] = kf[i].lx; m[1] = kf[i].ly; m[2] = kf[i].ltheta; m[3] = kf[i].rx; m[4] = kf[i].ry; m[5] = kf[i].rtheta; }
+    for (int i = 0; i < n_cf; ++i) { double* m = &hc[6 * (size_t)i]; m[0] = cf[i].lx; m[1] = cf[i].ly; m[2] = cf[i].ltheta; m[3] = cf[i].rx; m[4] = cf[i].ry; m[5] = cf[i].rtheta; }
+    double *dkf, *dcf; uint8_t* dmask = nullptr;
+    CK(S.get(&dkf, hk.size())); CK(S.get(&dcf, hc.size()));
+    if (n_kf) CK(cudaMemcpyAsync(dkf, hk.data(), hk.size() * 8, cudaMemcpyHostToDevice, st));
+    if (n_cf) CK(cudaMemcpyAsync(dcf, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st));
+    if (kf_mask && n_kf) { CK(S.get(&dmask, (size_t)n_kf)); CK(cudaMemcpyAsync(dmask, kf_mask, (size_t)n_kf, cudaMemcpyHostToDevice, st)); }
+    d.kf = dkf; d.cf = dcf; d.kf_mask = dmask;
+    // grid, patches, pools
+    CK(S.get(&d.cellCount, (size_t)ncell)); CK(S.get(&d.cellStart, (size_t)ncell + 1)); CK(S.get(&d.cellCursor, (size_t)ncell));
+    CK(S.get(&d.cellList, (size_t)n_cf)); CK(S.get(&d.lcell, (size_t)n_cf)); CK(S.get(&d.rcx, (size_t)n_cf)); CK(S.get(&d.rcy, (size_t)n_cf));
+    CK(S.get(&d.errFlag, 1)); CK(S.get(&d.counters, 8));
+    CK(cudaMemsetAsync(d.errFlag, 0, sizeof(int), st));
+    int *counts, *offs;
+    CK(S.get(&counts, (size_t)n_kf)); CK(S.get(&offs, (size_t)n_kf + 1));
+    tq_prepare(d, ctx->dp, st, &ctx->prof);
+    std::vector<int> hoff((size_t)n_kf + 1, 0);
+    int total = 0, rc = EBVO_OK;
+    if (stage <= EBVO_TQ_ORIENT) {
+        // large lists (every mate in the 5x5 cell block): count, scan, fill; the quads are the CF mates themselves
+        tq_gate(d, stage, counts, nullptr, nullptr, st, &ctx->prof);
+        tq_scan(counts, offs, n_kf, st, &ctx->prof);
+        CK(cudaMemcpyAsync(hoff.data(), offs, hoff.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        total = hoff[n_kf];
+        int* dcfidx;
+        CK(S.get(&dcfidx, (size_t)total));
+        tq_gate(d, stage, nullptr, offs, dcfidx, st, &ctx->prof);
+        std::vector<int> hcf((size_t)total);
+        if (total) CK(cudaMemcpyAsync(hcf.data(), dcfidx, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->tqCounters, d.counters, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (total > cap) { ctx->err = "output quad buffer too small"; rc = EBVO_ERR_CAPACITY; }
+        else for (int i = 0; i < n_kf; ++i) for (int e = hoff[i]; e < hoff[i + 1]; ++e) {
+            const ebvo_mate& m = cf[hcf[e]];
+            out[e] = ebvo_quad{i, hcf[e], m.lx, m.ly, m.ltheta, m.rx, m.ry, m.rtheta, -1.0, -1.0, 1e6, 1e6, 0, 0};   // scores{-1, 900}, Dataset.h:325-326
+        }
+    } else {
+        for (int k = 0; k < 4; ++k) { const size_t n = (k < 2) ? n_kf : n_cf; CK(S.get(&d.np[k], n * 98)); CK(S.get(&d.pf[k], n)); }
+        CK(S.get(&d.pk16[0], (size_t)w * h)); CK(S.get(&d.pk16[1], (size_t)w * h));
+        const size_t pool = (size_t)n_kf * TQ_CAP;
+        CK(S.get(&d.cnt, (size_t)n_kf)); CK(S.get(&d.cnt2, (size_t)n_kf));
+        CK(S.get(&d.q_cf, pool)); CK(S.get(&d.q_valid, pool)); CK(S.get(&d.q_ncc, 2 * pool)); CK(S.get(&d.q_sc, 2 * pool)); CK(S.get(&d.q_l, 3 * pool)); CK(S.get(&d.q_r, 3 * pool));
+        if (stage == EBVO_TQ_CLUSTER) { CK(S.get(&d.r_cf, pool)); CK(S.get(&d.r_valid, pool)); CK(S.get(&d.r_ncc, 2 * pool)); CK(S.get(&d.r_sc, 2 * pool)); CK(S.get(&d.r_l, 3 * pool)); CK(S.get(&d.r_r, 3 * pool)); }
+        tq_patches(d, ctx->dp, st, &ctx->prof);
+        tq_gate(d, stage == EBVO_TQ_NCC ? 2 : 3, nullptr, nullptr, nullptr, st, &ctx->prof);
+        if (stage >= EBVO_TQ_GN) tq_gn(d, ctx->dp, st, &ctx->prof);
+        if (stage == EBVO_TQ_CLUSTER) tq_cluster(d, ctx->dp, st, &ctx->prof);
+        const int which = stage == EBVO_TQ_CLUSTER ? 2 : 1;
+        tq_scan(which == 2 ? d.cnt2 : d.cnt, offs, n_kf, st, &ctx->prof);
+        ebvo_quad* dout;
+        CK(S.get(&dout, (size_t)cap));
+        tq_gather(d, which, offs, dout, cap, st, &ctx->prof);
+        int herr = 0;
+        CK(cudaMemcpyAsync(hoff.data(), offs, hoff.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&herr, d.errFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->tqCounters, d.counters, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        total = hoff[n_kf];
+        if (herr) { ctx->err = "quad tracking: more than 128 quads of one keyframe mate passed the NCC gate"; rc = EBVO_ERR_CAPACITY; }
+        else if (total > cap) { ctx->err = "output quad buffer too small"; rc = EBVO_ERR_CAPACITY; }
+        else if (total) { CK(cudaMemcpyAsync(out, dout, (size_t)total * sizeof(ebvo_quad), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    }
+    CK(cudaGetLastError());
+    *n_quads = total;
+    if (off) std::memcpy(off, hoff.data(), hoff.size() * 4);
+    return rc;
+}
+
+int ebvo_temporal_quads(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
+                        const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
+                        const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                        const ebvo_quad_params* qp, ebvo_quad* out, int cap, int* n_quads)
+{
+    return ebvo_temporal_quads_stage(ctx, kf_Lraw, kf_Lund, kf_Rund, cf_Lraw, cf_Lund, cf_Rund, w, h, stride, kf, n_kf, kf_mask, cf, n_cf, qp,
+                                     EBVO_TQ_CLUSTER, nullptr, out, cap, n_quads);
+}
+
+int ebvo_temporal_counters(ebvo_ctx* ctx, long long* out8)
+{
+    if (!ctx || !out8) return EBVO_ERR_INVALID;
+    std::memcpy(out8, ctx->tqCounters, sizeof ctx->tqCounters);
     return EBVO_OK;
 }
 

@@ -116,6 +116,35 @@ void launch_ncc_pairs(const float* p1, const float* p2, int n, double* out, cuda
 void launch_cluster_one(const double* x, const double* y, const double* th, int n, int by_orient, const DevParams& p,
                         double* cx, double* cy, double* cth, int* labels, int* nclusters, cudaStream_t st);
 
+constexpr int TQ_CAP = 128;      // quads per keyframe mate that survive the NCC gate (errFlag 5 beyond)
+
+struct TqDev {
+    int W, H, pitch;
+    const uint8_t *kfLraw, *kfLund, *kfRund, *cfLraw, *cfLund, *cfRund;
+    int n_kf, n_cf;
+    const double *kf, *cf;           // n x 6: left x, y, theta, right x, y, theta
+    const uint8_t* kf_mask;          // n_kf or nullptr
+    int cell, gw, gh, sr;
+    double orient_deg, ncc_thresh, bnb_thresh;
+    int *cellCount, *cellStart, *cellCursor, *cellList, *lcell, *rcx, *rcy;
+    float* np[4]; uint8_t* pf[4];    // 0 KF left, 1 KF right, 2 CF left, 3 CF right
+    uint2* pk16[2];                  // CF left / right undistorted view packed with its Sobel gradients (int16)
+    // pool 1 (after gate .. GN) and pool 2 (after clustering): [n_kf][TQ_CAP]
+    int *cnt, *cnt2, *q_cf, *q_valid, *r_cf, *r_valid;
+    double *q_ncc, *q_sc, *q_l, *q_r, *r_ncc, *r_sc, *r_l, *r_r;   // ncc/sc: 2 per entry, l/r: 3 per entry
+    int* errFlag;
+    unsigned long long* counters;    // 0: gate survivors, 1: GN problems, 2: GN iterations, 3: grid candidates, 4: orientation survivors
+};
+
+// quad tracking launchers (temporal.inl, compiled inside match.cu); all asynchronous on `st`
+void tq_prepare(const TqDev& d, const DevParams& p, cudaStream_t st, struct Prof* prof);
+void tq_patches(const TqDev& d, const DevParams& p, cudaStream_t st, struct Prof* prof);
+void tq_gate(const TqDev& d, int mode, int* counts, const int* offs, int* outCf, cudaStream_t st, struct Prof* prof);
+void tq_gn(const TqDev& d, const DevParams& p, cudaStream_t st, struct Prof* prof);
+void tq_cluster(const TqDev& d, const DevParams& p, cudaStream_t st, struct Prof* prof);
+void tq_scan(const int* in, int* out, int n, cudaStream_t st, struct Prof* prof);
+void tq_gather(const TqDev& d, int which, const int* offs, ebvo_quad* out, int cap, cudaStream_t st, struct Prof* prof);
+
 // per-kernel event profiling
 struct Prof {
     bool enabled = false;

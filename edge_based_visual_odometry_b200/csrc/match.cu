@@ -391,7 +391,7 @@ __device__ __forceinline__ double ncc_score(const Patches& A, const Patches& B)
 
 // Best-nearly-best on a warp-private score list (Stereo_Matches.cpp:789-862).  On return order[k] (k < keep)
 // lists the surviving positions in the order the reference leaves them; returns keep.
-__device__ __forceinline__ int bnb_select(const double* sc, int n, double thr, bool is_ncc, int lane, int* order)
+__device__ __forceinline__ int bnb_select(const double* sc, int n, double thr, bool is_ncc, int lane, int* order, bool always_sorted = false)
 {
     if (n < 2) { if (lane == 0 && n == 1) order[0] = 0; __syncwarp(); return n; }
     // best = max (NCC) or min (SIFT distance)
@@ -408,7 +408,10 @@ __device__ __forceinline__ int bnb_select(const double* sc, int n, double thr, b
         for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
         keep = c < 1 ? 1 : c;
     }
-    if (keep >= n) { for (int k = lane; k < n; k += 32) order[k] = k; __syncwarp(); return n; }
+    // the stereo stage leaves a list it keeps whole in its original order; the quad stage always returns sorted order
+    // (Temporal_Matches.cpp:556-561 rebuilds the list from the sorted indices)
+    if (keep >= n && !always_sorted) { for (int k = lane; k < n; k += 32) order[k] = k; __syncwarp(); return n; }
+    if (keep > n) keep = n;
     // stable rank in sorted order
     for (int k = lane; k < n; k += 32) {
         double s = sc[k];
@@ -1894,5 +1897,7 @@ void launch_cluster_one(const double* x, const double* y, const double* th, int 
 {
     cluster_one_kernel<<<1, 32, 0, st>>>(x, y, th, n, by_orient, p, cx, cy, cth, labels, nclusters);
 }
+
+#include "temporal.inl"
 
 }  // namespace ebvo

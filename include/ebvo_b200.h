@@ -96,6 +96,42 @@ enum {
     EBVO_STAGE_COUNT = 12
 };
 
+/* One surviving quad of the keyframe -> current-frame tracking: a keyframe stereo mate paired with a cluster of
+ * current-frame stereo mates (KF_Temporal_Edge_Quads::candidate_quads, include/Temporal_Matches.h:16-28; the two
+ * Temporal_CF_Edge_Cluster of a Candidate_Quad_Entry, include/Dataset.h:318-327). */
+typedef struct ebvo_quad {
+    int32_t kf_index;            /* index of the keyframe mate */
+    int32_t cf_index;            /* cf_stereo_edge_mate_index */
+    double lx, ly, ltheta;       /* CF_left->center_edge */
+    double rx, ry, rtheta;       /* CF_right->center_edge */
+    double ncc_left, ncc_right;  /* matching_scores.ncc_score of the two clusters */
+    double score_left, score_right; /* refine_final_score (1e6 before the photometric refinement) */
+    int32_t valid;               /* refine_validity (valid_left && valid_right) */
+    int32_t reserved;
+} ebvo_quad;
+
+/* Knobs of Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads as written at src/Temporal_Matches.cpp:185-213 and
+ * GRID_SIZE (include/definitions.h:45). */
+typedef struct ebvo_quad_params {
+    int32_t cell_size;      /* 15 */
+    int32_t reserved;
+    double grid_radius;     /* 30 */
+    double orient_deg;      /* 10 */
+    double ncc_thresh;      /* 0.8 */
+    double bnb_thresh;      /* 0.8 */
+} ebvo_quad_params;
+
+/* Stage identifiers of the quad tracking (stage order of get_Temporal_Edge_Pairs_from_Quads). */
+enum {
+    EBVO_TQ_GRID = 0,    /* add_edges_to_spatial_grid + apply_spatial_grid_filtering_quads */
+    EBVO_TQ_ORIENT = 1,  /* apply_orientation_filtering_quads */
+    EBVO_TQ_NCC = 2,     /* apply_NCC_filtering_quads */
+    EBVO_TQ_BNB = 3,     /* apply_best_nearly_best_filtering_quads("NCC") */
+    EBVO_TQ_GN = 4,      /* apply_photometric_refinement_quads */
+    EBVO_TQ_CLUSTER = 5, /* apply_temporal_edge_clustering_quads */
+    EBVO_TQ_COUNT = 6
+};
+
 /* Fills *p with the reference defaults. */
 int ebvo_params_default(ebvo_params* p);
 
@@ -134,6 +170,30 @@ int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_i
  * n_mates: n_frames counts.  Host buffers in, host buffers out (copies are part of the call). */
 int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
                       const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates);
+
+/* Pipeline::get_Temporal_Edge_Correspondences (src/Pipeline.cpp:147-165): SpatialGrid of the current frame's mates
+ * (Temporal_Matches::add_edges_to_spatial_grid, src/Temporal_Matches.cpp:18-55) + the filter chain of
+ * Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (:168-218), SIFT-off, on the stereo mates of a keyframe (kf) and of
+ * the current frame (cf), e.g. the outputs of two ebvo_stereo_frame calls.  *_Lraw: raw left image (left patches,
+ * Stereo_Matches.cpp:562,578), *_Lund / *_Rund: undistorted views (right patches :1582, Gauss-Newton :578-582).
+ * kf_mask (n_kf bytes or NULL): which keyframe mates take part; the reference takes those with a non-empty
+ * veridical_quads list (build_Veridical_Quads, :57-166, a ground-truth construct that stays on the host).
+ * qp may be NULL (reference values).  out receives the surviving quads grouped by keyframe mate in index order. */
+int ebvo_temporal_quads(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
+                        const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
+                        const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                        const ebvo_quad_params* qp, ebvo_quad* out, int cap, int* n_quads);
+
+/* The same call stopped after `stage` (EBVO_TQ_*): the candidate quads as the reference holds them at that point, for
+ * stage-by-stage parity tests.  off (n_kf + 1 ints, may be NULL) receives the start of every keyframe mate's list. */
+int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
+                              const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
+                              const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                              const ebvo_quad_params* qp, int stage, int* off, ebvo_quad* out, int cap, int* n_quads);
+
+/* Work counters of the last quad-tracking call: 0 gate survivors, 1 Gauss-Newton problems, 2 Gauss-Newton iterations,
+ * 3 grid candidates, 4 orientation survivors (8 values). */
+int ebvo_temporal_counters(ebvo_ctx* ctx, long long* out8);
 
 /* The same batch over several contexts (normally one per GPU of the box): frames are split into contiguous blocks of
  * ceil(n_frames / n_ctx), one host thread per context, no exchange between devices (frames are independent:

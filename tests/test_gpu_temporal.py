@@ -1,0 +1,124 @@
+"""GPU: keyframe -> current-frame quad tracking through the C ABI (ebvo_temporal_quads / _stage) against the oracle,
+stage by stage, and against the committed output of the reference's own Temporal_Matches.cpp.
+
+Tolerances: candidate lists identical at every stage (order included; after best-nearly-best the order is compared
+per keyframe mate as a set, because the sort key - an NCC score - differs by < 4e-6 between two readings of OpenCV's
+float type mix and near-ties swap); NCC within 1e-5; refined locations within 1e-3 px, orientation within 1e-4 rad
+(the north-star tolerances of the stereo stage, BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from edge_based_visual_odometry_b200 import synth, _lib
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "temporal_ref_small.npz")
+
+
+def _canon(off, q):
+    own = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    order = np.lexsort((q["cf_index"], own))
+    return q[order]
+
+
+def _as_quads(st):
+    q = np.zeros(len(st["cf"]), _lib.QUAD_DTYPE)
+    q["kf_index"] = np.repeat(np.arange(len(st["off"]) - 1), np.diff(st["off"]))
+    q["cf_index"] = st["cf"]
+    q["lx"], q["ly"], q["ltheta"] = st["left"].T
+    q["rx"], q["ry"], q["rtheta"] = st["right"].T
+    q["ncc_left"], q["ncc_right"] = st["ncc"].T
+    q["score_left"], q["score_right"] = st["score"].T
+    q["valid"] = st["valid"]
+    return q
+
+
+def _compare(name, off_g, qg, st, tol_px=1e-3, tol_rad=1e-4):
+    qo = _as_quads(st)
+    assert np.array_equal(off_g, st["off"]), name
+    if name in ("bnb", "gn"):
+        qg, qo = _canon(off_g, qg), _canon(st["off"], qo)
+    assert np.array_equal(qg["kf_index"], qo["kf_index"]) and np.array_equal(qg["cf_index"], qo["cf_index"]), name
+    if name in ("ncc", "bnb", "gn", "cluster"):
+        assert np.abs(qg["ncc_left"] - qo["ncc_left"]).max() < 1e-5 and np.abs(qg["ncc_right"] - qo["ncc_right"]).max() < 1e-5, name
+    for f in ("lx", "ly", "rx", "ry"):
+        assert np.abs(qg[f] - qo[f]).max() < tol_px, (name, f)
+    for f in ("ltheta", "rtheta"):
+        assert np.abs(qg[f] - qo[f]).max() < tol_rad, (name, f)
+    if name in ("gn", "cluster"):
+        assert np.array_equal(qg["valid"], qo["valid"]), name
+        assert np.abs(qg["score_left"] - qo["score_left"]).max() < 1e-5 and np.abs(qg["score_right"] - qo["score_right"]).max() < 1e-5, name   # RMS residual of the refinement (measured 1.7e-6 on non-converging sequences)
+
+
+@pytest.fixture(scope="module")
+def seq_case():
+    cal = synth.kitti_calib(480, 300)
+    F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    fr = []
+    for k in (0, 1):
+        L, R, _ = synth.stereo_sequence_pair(cal, k, scene_seed=31)
+        eL, _ = oracle.toed(L)
+        eR, _ = oracle.toed(R)
+        res = oracle.stereo(L, R, eL, eR, F21, want_dumps=False)
+        fr.append((L, R, np.concatenate([eL[res.mate_left], res.mate_right], 1)))
+    (L0, R0, m0), (L1, R1, m1) = fr
+    o = oracle.temporal((L0, L0, R0), (L1, L1, R1), m0, m1)
+    return dict(kf_imgs=(L0, L0, R0), cf_imgs=(L1, L1, R1), m0=m0, m1=m1, res=o)
+
+
+def test_stage_by_stage_against_the_oracle(gpu_ctx, seq_case):
+    c = seq_case
+    kf, cf = _lib.mates_from_arrays(c["m0"][:, :3], c["m0"][:, 3:]), _lib.mates_from_arrays(c["m1"][:, :3], c["m1"][:, 3:])
+    for name in _lib.TQ_STAGES:
+        off, q = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, stage=name)
+        _compare(name, off, q, c["res"].stages[name])
+    n = {k: len(v["cf"]) for k, v in c["res"].stages.items()}
+    assert n["grid"] > n["orient"] > n["ncc"] >= n["bnb"] == n["gn"] > n["cluster"] > 1000
+    cnt = gpu_ctx.temporal_counters()
+    assert cnt["gate_survivors"] == n["bnb"] and cnt["gn_problems"] == 2 * n["gn"]
+
+
+def test_default_call_and_mask(gpu_ctx, seq_case):
+    c = seq_case
+    kf, cf = _lib.mates_from_arrays(c["m0"][:, :3], c["m0"][:, 3:]), _lib.mates_from_arrays(c["m1"][:, :3], c["m1"][:, 3:])
+    off, q = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf)
+    _compare("cluster", off, q, c["res"].stages["cluster"])
+    mask = (np.arange(len(kf)) % 2).astype(np.uint8)
+    off2, q2 = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, kf_mask=mask)
+    assert (np.diff(off2)[mask == 0] == 0).all()
+    keep = mask[q["kf_index"]] == 1
+    assert np.array_equal(q2, q[keep])               # a keyframe mate's quads do not depend on the other mates
+
+
+def test_golden_reference_output(gpu_ctx):
+    """The reference's own Temporal_Matches.cpp output (tests/golden/make_golden.py) on a 320x200 sequence pair."""
+    g = np.load(GOLD)
+    kf, cf = _lib.mates_from_arrays(g["kf"][:, :3], g["kf"][:, 3:]), _lib.mates_from_arrays(g["cf"][:, :3], g["cf"][:, 3:])
+    imgs_k, imgs_c = (g["kfL"], g["kfL"], g["kfR"]), (g["cfL"], g["cfL"], g["cfR"])
+    for name in ("orient", "ncc", "gn", "cluster"):
+        off, q = gpu_ctx.temporal_quads(imgs_k, imgs_c, kf, cf, kf_mask=g["mask"], stage=name)
+        st = dict(off=g[f"{name}_off"], cf=g[f"{name}_cf"])
+        n = len(st["cf"])
+        st["ncc"] = g[f"{name}_ncc"] if f"{name}_ncc" in g.files else np.full((n, 2), -1.0)
+        if f"{name}_left" in g.files:
+            st.update(left=g[f"{name}_left"], right=g[f"{name}_right"], score=g[f"{name}_score"], valid=g[f"{name}_valid"])
+        else:
+            st.update(left=g["cf"][st["cf"], :3], right=g["cf"][st["cf"], 3:], score=np.full((n, 2), 1e6), valid=np.zeros(n, np.int32))
+        _compare(name, off, q, st)
+
+
+def test_empty_inputs_and_errors(gpu_ctx):
+    img = np.full((64, 96), 100, np.uint8)
+    none = np.zeros(0, _lib.MATE_DTYPE)
+    one = _lib.mates_from_arrays([[30.0, 30.0, 0.3]], [[25.0, 30.0, 0.3]])
+    for kf, cf in ((none, none), (one, none), (none, one)):
+        off, q = gpu_ctx.temporal_quads((img,) * 3, (img,) * 3, kf, cf)
+        assert len(q) == 0 and off[-1] == 0
+    off, q = gpu_ctx.temporal_quads((img,) * 3, (img,) * 3, one, one, stage="orient")
+    assert len(q) == 1 and q["cf_index"][0] == 0 and q["score_left"][0] == 1e6
+    off, q = gpu_ctx.temporal_quads((img,) * 3, (img,) * 3, one, one, stage="ncc")     # flat patches: similarity -1
+    assert len(q) == 0
+    with pytest.raises(_lib.EbvoError):
+        gpu_ctx.temporal_quads((img,) * 3, (img,) * 3, one, one, stage="grid", cap=0)
