@@ -171,3 +171,37 @@ def test_stereo_matches_dropin_sift_on(tmp_path):
     want = dL[left, 0].sum(1)
     dsum = np.abs(rows[:, 14] - want)      # sums of 128 entries: a handful of off-by-one entries per descriptor at most
     assert (rows[:, 14] >= 0).all() and (rows[:, 15] >= 0).all() and dsum.max() <= 16 and (dsum > 0).mean() < 0.05
+
+
+EXE_TEMPORAL = os.path.join(ROOT, "dropin", "_build", "test_dropin_temporal")
+
+
+@pytest.mark.skipif(not os.path.exists(EXE_TEMPORAL), reason="dropin/_build not built (needs the reference headers at build time)")
+def test_temporal_matches_member_backed_by_the_gpu_against_reference_output(tmp_path):
+    """Pipeline::get_Temporal_Edge_Correspondences' call sequence on the reference's own classes, with
+    get_Temporal_Edge_Pairs_from_Quads replaced by dropin/temporal_matches_b200.cpp, against the output of the
+    reference's own CPU code on the same sequence pair (tests/golden/temporal_ref_small.npz)."""
+    g = np.load(os.path.join(GOLDEN, "temporal_ref_small.npz"))
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    H, W = g["kfL"].shape
+    with open(inp, "wb") as f:
+        np.array([W, H, len(g["kf"]), len(g["cf"])], np.int32).tofile(f)
+        for k in ("kfL", "kfR", "cfL", "cfR"):
+            np.ascontiguousarray(g[k], np.uint8).tofile(f)
+        np.ascontiguousarray(g["kf"], np.float64).tofile(f)
+        np.ascontiguousarray(g["cf"], np.float64).tofile(f)
+        np.ascontiguousarray(g["mask"], np.uint8).tofile(f)
+    out = subprocess.run([EXE_TEMPORAL, str(inp), str(outp)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    raw = np.fromfile(outp, np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    rows = raw[4:].view(np.float64).reshape(n, 13)
+    off = g["cluster_off"]
+    assert n == off[-1] > 1000
+    own = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    assert np.array_equal(rows[:, 0].astype(int), own) and np.array_equal(rows[:, 1].astype(int), g["cluster_cf"])
+    assert np.abs(rows[:, 2:4] - g["cluster_left"][:, :2]).max() < 1e-3 and np.abs(rows[:, 4] - g["cluster_left"][:, 2]).max() < 1e-4
+    assert np.abs(rows[:, 5:7] - g["cluster_right"][:, :2]).max() < 1e-3 and np.abs(rows[:, 7] - g["cluster_right"][:, 2]).max() < 1e-4
+    assert np.abs(rows[:, 8:10] - g["cluster_ncc"]).max() < 1e-5
+    assert np.abs(rows[:, 10:12] - g["cluster_score"]).max() < 1e-5
+    assert np.array_equal(rows[:, 12].astype(int), g["cluster_valid"])
