@@ -306,16 +306,18 @@ class Context:
         kf = np.ascontiguousarray(kf, MATE_DTYPE); cf = np.ascontiguousarray(cf, MATE_DTYPE)
         mask = None if kf_mask is None else np.ascontiguousarray(kf_mask, np.uint8)
         k = TQ_STAGES.index(stage) if isinstance(stage, str) else int(stage)
-        if cap is None:
-            cap = max(1, len(kf) * 128 if k >= 2 else len(kf) * max(len(cf), 1))
-            if k < 2:
-                cap = min(cap, 64 * 1024 * 1024)
+        full = max(1, len(kf) * 128 if k >= 2 else min(len(kf) * max(len(cf), 1), 64 * 1024 * 1024))
+        caps = [cap] if cap is not None else ([min(full, max(16 * len(kf), 1 << 16)), full] if k >= 2 else [full])
         off = np.zeros(len(kf) + 1, np.int32)
-        out = np.zeros(cap, QUAD_DTYPE)
         n = C.c_int()
         qp = C.byref(params) if params is not None else None
-        self._ck(self.L.ebvo_temporal_quads_stage(self.h, *[_p(a) for a in imgs], w, h, imgs[0].strides[0], _p(kf), len(kf), _p(mask),
-                                                  _p(cf), len(cf), qp, k, _p(off), _p(out), cap, C.byref(n)))
+        for c in caps:       # a modest buffer first, the worst case (128 quads per keyframe mate) only when it is needed
+            out = np.empty(c, QUAD_DTYPE)
+            rc = self.L.ebvo_temporal_quads_stage(self.h, *[_p(a) for a in imgs], w, h, imgs[0].strides[0], _p(kf), len(kf), _p(mask),
+                                                  _p(cf), len(cf), qp, k, _p(off), _p(out), c, C.byref(n))
+            if rc != -4 or c == caps[-1]:
+                break
+        self._ck(rc)
         return off, out[:n.value].copy()
 
     def temporal_counters(self):

@@ -348,6 +348,10 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     *out = ctx;   // returned even on failure so that ebvo_last_error() can be read; caller destroys it
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    {   // the quad-tracking call takes its scratch from the stream-ordered allocator: keep freed blocks in the pool between calls
+        cudaMemPool_t mp; unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     CK(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
     init_toed_device();
@@ -963,6 +967,7 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
         else if (total > cap) { ctx->err = "output quad buffer too small"; rc = EBVO_ERR_CAPACITY; }
         else if (total) { CK(cudaMemcpyAsync(out, dout, (size_t)total * sizeof(ebvo_quad), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
     }
+    if (ctx->prof.enabled) ctx->prof.collect();
     CK(cudaGetLastError());
     *n_quads = total;
     if (off) std::memcpy(off, hoff.data(), hoff.size() * 4);

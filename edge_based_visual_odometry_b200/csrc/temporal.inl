@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_kernel(TqDev d, DevParams p
     for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < d.n_kf; i += gridDim.x * WPB) {
         const int n = d.cnt[i];
         if (n == 0) continue;
-        for (int sd = 0; sd < 2; ++sd) {
+        {
+            const int sd = blockIdx.y;      // left and right views are refined by different warps
             const double* k = d.kf + 6 * (size_t)i + 3 * sd;
             const double kx = k[0], ky = k[1], kth = k[2];
             const uint8_t* Ikf = sd ? d.kfRund : d.kfLund;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_kernel(TqDev d, DevParams p
                 if (lane == 0) {
                     d.q_sc[2 * e + sd] = score;
                     if (valid) { double* o = (sd ? d.q_r : d.q_l) + 3 * e; o[0] = kx - d0; o[1] = ky - d1; }     // :623-632
-                    d.q_valid[e] = sd ? (d.q_valid[e] && valid) : (valid ? 1 : 0);                       // valid_left && valid_right
+                    if (valid) atomicOr(&d.q_valid[e], 1 << sd);                                        // refine_validity = both bits (valid_left && valid_right)
                 }
             }
             __syncwarp();
@@ -429,7 +430,7 @@ __global__ void tq_gather_kernel(TqDev d, int which, const int* offs, ebvo_quad*
         q.rx = r[3 * e]; q.ry = r[3 * e + 1]; q.rtheta = r[3 * e + 2];
         q.ncc_left = ncc[2 * e]; q.ncc_right = ncc[2 * e + 1];
         q.score_left = sc[2 * e]; q.score_right = sc[2 * e + 1];
-        q.valid = va[e]; q.reserved = 0;
+        q.valid = va[e] == 3; q.reserved = 0;
         out[o0 + k] = q;
     }
 }
@@ -468,7 +469,7 @@ void tq_gate(const TqDev& d, int mode, int* counts, const int* offs, int* outCf,
 }
 void tq_gn(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {
-    if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<tq_warp_blocks(d.n_kf), 32 * WPB, 0, st>>>(d, p)));
+    if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<dim3(tq_warp_blocks(d.n_kf), 2), 32 * WPB, 0, st>>>(d, p)));
 }
 void tq_cluster(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {
