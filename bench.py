@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 FP32_LANES_PER_SM = 128
 TOED_FLOP_PER_PX = 1636.0      # 818 MAC per input pixel, separable form
 GN_FLOP_PER_ITER = 5300.0      # 98 samples x 54 FP64 flop per Gauss-Newton iteration
-GN_DRAM_BYTES_PER_FRAME = 78.9e6 / 8   # ncu dram__bytes_{read,write}.sum of one gn launch over 8 frames (profiles/r01_ncu_gn_tile64.txt)
+GN_DRAM_BYTES_PER_FRAME = 82.6e6 / 8   # ncu dram__bytes_{read,write}.sum of one gn launch over 8 frames (profiles/r01_ncu_gn_lerp64.txt)
 
 
 def read_peaks():
@@ -155,7 +155,7 @@ def main():
                     help="kitti = the BASELINE.json metric (default); euroc / 4k = BASELINE configs[1] / configs[4] shapes (extra measurements)")
     ap.add_argument("--density", type=float, default=1.0, help="synthetic scene density (objects per area), the 4K stress sweep varies it")
     ap.add_argument("--sift", action="store_true", help="SIFT-on: descriptors, SIFT gate and BNB-SIFT on the device (sift_mode 1)")
-    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32")
+    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32, 3 the round-1 tiled kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -319,7 +319,7 @@ def main():
         peak = gn_peak if dom_is_gn else fp32_peak
         roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": ("fp64" if gn_peak == fp64_peak else "fp32") if dom_is_gn else "fp32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
-                # DRAM bytes of one launch of the dominant kernel: ncu --set full capture profiles/r01_ncu_gn_tile64.txt
+                # DRAM bytes of one launch of the dominant kernel: ncu --set full capture profiles/r01_ncu_gn_lerp64.txt
                 # (dram__bytes_read.sum + dram__bytes_write.sum = 78.9 MB for 8 frames), scaled to this batch
                 "traffic": GN_DRAM_BYTES_PER_FRAME * B if dom_is_gn else None,
                 "algorithmic_flop_per_launch": gn_flops / args.steps if dom_is_gn else toed_flops / args.steps,
