@@ -28,21 +28,32 @@ constexpr int WPB = 4;        // warps per block in the warp-per-item kernels
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GEO = 8;        // doubles per left edge in DevBatch::lines: a, b, c, dirx, diry, sin(thL), cos(thL), pad
 
+// 64-bit shuffles without the `asm volatile` register moves of the CUDA header's double overloads (those cost two MOVs per
+// shuffle that ptxas may not remove: 6 % of the Gauss-Newton kernel's instructions); pure data movement, same values.
+__device__ __forceinline__ double shfl_xor_d(double v, int m)
+{
+    return __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(v), m), __shfl_xor_sync(FULL, __double2loint(v), m));
+}
+__device__ __forceinline__ double shfl_idx_d(double v, int src)
+{
+    return __hiloint2double(__shfl_sync(FULL, __double2hiint(v), src), __shfl_sync(FULL, __double2loint(v), src));
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = 16; o; o >>= 1) v += shfl_xor_d(v, o);
     return v;
 }
 __device__ __forceinline__ void warp_sum2(double& a, double& b)
 {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    for (int o = 16; o; o >>= 1) { a += shfl_xor_d(a, o); b += shfl_xor_d(b, o); }
 }
 __device__ __forceinline__ void warp_sum3(double& a, double& b, double& c)
 {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); c += __shfl_xor_sync(FULL, c, o); }
+    for (int o = 16; o; o >>= 1) { a += shfl_xor_d(a, o); b += shfl_xor_d(b, o); c += shfl_xor_d(c, o); }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -398,7 +409,7 @@ __device__ __forceinline__ int bnb_select(const double* sc, int n, double thr, b
     double best = is_ncc ? -CUDART_INF : CUDART_INF;
     for (int k = lane; k < n; k += 32) best = is_ncc ? fmax(best, sc[k]) : fmin(best, sc[k]);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(FULL, best, o); best = is_ncc ? fmax(best, t) : fmin(best, t); }
+    for (int o = 16; o; o >>= 1) { double t = shfl_xor_d(best, o); best = is_ncc ? fmax(best, t) : fmin(best, t); }
     int keep;
     if (best == 0.0) keep = 1;
     else {
@@ -828,7 +839,7 @@ constexpr int GN_R = GN_RV;            // tile reach along the epipolar directio
 __device__ __forceinline__ double half_sum(double v)   // sum over the 16 lanes of a half-warp, result in every lane
 {
 #pragma unroll
-    for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = 8; o; o >>= 1) v += shfl_xor_d(v, o);
     return v;
 }
 // a / 49 correctly rounded without the division sequence (Markstein: q = a*y, r = a - 49 q exactly, q + r*y)
@@ -1144,7 +1155,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     const double my = fmin((yc - hext) - (double)oy, ((double)(oy + THp - 1) - hext) - yc);
                     double reach = fmin(fmin(mx / fabs(dirx), my / fabs(diry)), (double)Rint);   // x / 0 = inf, 0 / 0 = NaN is ignored by fmin
                     if (!(mx >= 0.0 && my >= 0.0)) reach = -1.0;
-                    reach = fmin(reach, __shfl_xor_sync(FULL, reach, 16));
+                    reach = fmin(reach, shfl_xor_d(reach, 16));
                     if (reach >= 1.0) { alpha0 = 0.0; Rv = reach - 1e-6; }
                 }
                 for (int it = 0; it < p.gn_max_iter; ++it) {
@@ -1190,7 +1201,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
                     double vi48, vg48;
                     {
-                        const double x = __shfl_sync(FULL, xs, cSmp << 4) + rx48, y = __shfl_sync(FULL, ys, cSmp << 4) + ry48;
+                        const double x = shfl_idx_d(xs, cSmp << 4) + rx48, y = shfl_idx_d(ys, cSmp << 4) + ry48;
                         const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
                         const int xi = (int)min((unsigned)(__double2loint(tx) - oxC), (unsigned)(TWp - 2));
@@ -1200,11 +1211,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                         const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
                         const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));       // top (row 0) or bottom (row 1)
-                        const double oth = __shfl_xor_sync(FULL, lin, 1);
+                        const double oth = shfl_xor_d(lin, 1);
                         const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
                         const double v = round_to_float(fma(bb, bot - top, top));
-                        vi48 = __shfl_sync(FULL, v, 6 * hw);
-                        const double gx = __shfl_sync(FULL, v, 6 * hw + 2), gy = __shfl_sync(FULL, v, 6 * hw + 4);
+                        vi48 = shfl_idx_d(v, 6 * hw);
+                        const double gx = shfl_idx_d(v, 6 * hw + 2), gy = shfl_idx_d(v, 6 * hw + 4);
                         vg48 = -gx * dirx + gy * diry;
                     }
                     sR = half_sum(sR) + vi48;
