@@ -12,8 +12,9 @@
 // the CPU body under another name and every other member (add_edges_to_spatial_grid, build_Veridical_Quads, the
 // individual apply_* filters, the writers) as it is.  dropin/Makefile does this with the reference source in place.
 //
-// Scope: SIFT-off (apply_SIFT_filtering_quads and the SIFT best-nearly-best pass are skipped; with every sift_score
-// at its initial 900 the latter keeps everything).  The per-stage Evaluate_Temporal_Edge_Pairs_on_Quads metrics
+// Scope: the SIFT gate and the SIFT best-nearly-best pass run when every mate carries descriptor pairs (the stereo drop-in's
+// default flow fills them); with a mate lacking them the reference's min_sift returns 900 for it (:482-483), which fails the
+// 200 gate for every quad, whereas this drop-in then runs SIFT-off (EBVO_DROPIN_SIFT=0 selects that explicitly).  The per-stage Evaluate_Temporal_Edge_Pairs_on_Quads metrics
 // (ground-truth diagnostics, has_gt() only) are not produced: the returned Frame_Evaluation_Metrics is empty.
 // Which keyframe mates take part is read from the argument exactly as the reference does: those whose
 // veridical_quads list (built on the host by build_Veridical_Quads from ground-truth poses) is non-empty (:345).
@@ -76,11 +77,24 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
     auto pack = [&](const cv::Mat& m) { return ebvo_dropin::packed_u8(m.data, H, W, m.step); };
     const std::vector<unsigned char> kL = pack(keyframe.left_image), kLu = pack(keyframe.left_image_undistorted), kRu = pack(keyframe.right_image_undistorted);
     const std::vector<unsigned char> cL = pack(current_frame.left_image), cLu = pack(current_frame.left_image_undistorted), cRu = pack(current_frame.right_image_undistorted);
-    ebvo_quad_params qp{left_spatial_grids.cell_size, 0, 30.0, 10.0, 0.8, 0.8};     // thresholds as written at :185-196
+    ebvo_quad_params qp{left_spatial_grids.cell_size, 0, 30.0, 10.0, 0.8, 0.8, 200.0};     // thresholds as written at :185-196
+    // descriptor pairs of the mates (filled by the stereo stage's drop-in in its default SIFT-on flow): all present => SIFT-on
+    auto descs = [](const std::vector<final_stereo_edge_pair>& v, bool right, std::vector<float>& out) {
+        out.assign(v.size() * 256, 0.f);
+        for (size_t i = 0; i < v.size(); ++i) {
+            const auto& p = right ? v[i].right_edge_descriptors : v[i].left_edge_descriptors;
+            if (p.first.empty() || p.second.empty() || p.first.cols != 128 || p.second.cols != 128) return false;
+            for (int k = 0; k < 128; ++k) { out[i * 256 + k] = p.first.at<float>(0, k); out[i * 256 + 128 + k] = p.second.at<float>(0, k); }
+        }
+        return !v.empty();
+    };
+    std::vector<float> dkl, dkr, dcl, dcr;
+    const bool sift_on = ebvo_dropin::sift_enabled() && descs(KF, false, dkl) && descs(KF, true, dkr) && descs(CF, false, dcl) && descs(CF, true, dcr);
     std::vector<ebvo_quad> out((size_t)n_kf * 128);
     int n = 0;
     const int rc = ebvo_temporal_quads(ctx, kL.data(), kLu.data(), kRu.data(), cL.data(), cLu.data(), cRu.data(), W, H, W, kf.data(), n_kf,
-                                       mask.data(), cf.data(), n_cf, &qp, out.data(), (int)out.size(), &n);
+                                       mask.data(), cf.data(), n_cf, sift_on ? dkl.data() : nullptr, sift_on ? dkr.data() : nullptr,
+                                       sift_on ? dcl.data() : nullptr, sift_on ? dcr.data() : nullptr, &qp, out.data(), (int)out.size(), &n);
     if (rc != EBVO_OK) {
         std::printf("\033[1;31m[ERROR] ebvo_temporal_quads failed (%d): %s\033[0m\n", rc, ebvo_last_error(ctx));
         return frame_metrics;
@@ -98,7 +112,7 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
         l.center_edge = CF[(size_t)q.cf_index].left_edge; r.center_edge = CF[(size_t)q.cf_index].right_edge;
         l.center_edge.location = cv::Point2d(q.lx, q.ly); l.center_edge.orientation = q.ltheta;
         r.center_edge.location = cv::Point2d(q.rx, q.ry); r.center_edge.orientation = q.rtheta;
-        l.matching_scores = scores{q.ncc_left, 900.0}; r.matching_scores = scores{q.ncc_right, 900.0};
+        l.matching_scores = scores{q.ncc_left, q.sift_left}; r.matching_scores = scores{q.ncc_right, q.sift_right};
         l.refine_final_score = q.score_left; r.refine_final_score = q.score_right;
         l.refine_validity = r.refine_validity = q.valid != 0;
         candidate_cluster_pairs_[(size_t)g].emplace_back(std::move(l), std::move(r));

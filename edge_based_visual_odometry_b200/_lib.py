@@ -61,15 +61,16 @@ assert MATE_DTYPE.itemsize == C.sizeof(Mate) == 64
 # ebvo_quad (include/ebvo_b200.h): one surviving quad of the keyframe -> current-frame tracking
 QUAD_DTYPE = np.dtype([("kf_index", "<i4"), ("cf_index", "<i4"), ("lx", "<f8"), ("ly", "<f8"), ("ltheta", "<f8"),
                        ("rx", "<f8"), ("ry", "<f8"), ("rtheta", "<f8"), ("ncc_left", "<f8"), ("ncc_right", "<f8"),
-                       ("score_left", "<f8"), ("score_right", "<f8"), ("valid", "<i4"), ("reserved", "<i4")])
-assert QUAD_DTYPE.itemsize == 96
-TQ_STAGES = ["grid", "orient", "ncc", "bnb", "gn", "cluster"]
+                       ("sift_left", "<f8"), ("sift_right", "<f8"), ("score_left", "<f8"), ("score_right", "<f8"),
+                       ("valid", "<i4"), ("reserved", "<i4")])
+assert QUAD_DTYPE.itemsize == 112
+TQ_STAGES = ["grid", "orient", "ncc", "sift", "bnb", "bnb_sift", "gn", "cluster"]
 
 
 class QuadParams(C.Structure):
     """ebvo_quad_params: knobs of Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (reference values)."""
     _fields_ = [("cell_size", C.c_int32), ("reserved", C.c_int32), ("grid_radius", C.c_double), ("orient_deg", C.c_double),
-                ("ncc_thresh", C.c_double), ("bnb_thresh", C.c_double)]
+                ("ncc_thresh", C.c_double), ("bnb_thresh", C.c_double), ("sift_thresh", C.c_double)]
 
 
 def mates_from_arrays(left_xyt, right_xyt) -> np.ndarray:
@@ -298,9 +299,11 @@ class Context:
         self._ck(self.L.ebvo_cluster(self.h, _p(e), len(e), int(by_orientation), _p(cen), _p(lab), C.byref(n)))
         return cen[:n.value].copy(), lab[:len(e)].copy()
 
-    def temporal_quads(self, kf_imgs, cf_imgs, kf, cf, kf_mask=None, stage="cluster", params=None, cap=None):
+    def temporal_quads(self, kf_imgs, cf_imgs, kf, cf, kf_mask=None, stage="cluster", params=None, cap=None, desc=None):
         """Keyframe -> current-frame quad tracking (ebvo_temporal_quads_stage).  kf_imgs / cf_imgs = (L_raw, L_und, R_und)
-        uint8 images; kf / cf = MATE_DTYPE arrays.  Returns (off[n_kf + 1], quads) after `stage`."""
+        uint8 images; kf / cf = MATE_DTYPE arrays; desc = optional (kf_left, kf_right, cf_left, cf_right) descriptor pairs,
+        each (n, 2, 128) float32 (SIFT-on).  Returns (off[n_kf + 1], quads) after `stage`."""
+        dd = [None] * 4 if desc is None else [None if a is None else np.ascontiguousarray(a, np.float32).reshape(-1, 256) for a in desc]
         imgs = [np.ascontiguousarray(a, np.uint8) for a in (*kf_imgs, *cf_imgs)]
         h, w = imgs[0].shape
         kf = np.ascontiguousarray(kf, MATE_DTYPE); cf = np.ascontiguousarray(cf, MATE_DTYPE)
@@ -314,7 +317,7 @@ class Context:
         for c in caps:       # a modest buffer first, the worst case (128 quads per keyframe mate) only when it is needed
             out = np.empty(c, QUAD_DTYPE)
             rc = self.L.ebvo_temporal_quads_stage(self.h, *[_p(a) for a in imgs], w, h, imgs[0].strides[0], _p(kf), len(kf), _p(mask),
-                                                  _p(cf), len(cf), qp, k, _p(off), _p(out), c, C.byref(n))
+                                                  _p(cf), len(cf), *[_p(a) for a in dd], qp, k, _p(off), _p(out), c, C.byref(n))
             if rc != -4 or c == caps[-1]:
                 break
         self._ck(rc)

@@ -873,6 +873,7 @@ int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientatio
 int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
                               const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
                               const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                              const float* desc_kf_l, const float* desc_kf_r, const float* desc_cf_l, const float* desc_cf_r,
                               const ebvo_quad_params* qp, int stage, int* off, ebvo_quad* out, int cap, int* n_quads)
 {
     if (!ctx) return EBVO_ERR_INVALID;
@@ -880,7 +881,11 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
         (n_kf && !kf) || (n_cf && !cf) || stage < 0 || stage >= EBVO_TQ_COUNT || cap < 0 || (cap && !out) || !n_quads) {
         ctx->err = "ebvo_temporal_quads: invalid argument"; return EBVO_ERR_INVALID;
     }
-    ebvo_quad_params q{15, 0, 30.0, 10.0, 0.8, 0.8};
+    ebvo_quad_params q{15, 0, 30.0, 10.0, 0.8, 0.8, 200.0};
+    const float* hdesc[4] = {desc_kf_l, desc_kf_r, desc_cf_l, desc_cf_r};
+    const int ndesc = (desc_kf_l != nullptr) + (desc_kf_r != nullptr) + (desc_cf_l != nullptr) + (desc_cf_r != nullptr);
+    if (ndesc != 0 && ndesc != 4) { ctx->err = "ebvo_temporal_quads: pass all four descriptor arrays or none"; return EBVO_ERR_INVALID; }
+    const bool sift_on = ndesc == 4 && n_kf > 0 && n_cf > 0;
     if (qp) q = *qp;
     if (q.cell_size <= 0 || !(q.grid_radius >= 0)) { ctx->err = "ebvo_temporal_quads: invalid grid parameters"; return EBVO_ERR_INVALID; }
     *n_quads = 0;
@@ -892,7 +897,7 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
     d.n_kf = n_kf; d.n_cf = n_cf;
     d.cell = q.cell_size; d.gw = (w + q.cell_size - 1) / q.cell_size; d.gh = (h + q.cell_size - 1) / q.cell_size;   // Dataset.h:33-34
     d.sr = (int)std::ceil(q.grid_radius / q.cell_size);                                                             // Dataset.h:96
-    d.orient_deg = q.orient_deg; d.ncc_thresh = q.ncc_thresh; d.bnb_thresh = q.bnb_thresh;
+    d.orient_deg = q.orient_deg; d.ncc_thresh = q.ncc_thresh; d.bnb_thresh = q.bnb_thresh; d.sift_thresh = q.sift_thresh;
     const int ncell = d.gw * d.gh;
     // images
     uint8_t* img[6];
@@ -912,6 +917,12 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
     if (n_cf) CK(cudaMemcpyAsync(dcf, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st));
     if (kf_mask && n_kf) { CK(S.get(&dmask, (size_t)n_kf)); CK(cudaMemcpyAsync(dmask, kf_mask, (size_t)n_kf, cudaMemcpyHostToDevice, st)); }
     d.kf = dkf; d.cf = dcf; d.kf_mask = dmask;
+    for (int k = 0; k < 4; ++k) d.desc[k] = nullptr;
+    if (sift_on && stage >= EBVO_TQ_SIFT) for (int k = 0; k < 4; ++k) {
+        float* dd; const size_t n = (size_t)(k < 2 ? n_kf : n_cf) * 256;
+        CK(S.get(&dd, n)); CK(cudaMemcpyAsync(dd, hdesc[k], n * sizeof(float), cudaMemcpyHostToDevice, st));
+        d.desc[k] = dd;
+    }
     // grid, patches, pools
     CK(S.get(&d.cellCount, (size_t)ncell)); CK(S.get(&d.cellStart, (size_t)ncell + 1)); CK(S.get(&d.cellCursor, (size_t)ncell));
     CK(S.get(&d.cellList, (size_t)n_cf)); CK(S.get(&d.lcell, (size_t)n_cf)); CK(S.get(&d.rcx, (size_t)n_cf)); CK(S.get(&d.rcy, (size_t)n_cf));
@@ -939,17 +950,17 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
         if (total > cap) { ctx->err = "output quad buffer too small"; rc = EBVO_ERR_CAPACITY; }
         else for (int i = 0; i < n_kf; ++i) for (int e = hoff[i]; e < hoff[i + 1]; ++e) {
             const ebvo_mate& m = cf[hcf[e]];
-            out[e] = ebvo_quad{i, hcf[e], m.lx, m.ly, m.ltheta, m.rx, m.ry, m.rtheta, -1.0, -1.0, 1e6, 1e6, 0, 0};   // scores{-1, 900}, Dataset.h:325-326
+            out[e] = ebvo_quad{i, hcf[e], m.lx, m.ly, m.ltheta, m.rx, m.ry, m.rtheta, -1.0, -1.0, 900.0, 900.0, 1e6, 1e6, 0, 0};   // scores{-1, 900}, Dataset.h:325-326
         }
     } else {
         for (int k = 0; k < 4; ++k) { const size_t n = (k < 2) ? n_kf : n_cf; CK(S.get(&d.np[k], n * 98)); CK(S.get(&d.pf[k], n)); }
         CK(S.get(&d.pk16[0], (size_t)w * h)); CK(S.get(&d.pk16[1], (size_t)w * h));
         const size_t pool = (size_t)n_kf * TQ_CAP;
         CK(S.get(&d.cnt, (size_t)n_kf)); CK(S.get(&d.cnt2, (size_t)n_kf));
-        CK(S.get(&d.q_cf, pool)); CK(S.get(&d.q_valid, pool)); CK(S.get(&d.q_ncc, 2 * pool)); CK(S.get(&d.q_sc, 2 * pool)); CK(S.get(&d.q_l, 3 * pool)); CK(S.get(&d.q_r, 3 * pool));
-        if (stage == EBVO_TQ_CLUSTER) { CK(S.get(&d.r_cf, pool)); CK(S.get(&d.r_valid, pool)); CK(S.get(&d.r_ncc, 2 * pool)); CK(S.get(&d.r_sc, 2 * pool)); CK(S.get(&d.r_l, 3 * pool)); CK(S.get(&d.r_r, 3 * pool)); }
+        CK(S.get(&d.q_cf, pool)); CK(S.get(&d.q_valid, pool)); CK(S.get(&d.q_ncc, 2 * pool)); CK(S.get(&d.q_sift, 2 * pool)); CK(S.get(&d.q_sc, 2 * pool)); CK(S.get(&d.q_l, 3 * pool)); CK(S.get(&d.q_r, 3 * pool));
+        if (stage == EBVO_TQ_CLUSTER) { CK(S.get(&d.r_cf, pool)); CK(S.get(&d.r_valid, pool)); CK(S.get(&d.r_ncc, 2 * pool)); CK(S.get(&d.r_sift, 2 * pool)); CK(S.get(&d.r_sc, 2 * pool)); CK(S.get(&d.r_l, 3 * pool)); CK(S.get(&d.r_r, 3 * pool)); }
         tq_patches(d, ctx->dp, st, &ctx->prof);
-        tq_gate(d, stage == EBVO_TQ_NCC ? 2 : 3, nullptr, nullptr, nullptr, st, &ctx->prof);
+        tq_gate(d, stage >= EBVO_TQ_BNB_SIFT ? 5 : stage, nullptr, nullptr, nullptr, st, &ctx->prof);      // gate modes 2..5 = stages NCC..BNB_SIFT
         if (stage >= EBVO_TQ_GN) tq_gn(d, ctx->dp, st, &ctx->prof);
         if (stage == EBVO_TQ_CLUSTER) tq_cluster(d, ctx->dp, st, &ctx->prof);
         const int which = stage == EBVO_TQ_CLUSTER ? 2 : 1;
@@ -977,10 +988,11 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
 int ebvo_temporal_quads(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
                         const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
                         const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                        const float* desc_kf_l, const float* desc_kf_r, const float* desc_cf_l, const float* desc_cf_r,
                         const ebvo_quad_params* qp, ebvo_quad* out, int cap, int* n_quads)
 {
-    return ebvo_temporal_quads_stage(ctx, kf_Lraw, kf_Lund, kf_Rund, cf_Lraw, cf_Lund, cf_Rund, w, h, stride, kf, n_kf, kf_mask, cf, n_cf, qp,
-                                     EBVO_TQ_CLUSTER, nullptr, out, cap, n_quads);
+    return ebvo_temporal_quads_stage(ctx, kf_Lraw, kf_Lund, kf_Rund, cf_Lraw, cf_Lund, cf_Rund, w, h, stride, kf, n_kf, kf_mask, cf, n_cf,
+                                     desc_kf_l, desc_kf_r, desc_cf_l, desc_cf_r, qp, EBVO_TQ_CLUSTER, nullptr, out, cap, n_quads);
 }
 
 int ebvo_temporal_counters(ebvo_ctx* ctx, long long* out8)

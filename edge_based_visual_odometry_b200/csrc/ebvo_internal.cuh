@@ -125,13 +125,15 @@ struct TqDev {
     const double *kf, *cf;           // n x 6: left x, y, theta, right x, y, theta
     const uint8_t* kf_mask;          // n_kf or nullptr
     int cell, gw, gh, sr;
-    double orient_deg, ncc_thresh, bnb_thresh;
+    double orient_deg, ncc_thresh, bnb_thresh, sift_thresh;
+    const float* desc[4];            // 0 KF left, 1 KF right, 2 CF left, 3 CF right: n x 2 x 128 floats, or all nullptr (SIFT-off)
     int *cellCount, *cellStart, *cellCursor, *cellList, *lcell, *rcx, *rcy;
     float* np[4]; uint8_t* pf[4];    // 0 KF left, 1 KF right, 2 CF left, 3 CF right
     uint2* pk16[2];                  // CF left / right undistorted view packed with its Sobel gradients (int16)
     // pool 1 (after gate .. GN) and pool 2 (after clustering): [n_kf][TQ_CAP]
     int *cnt, *cnt2, *q_cf, *q_valid, *r_cf, *r_valid;
     double *q_ncc, *q_sc, *q_l, *q_r, *r_ncc, *r_sc, *r_l, *r_r;   // ncc/sc: 2 per entry, l/r: 3 per entry
+    double *q_sift, *r_sift;         // 2 per entry
     int* errFlag;
     unsigned long long* counters;    // 0: gate survivors, 1: GN problems, 2: GN iterations, 3: grid candidates, 4: orientation survivors
 };

@@ -15,7 +15,8 @@
 //                     equations, Eigen's pivoted 2x2 LDLT restated
 //   tq_cluster        EdgeClusterer by orientation on the refined left edges + the right-centre means (:636-733)
 //   tq_gather         ordered compaction into ebvo_quad records
-// SIFT-off (apply_SIFT_filtering_quads and the SIFT best-nearly-best pass are skipped, as in the stereo stage's default).
+// The SIFT gate (:471-515) and the SIFT best-nearly-best pass run inside tq_gate on caller-supplied descriptor pairs
+// (the mates' left / right_edge_descriptors); without them both are skipped ("SIFT-off", as the stereo stage's default).
 
 static_assert(TQ_CAP <= MAXC, "the warp-private lists of the quad kernels reuse the stereo stage's capacity");
 
@@ -124,14 +125,17 @@ __global__ void __launch_bounds__(32 * WPB) tq_patch_kernel(TqDev d, DevParams p
     }
 }
 
-// mode 0: grid stage only, 1: + orientation, 2: + NCC gate, 3: + best-nearly-best.  Modes 0 / 1 serve the stage dumps:
-// they count (offs == nullptr) or write the CF indices at offs[i] (two passes); modes 2 / 3 fill pool 1.
+// mode 0: grid stage only, 1: + orientation, 2: + NCC gate, 3: + SIFT gate, 4: + best-nearly-best on NCC, 5: + on SIFT.
+// Modes 0 / 1 serve the stage dumps: they count (offs == nullptr) or write the CF indices at offs[i] (two passes);
+// modes >= 2 fill pool 1.
 __global__ void __launch_bounds__(32 * WPB) tq_gate_kernel(TqDev d, int mode, int* counts, const int* offs, int* outCf)
 {
     __shared__ int s_cf[WPB][TQ_CAP];
     __shared__ double s_nl[WPB][TQ_CAP], s_nr[WPB][TQ_CAP];
-    __shared__ int s_or[WPB][TQ_CAP];
+    __shared__ double s_sl[WPB][TQ_CAP], s_sr[WPB][TQ_CAP], s_tmp[WPB][TQ_CAP];
+    __shared__ int s_or[WPB][TQ_CAP], s_or2[WPB][TQ_CAP], s_or3[WPB][TQ_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool sift = d.desc[0] != nullptr && mode >= 3;
     unsigned long long nGrid = 0, nOri = 0, nKeep = 0;
     for (int i = blockIdx.x * WPB + w; i < d.n_kf; i += gridDim.x * WPB) {
         if (d.kf_mask && !d.kf_mask[i]) { if (lane == 0) { if (mode < 2) { if (!offs) counts[i] = 0; } else d.cnt[i] = 0; } continue; }
@@ -141,6 +145,11 @@ __global__ void __launch_bounds__(32 * WPB) tq_gate_kernel(TqDev d, int mode, in
         const int rx0 = (int)k[3] / d.cell, ry0 = (int)k[4] / d.cell;
         Patches KL, KR;
         if (mode >= 2) { load_patches(d.np[0], d.pf[0], i, lane, KL); load_patches(d.np[1], d.pf[1], i, lane, KR); }
+        float4 kl1 = make_float4(0, 0, 0, 0), kl2 = kl1, kr1 = kl1, kr2 = kl1;      // keyframe descriptor pairs, 4 floats per lane
+        if (sift) {
+            const float4* a = reinterpret_cast<const float4*>(d.desc[0] + (size_t)i * 256); kl1 = a[lane]; kl2 = a[32 + lane];
+            const float4* b = reinterpret_cast<const float4*>(d.desc[1] + (size_t)i * 256); kr1 = b[lane]; kr2 = b[32 + lane];
+        }
         int n = 0;                       // entries produced so far (warp-uniform)
         int ns = 0;
         const int obase = (mode < 2 && offs) ? offs[i] : 0;
@@ -185,7 +194,27 @@ __global__ void __launch_bounds__(32 * WPB) tq_gate_kernel(TqDev d, int mode, in
                         load_patches(d.np[3], d.pf[3], c2, lane, CR);
                         const double sr_ = ncc_score(KR, CR);
                         if (!(sr_ > d.ncc_thresh)) continue;
-                        if (ns < TQ_CAP) { if (lane == 0) { s_cf[w][ns] = c2; s_nl[w][ns] = sl; s_nr[w][ns] = sr_; } ++ns; }
+                        double fl = 900.0, fr = 900.0;          // scores{-1.0, 900.0} (:364)
+                        if (sift) {
+                            // min of the four L2 distances on both views (:481-489), gate < sift_thresh (:499)
+                            auto d2 = [](float4 u, float4 v) {
+                                const double x = (double)u.x - (double)v.x, y = (double)u.y - (double)v.y, z = (double)u.z - (double)v.z, q = (double)u.w - (double)v.w;
+                                return x * x + y * y + z * z + q * q;
+                            };
+                            const float4* cl = reinterpret_cast<const float4*>(d.desc[2] + (size_t)c2 * 256);
+                            const float4 b1 = cl[lane], b2 = cl[32 + lane];
+                            double d11 = d2(kl1, b1), d12 = d2(kl1, b2), d21 = d2(kl2, b1), d22 = d2(kl2, b2);
+                            warp_sum2(d11, d12); warp_sum2(d21, d22);
+                            fl = fmin(fmin(sqrt(d11), sqrt(d12)), fmin(sqrt(d21), sqrt(d22)));
+                            if (!(fl < d.sift_thresh)) continue;
+                            const float4* cr = reinterpret_cast<const float4*>(d.desc[3] + (size_t)c2 * 256);
+                            const float4 c1 = cr[lane], c2_ = cr[32 + lane];
+                            d11 = d2(kr1, c1); d12 = d2(kr1, c2_); d21 = d2(kr2, c1); d22 = d2(kr2, c2_);
+                            warp_sum2(d11, d12); warp_sum2(d21, d22);
+                            fr = fmin(fmin(sqrt(d11), sqrt(d12)), fmin(sqrt(d21), sqrt(d22)));
+                            if (!(fr < d.sift_thresh)) continue;
+                        }
+                        if (ns < TQ_CAP) { if (lane == 0) { s_cf[w][ns] = c2; s_nl[w][ns] = sl; s_nr[w][ns] = sr_; s_sl[w][ns] = fl; s_sr[w][ns] = fr; } ++ns; }
                         else if (lane == 0) atomicExch(d.errFlag, 5);
                     }
                 }
@@ -194,14 +223,25 @@ __global__ void __launch_bounds__(32 * WPB) tq_gate_kernel(TqDev d, int mode, in
         if (mode < 2) { if (!offs && lane == 0) counts[i] = n; continue; }
         __syncwarp();
         int keep = ns;
-        if (mode >= 3) keep = bnb_select(s_nl[w], ns, d.bnb_thresh, true, lane, s_or[w], true);
+        if (mode >= 4) keep = bnb_select(s_nl[w], ns, d.bnb_thresh, true, lane, s_or[w], true);
         else for (int q = lane; q < ns; q += 32) s_or[w][q] = q;
         __syncwarp();
+        if (mode >= 5 && sift && keep >= 2) {      // second pass on the left SIFT distance of the survivors, in their new order (:196)
+            for (int q = lane; q < keep; q += 32) s_tmp[w][q] = s_sl[w][s_or[w][q]];
+            __syncwarp();
+            const int keep2 = bnb_select(s_tmp[w], keep, d.bnb_thresh, false, lane, s_or2[w], true);
+            for (int q = lane; q < keep2; q += 32) s_or3[w][q] = s_or[w][s_or2[w][q]];
+            __syncwarp();
+            for (int q = lane; q < keep2; q += 32) s_or[w][q] = s_or3[w][q];
+            keep = keep2;
+            __syncwarp();
+        }
         for (int q = lane; q < keep; q += 32) {
             const int o = s_or[w][q], c2 = s_cf[w][o];
             const size_t e = (size_t)i * TQ_CAP + q;
             const double* m = d.cf + 6 * (size_t)c2;
             d.q_cf[e] = c2; d.q_ncc[2 * e] = s_nl[w][o]; d.q_ncc[2 * e + 1] = s_nr[w][o];
+            d.q_sift[2 * e] = s_sl[w][o]; d.q_sift[2 * e + 1] = s_sr[w][o];
             d.q_l[3 * e] = m[0]; d.q_l[3 * e + 1] = m[1]; d.q_l[3 * e + 2] = m[2];
             d.q_r[3 * e] = m[3]; d.q_r[3 * e + 1] = m[4]; d.q_r[3 * e + 2] = m[5];
             d.q_sc[2 * e] = 1e6; d.q_sc[2 * e + 1] = 1e6; d.q_valid[e] = 0;      // Dataset.h:325-326
@@ -371,7 +411,7 @@ __global__ void __launch_bounds__(32 * WPB) tq_cluster_kernel(TqDev d, DevParams
                 d.cnt2[i] = n;
                 if (n == 1) {
                     d.r_cf[base] = d.q_cf[base]; d.r_valid[base] = d.q_valid[base];
-                    for (int k = 0; k < 2; ++k) { d.r_ncc[2 * base + k] = d.q_ncc[2 * base + k]; d.r_sc[2 * base + k] = d.q_sc[2 * base + k]; }
+                    for (int k = 0; k < 2; ++k) { d.r_ncc[2 * base + k] = d.q_ncc[2 * base + k]; d.r_sc[2 * base + k] = d.q_sc[2 * base + k]; d.r_sift[2 * base + k] = d.q_sift[2 * base + k]; }
                     for (int k = 0; k < 3; ++k) { d.r_l[3 * base + k] = d.q_l[3 * base + k]; d.r_r[3 * base + k] = d.q_r[3 * base + k]; }
                 }
             }
@@ -404,6 +444,7 @@ __global__ void __launch_bounds__(32 * WPB) tq_cluster_kernel(TqDev d, DevParams
             d.r_cf[o] = d.q_cf[b]; d.r_valid[o] = d.q_valid[b];
             d.r_ncc[2 * o] = d.q_ncc[2 * b]; d.r_ncc[2 * o + 1] = d.q_ncc[2 * b + 1];
             d.r_sc[2 * o] = d.q_sc[2 * b]; d.r_sc[2 * o + 1] = d.q_sc[2 * b + 1];
+            d.r_sift[2 * o] = d.q_sift[2 * b]; d.r_sift[2 * o + 1] = d.q_sift[2 * b + 1];
             d.r_l[3 * o] = s_ox[w][c]; d.r_l[3 * o + 1] = s_oy[w][c]; d.r_l[3 * o + 2] = s_ot[w][c];
             if (cnt == 1) { d.r_r[3 * o] = sx; d.r_r[3 * o + 1] = sy; d.r_r[3 * o + 2] = st; }
             else { d.r_r[3 * o] = sx / cnt; d.r_r[3 * o + 1] = sy / cnt; d.r_r[3 * o + 2] = st / cnt; }
@@ -420,6 +461,7 @@ __global__ void tq_gather_kernel(TqDev d, int which, const int* offs, ebvo_quad*
     const int* cnt = which == 2 ? d.cnt2 : d.cnt;
     const int n = cnt[i], o0 = offs[i];
     const int* cf = which == 2 ? d.r_cf : d.q_cf; const int* va = which == 2 ? d.r_valid : d.q_valid;
+    const double* sf = which == 2 ? d.r_sift : d.q_sift;
     const double *ncc = which == 2 ? d.r_ncc : d.q_ncc, *sc = which == 2 ? d.r_sc : d.q_sc, *l = which == 2 ? d.r_l : d.q_l, *r = which == 2 ? d.r_r : d.q_r;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         if (o0 + k >= cap) break;
@@ -429,6 +471,7 @@ __global__ void tq_gather_kernel(TqDev d, int which, const int* offs, ebvo_quad*
         q.lx = l[3 * e]; q.ly = l[3 * e + 1]; q.ltheta = l[3 * e + 2];
         q.rx = r[3 * e]; q.ry = r[3 * e + 1]; q.rtheta = r[3 * e + 2];
         q.ncc_left = ncc[2 * e]; q.ncc_right = ncc[2 * e + 1];
+        q.sift_left = sf[2 * e]; q.sift_right = sf[2 * e + 1];
         q.score_left = sc[2 * e]; q.score_right = sc[2 * e + 1];
         q.valid = va[e] == 3; q.reserved = 0;
         out[o0 + k] = q;

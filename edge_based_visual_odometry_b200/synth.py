@@ -235,6 +235,23 @@ def stereo_sequence_pair(cal: Calibration | str = "kitti", frame: int = 0, step=
     return out[0], out[1], (sx, sy)
 
 
+def position_descriptors(xyt, seed: int = 0) -> np.ndarray:
+    """Deterministic stand-in for the (n, 2, 128) SIFT descriptor pairs of a set of edges: integer-valued float32 entries
+    in [0, 255] that vary smoothly with the edge position and orientation, so that nearby, similarly oriented edges of two
+    frames have close descriptors and distant ones do not.  Used where the stage logic around descriptors is under test
+    (gates, best-nearly-best) and real cv::SIFT output would have to be stored."""
+    xyt = np.asarray(xyt, np.float64).reshape(-1, 3)
+    k = np.arange(128, dtype=np.float64)[None, :]
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 2 * np.pi, (2, 128))
+    out = np.zeros((len(xyt), 2, 128), np.float32)
+    for j in range(2):
+        v = 110 + 60 * np.sin(xyt[:, :1] * (0.02 + 0.0007 * k) + ph[j]) + 50 * np.cos(xyt[:, 1:2] * (0.03 + 0.0005 * k) + 2 * ph[j]) \
+            + 30 * np.sin(2 * xyt[:, 2:3] + 0.05 * k + j)
+        out[:, j] = np.clip(np.rint(v), 0, 255)
+    return out
+
+
 def fundamental_matrices(cal: Calibration):
     """F21 and F12 exactly as the reference builds them (Dataset.cpp:102-112).
 

@@ -105,6 +105,7 @@ typedef struct ebvo_quad {
     double lx, ly, ltheta;       /* CF_left->center_edge */
     double rx, ry, rtheta;       /* CF_right->center_edge */
     double ncc_left, ncc_right;  /* matching_scores.ncc_score of the two clusters */
+    double sift_left, sift_right; /* matching_scores.sift_score (900 when the SIFT stages did not run) */
     double score_left, score_right; /* refine_final_score (1e6 before the photometric refinement) */
     int32_t valid;               /* refine_validity (valid_left && valid_right) */
     int32_t reserved;
@@ -118,7 +119,8 @@ typedef struct ebvo_quad_params {
     double grid_radius;     /* 30 */
     double orient_deg;      /* 10 */
     double ncc_thresh;      /* 0.8 */
-    double bnb_thresh;      /* 0.8 */
+    double bnb_thresh;      /* 0.8 (both best-nearly-best passes) */
+    double sift_thresh;     /* 200 */
 } ebvo_quad_params;
 
 /* Stage identifiers of the quad tracking (stage order of get_Temporal_Edge_Pairs_from_Quads). */
@@ -126,10 +128,12 @@ enum {
     EBVO_TQ_GRID = 0,    /* add_edges_to_spatial_grid + apply_spatial_grid_filtering_quads */
     EBVO_TQ_ORIENT = 1,  /* apply_orientation_filtering_quads */
     EBVO_TQ_NCC = 2,     /* apply_NCC_filtering_quads */
-    EBVO_TQ_BNB = 3,     /* apply_best_nearly_best_filtering_quads("NCC") */
-    EBVO_TQ_GN = 4,      /* apply_photometric_refinement_quads */
-    EBVO_TQ_CLUSTER = 5, /* apply_temporal_edge_clustering_quads */
-    EBVO_TQ_COUNT = 6
+    EBVO_TQ_SIFT = 3,    /* apply_SIFT_filtering_quads (pass-through without descriptors) */
+    EBVO_TQ_BNB = 4,     /* apply_best_nearly_best_filtering_quads("NCC") */
+    EBVO_TQ_BNB_SIFT = 5,/* apply_best_nearly_best_filtering_quads("SIFT") (pass-through without descriptors) */
+    EBVO_TQ_GN = 6,      /* apply_photometric_refinement_quads */
+    EBVO_TQ_CLUSTER = 7, /* apply_temporal_edge_clustering_quads */
+    EBVO_TQ_COUNT = 8
 };
 
 /* Fills *p with the reference defaults. */
@@ -173,15 +177,18 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
 
 /* Pipeline::get_Temporal_Edge_Correspondences (src/Pipeline.cpp:147-165): SpatialGrid of the current frame's mates
  * (Temporal_Matches::add_edges_to_spatial_grid, src/Temporal_Matches.cpp:18-55) + the filter chain of
- * Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (:168-218), SIFT-off, on the stereo mates of a keyframe (kf) and of
+ * Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (:168-218) on the stereo mates of a keyframe (kf) and of
  * the current frame (cf), e.g. the outputs of two ebvo_stereo_frame calls.  *_Lraw: raw left image (left patches,
  * Stereo_Matches.cpp:562,578), *_Lund / *_Rund: undistorted views (right patches :1582, Gauss-Newton :578-582).
  * kf_mask (n_kf bytes or NULL): which keyframe mates take part; the reference takes those with a non-empty
  * veridical_quads list (build_Veridical_Quads, :57-166, a ground-truth construct that stays on the host).
- * qp may be NULL (reference values).  out receives the surviving quads grouped by keyframe mate in index order. */
+ * desc_kf_l / desc_kf_r / desc_cf_l / desc_cf_r: the mates' left_edge_descriptors / right_edge_descriptors as n x 2 x 128
+ * floats (final_stereo_edge_pair, include/Dataset.h:299-300); all four NULL => the SIFT gate (:471-515) and the SIFT
+ * best-nearly-best pass are skipped ("SIFT-off").  qp may be NULL (reference values).  out receives the surviving quads grouped by keyframe mate in index order. */
 int ebvo_temporal_quads(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
                         const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
                         const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                        const float* desc_kf_l, const float* desc_kf_r, const float* desc_cf_l, const float* desc_cf_r,
                         const ebvo_quad_params* qp, ebvo_quad* out, int cap, int* n_quads);
 
 /* The same call stopped after `stage` (EBVO_TQ_*): the candidate quads as the reference holds them at that point, for
@@ -189,6 +196,7 @@ int ebvo_temporal_quads(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf
 int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8_t* kf_Lund, const uint8_t* kf_Rund,
                               const uint8_t* cf_Lraw, const uint8_t* cf_Lund, const uint8_t* cf_Rund, int w, int h, int stride,
                               const ebvo_mate* kf, int n_kf, const uint8_t* kf_mask, const ebvo_mate* cf, int n_cf,
+                              const float* desc_kf_l, const float* desc_kf_r, const float* desc_cf_l, const float* desc_cf_r,
                               const ebvo_quad_params* qp, int stage, int* off, ebvo_quad* out, int cap, int* n_quads);
 
 /* Work counters of the last quad-tracking call: 0 gate survivors, 1 Gauss-Newton problems, 2 Gauss-Newton iterations,

@@ -293,7 +293,7 @@ def ref_cluster(xyt, by_orientation=True):
 # keyframe -> current-frame quad tracking (Temporal_Matches.cpp): restatement (temporal_oracle.inl) and the reference's
 # own source compiled in place (ref_temporal_harness.cpp -> _ref/libtemporal_ref.so)
 # ---------------------------------------------------------------------------------------------------------------
-TQ_STAGES = ["grid", "orient", "ncc", "bnb", "gn", "cluster"]
+TQ_STAGES = ["grid", "orient", "ncc", "sift", "bnb", "bnb_sift", "gn", "cluster"]
 _TREF = None
 
 
@@ -321,11 +321,20 @@ class QuadResult:
         for k, name in enumerate(TQ_STAGES):
             tot = total(k)
             off, cf, valid = np.zeros(n_kf + 1, np.int32), np.zeros(tot, np.int32), np.zeros(tot, np.int32)
-            l, r, ncc, sc = np.zeros((tot, 3)), np.zeros((tot, 3)), np.zeros((tot, 2)), np.zeros((tot, 2))
-            get(k, _p(off), _p(cf), _p(l), _p(r), _p(ncc), _p(sc), _p(valid))
-            self.stages[name] = dict(off=off, cf=cf, left=l, right=r, ncc=ncc, score=sc, valid=valid)
+            l, r, ncc, sc, sift = np.zeros((tot, 3)), np.zeros((tot, 3)), np.zeros((tot, 2)), np.zeros((tot, 2)), np.zeros((tot, 2))
+            get(k, _p(off), _p(cf), _p(l), _p(r), _p(ncc), _p(sc), _p(valid), _p(sift))
+            self.stages[name] = dict(off=off, cf=cf, left=l, right=r, ncc=ncc, score=sc, valid=valid, sift=sift)
         self.seconds = 0.0
         self.counts = {}
+
+
+def _tq_desc(desc, kf, cf):
+    """desc = (kf_left, kf_right, cf_left, cf_right), each (n, 2, 128) float32 descriptor pairs, or None (SIFT-off)."""
+    if desc is None:
+        return [None] * 4
+    out = [np.ascontiguousarray(d, dtype=np.float32).reshape(-1, 256) for d in desc]
+    assert len(out[0]) == len(out[1]) == len(kf) and len(out[2]) == len(out[3]) == len(cf)
+    return out
 
 
 def _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask):
@@ -337,14 +346,17 @@ def _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask):
     return imgs, H, W, kf, cf, mask
 
 
-def temporal(kf_imgs, cf_imgs, kf, cf, kf_mask=None, cell=15, radius=30.0, orient_deg=10.0, ncc_thresh=0.8, bnb=0.8) -> QuadResult:
-    """Run the quad-tracking restatement.  kf_imgs / cf_imgs = (L_raw, L_und, R_und); kf / cf = n x 6 (left xyt, right xyt)."""
+def temporal(kf_imgs, cf_imgs, kf, cf, kf_mask=None, cell=15, radius=30.0, orient_deg=10.0, ncc_thresh=0.8, bnb=0.8,
+             desc=None, sift_thresh=200.0) -> QuadResult:
+    """Run the quad-tracking restatement.  kf_imgs / cf_imgs = (L_raw, L_und, R_und); kf / cf = n x 6 (left xyt, right xyt);
+    desc = optional descriptor pairs (see _tq_desc): with them the SIFT gate and the SIFT best-nearly-best pass run."""
     imgs, H, W, kf, cf, mask = _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask)
+    dd = _tq_desc(desc, kf, cf)
     L = lib()
     L.to_run.restype = C.c_void_p
     L.to_stage_total.restype = C.c_int
     h = C.c_void_p(L.to_run(*[_p(a) for a in imgs], H, W, _p(kf), len(kf), _p(mask), _p(cf), len(cf), cell, C.c_double(radius),
-                            C.c_double(orient_deg), C.c_double(ncc_thresh), C.c_double(bnb)))
+                            C.c_double(orient_deg), C.c_double(ncc_thresh), C.c_double(bnb), *[_p(a) for a in dd], C.c_double(sift_thresh)))
     res = QuadResult(lambda k: L.to_stage_total(h, k), lambda k, *a: L.to_get_stage(h, k, *a), len(kf))
     sec, cnt = C.c_double(), (C.c_long * 2)()
     L.to_get_stats(h, C.byref(sec), cnt)
@@ -353,11 +365,12 @@ def temporal(kf_imgs, cf_imgs, kf, cf, kf_mask=None, cell=15, radius=30.0, orien
     return res
 
 
-def temporal_reference(kf_imgs, cf_imgs, kf, cf, kf_mask=None) -> QuadResult:
-    """Run the reference's own quad stages (oracle/ref_temporal_harness.cpp; SIFT-off; thresholds of Temporal_Matches.cpp:185-213)."""
+def temporal_reference(kf_imgs, cf_imgs, kf, cf, kf_mask=None, desc=None) -> QuadResult:
+    """Run the reference's own quad stages (oracle/ref_temporal_harness.cpp; thresholds of Temporal_Matches.cpp:185-213)."""
     imgs, H, W, kf, cf, mask = _tq_args(kf_imgs, cf_imgs, kf, cf, kf_mask)
+    dd = _tq_desc(desc, kf, cf)
     R = temporal_ref_lib()
-    h = C.c_void_p(R.rt_run(*[_p(a) for a in imgs], H, W, _p(kf), len(kf), _p(mask), _p(cf), len(cf)))
+    h = C.c_void_p(R.rt_run(*[_p(a) for a in imgs], H, W, _p(kf), len(kf), _p(mask), _p(cf), len(cf), *[_p(a) for a in dd]))
     res = QuadResult(lambda k: R.rt_stage_total(h, k), lambda k, *a: R.rt_get_stage(h, k, *a), len(kf))
     R.rt_free(h)
     return res

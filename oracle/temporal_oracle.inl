@@ -12,13 +12,16 @@
 //   TQ_NCC     apply_NCC_filtering_quads (:416-469): max of the 4 patch similarities > 0.8 on both views; KF/CF left
 //              patches come from the RAW left images (Stereo_Matches.cpp:562,578), right patches from the UNDISTORTED
 //              right images (:1580,1622)
+//   TQ_SIFT    apply_SIFT_filtering_quads (:471-515): min of the 4 descriptor distances < 200 on both views (only when
+//              the caller supplies descriptors; a pass-through otherwise)
 //   TQ_BNB     apply_best_nearly_best_filtering_quads (:517-570) on the left NCC score, ratio 0.8
+//   TQ_BNB_SIFT the same on the left SIFT distance, ratio 0.8 (pass-through without descriptors)
 //   TQ_GN      apply_photometric_refinement_quads (:572-634) + min_Edge_Photometric_Residual_by_Gauss_Newton (:735-851):
 //              2-D Gauss-Newton on both views (Huber 3, <= 20 iterations, 2x2 LDLT as Eigen does it)
 //   TQ_CLUSTER apply_temporal_edge_clustering_quads (:636-733): EdgeClusterer by orientation on the refined left
 //              edges, right centre = plain mean of the members' right edges
-// Documented deviations: SIFT-off (apply_SIFT_filtering_quads and the BNB pass on SIFT scores are skipped, as in the
-// stereo oracle); which KF mates take part (the reference takes those with a non-empty veridical_quads list, a
+// Documented deviations: descriptors are not computed here (cv::SIFT is OpenCV code): without caller-supplied descriptor
+// pairs the two SIFT stages are skipped ("SIFT-off", as in the stereo oracle); which KF mates take part (the reference takes those with a non-empty veridical_quads list, a
 // ground-truth construct, :57-166) is an input mask.
 //
 // Pinned against the reference's own Temporal_Matches.cpp compiled in place (oracle/ref_temporal_harness.cpp ->
@@ -26,13 +29,14 @@
 
 namespace {
 
-enum { TQ_GRID = 0, TQ_ORIENT, TQ_NCC, TQ_BNB, TQ_GN, TQ_CLUSTER, TQ_COUNT };
+enum { TQ_GRID = 0, TQ_ORIENT, TQ_NCC, TQ_SIFT, TQ_BNB, TQ_BNB_SIFT, TQ_GN, TQ_CLUSTER, TQ_COUNT };
 
 struct Mate { E l, r; };
 struct Quad {
     int cf = -1;          // cf_stereo_edge_mate_index
     E l, r;               // Temporal_CF_Edge_Cluster.center_edge (left / right)
     double ncc_l = -1, ncc_r = -1;
+    double sift_l = 900, sift_r = 900;   // scores{-1.0, 900.0} (:364)
     double sc_l = 1e6, sc_r = 1e6;   // refine_final_score (Dataset.h:325: 1e6 until the refinement runs)
     int valid = 0;               // refine_validity (valid_left && valid_right)
 };
@@ -135,8 +139,10 @@ extern "C" {
 // kf, cf: n x 6 doubles (left x, y, theta, right x, y, theta); kf_mask: n_kf bytes or NULL (= every KF mate)
 void *to_run(const uint8_t *kfLraw, const uint8_t *kfLund, const uint8_t *kfRund, const uint8_t *cfLraw, const uint8_t *cfLund,
              const uint8_t *cfRund, int H, int W, const double *kf, int n_kf, const uint8_t *kf_mask, const double *cf, int n_cf,
-             int cell_size, double grid_radius, double orient_deg, double ncc_thresh, double bnb_thresh)
+             int cell_size, double grid_radius, double orient_deg, double ncc_thresh, double bnb_thresh,
+             const float *descKfL, const float *descKfR, const float *descCfL, const float *descCfR, double sift_thresh)
 {
+    const bool sift_on = descKfL && descKfR && descCfL && descCfR;   // n x 2 x 128 floats per array (first, second descriptor)
     P p;
     TResult *res = new TResult;
     res->n_kf = n_kf;
@@ -218,22 +224,41 @@ void *to_run(const uint8_t *kfLraw, const uint8_t *kfLund, const uint8_t *kfRund
             q.swap(o);
         }
         res->stage[TQ_NCC][i] = q;
-        // ---- TQ_BNB (left NCC score; std::sort on descending score, ties keep index order here) ----
-        if (q.size() >= 2) {
-            std::vector<size_t> idx(q.size());
-            std::iota(idx.begin(), idx.end(), 0);
-            std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return q[a].ncc_l > q[b].ncc_l; });
-            const double best = q[idx[0]].ncc_l;
-            size_t keep = 1;
-            for (size_t j = 0; j + 1 < q.size(); ++j) {
-                if (best == 0) break;
-                if (q[idx[j + 1]].ncc_l / best >= bnb_thresh) ++keep; else break;
-            }
+        // ---- TQ_SIFT ----
+        if (sift_on) {
+            auto l2 = [](const float *a, const float *b) { double t = 0; for (int k = 0; k < 128; ++k) { double d = (double)a[k] - (double)b[k]; t += d * d; } return std::sqrt(t); };
+            auto min_sift = [&](const float *a, const float *b) { return std::min({l2(a, b), l2(a, b + 128), l2(a + 128, b), l2(a + 128, b + 128)}); };
             std::vector<Quad> o;
-            for (size_t k = 0; k < keep; ++k) o.push_back(q[idx[k]]);
+            for (Quad e : q) {
+                const double sl = min_sift(descKfL + (size_t)i * 256, descCfL + (size_t)e.cf * 256);
+                const double sr = min_sift(descKfR + (size_t)i * 256, descCfR + (size_t)e.cf * 256);
+                if (sl < sift_thresh && sr < sift_thresh) { e.sift_l = sl; e.sift_r = sr; o.push_back(e); }
+            }
             q.swap(o);
         }
-        res->stage[TQ_BNB][i] = q;
+        res->stage[TQ_SIFT][i] = q;
+        // ---- TQ_BNB / TQ_BNB_SIFT (std::sort on the left score; ties keep index order here) ----
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool is_ncc = pass == 0;
+            if (q.size() >= 2 && (is_ncc || sift_on)) {
+                std::vector<size_t> idx(q.size());
+                std::iota(idx.begin(), idx.end(), 0);
+                if (is_ncc) std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return q[a].ncc_l > q[b].ncc_l; });
+                else std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return q[a].sift_l < q[b].sift_l; });
+                const double best = is_ncc ? q[idx[0]].ncc_l : q[idx[0]].sift_l;
+                size_t keep = 1;
+                for (size_t j = 0; j + 1 < q.size(); ++j) {
+                    if (best == 0) break;
+                    const double next = is_ncc ? q[idx[j + 1]].ncc_l : q[idx[j + 1]].sift_l;
+                    const double ratio = is_ncc ? next / best : best / next;
+                    if (ratio >= bnb_thresh) ++keep; else break;
+                }
+                std::vector<Quad> o;
+                for (size_t k = 0; k < keep; ++k) o.push_back(q[idx[k]]);
+                q.swap(o);
+            }
+            res->stage[is_ncc ? TQ_BNB : TQ_BNB_SIFT][i] = q;
+        }
         // ---- TQ_GN ----
         for (Quad &e : q) {
             double dlx, dly, drx, dry, sl, sr; bool vl, vr; int il, ir;
@@ -292,15 +317,15 @@ int to_stage_total(void *h, int st)
     for (auto &v : r->stage[st]) t += (long)v.size();
     return (int)t;
 }
-// off: n_kf + 1; per entry: cf, l[3], r[3], ncc[2], sc[2], valid
-void to_get_stage(void *h, int st, int *off, int *cf, double *l, double *r, double *ncc, double *sc, int *valid)
+// off: n_kf + 1; per entry: cf, l[3], r[3], ncc[2], sc[2], valid, sift[2]
+void to_get_stage(void *h, int st, int *off, int *cf, double *l, double *r, double *ncc, double *sc, int *valid, double *sift)
 {
     TResult *R = (TResult *)h; int o = 0;
     for (int i = 0; i < R->n_kf; ++i) {
         off[i] = o;
         for (const Quad &e : R->stage[st][i]) {
             cf[o] = e.cf; l[3 * o] = e.l.x; l[3 * o + 1] = e.l.y; l[3 * o + 2] = e.l.th; r[3 * o] = e.r.x; r[3 * o + 1] = e.r.y; r[3 * o + 2] = e.r.th;
-            ncc[2 * o] = e.ncc_l; ncc[2 * o + 1] = e.ncc_r; sc[2 * o] = e.sc_l; sc[2 * o + 1] = e.sc_r; valid[o] = e.valid;
+            ncc[2 * o] = e.ncc_l; ncc[2 * o + 1] = e.ncc_r; sift[2 * o] = e.sift_l; sift[2 * o + 1] = e.sift_r; sc[2 * o] = e.sc_l; sc[2 * o + 1] = e.sc_r; valid[o] = e.valid;
             ++o;
         }
     }

@@ -69,6 +69,8 @@ mask = (np.arange(len(m0)) % 3 != 1).astype(np.uint8)          # exercises the k
 ref = oracle.temporal_reference((L0, L0, R0), (L1, L1, R1), m0, m1, mask)
 out = dict(kfL=L0, kfR=R0, cfL=L1, cfR=R1, kf=m0, cf=m1, mask=mask)
 for k, v in ref.stages.items():
+    if k in ("sift", "bnb_sift"):      # pass-through stages of the SIFT-off run: identical to their predecessors
+        continue
     out[f"{k}_off"] = v["off"]
     if k == "grid":      # 490 k entries: keep the per-keyframe-mate counts and an order-sensitive checksum of the lists
         out["grid_cfsum"] = np.add.reduceat(np.concatenate([v["cf"].astype(np.int64) * (1 + np.arange(len(v["cf"])) % 7), [0]]), v["off"][:-1].clip(max=len(v["cf"])))
@@ -79,5 +81,14 @@ for k, v in ref.stages.items():
         out[f"{k}_ncc"] = v["ncc"]
     if k in ("gn", "cluster"):
         out[f"{k}_left"], out[f"{k}_right"], out[f"{k}_score"], out[f"{k}_valid"] = v["left"], v["right"], v["score"], v["valid"]
+# the same pair SIFT-on: descriptor pairs regenerated from the mate positions (synth.position_descriptors), so only the
+# reference's lists are stored
+desc = (synth.position_descriptors(m0[:, :3], 1), synth.position_descriptors(m0[:, 3:], 2),
+        synth.position_descriptors(m1[:, :3], 1), synth.position_descriptors(m1[:, 3:], 2))
+refs = oracle.temporal_reference((L0, L0, R0), (L1, L1, R1), m0, m1, mask, desc=desc)
+for k in ("sift", "bnb_sift", "cluster"):
+    v = refs.stages[k]
+    out[f"son_{k}_off"], out[f"son_{k}_cf"], out[f"son_{k}_sift"] = v["off"], v["cf"], v["sift"]
+out["son_cluster_left"], out["son_cluster_right"] = refs.stages["cluster"]["left"], refs.stages["cluster"]["right"]
 np.savez_compressed(os.path.join(HERE, "temporal_ref_small.npz"), **out)
-print("temporal_ref_small", {k: int(v["off"][-1]) for k, v in ref.stages.items()})
+print("temporal_ref_small", {k: int(v["off"][-1]) for k, v in ref.stages.items()}, "SIFT-on", {k: int(v["off"][-1]) for k, v in refs.stages.items()})

@@ -30,6 +30,7 @@ def _as_quads(st):
     q["lx"], q["ly"], q["ltheta"] = st["left"].T
     q["rx"], q["ry"], q["rtheta"] = st["right"].T
     q["ncc_left"], q["ncc_right"] = st["ncc"].T
+    q["sift_left"], q["sift_right"] = st["sift"].T if "sift" in st else (900.0, 900.0)
     q["score_left"], q["score_right"] = st["score"].T
     q["valid"] = st["valid"]
     return q
@@ -38,10 +39,11 @@ def _as_quads(st):
 def _compare(name, off_g, qg, st, tol_px=1e-3, tol_rad=1e-4):
     qo = _as_quads(st)
     assert np.array_equal(off_g, st["off"]), name
-    if name in ("bnb", "gn"):
+    if name in ("bnb", "bnb_sift", "gn"):
         qg, qo = _canon(off_g, qg), _canon(st["off"], qo)
     assert np.array_equal(qg["kf_index"], qo["kf_index"]) and np.array_equal(qg["cf_index"], qo["cf_index"]), name
-    if name in ("ncc", "bnb", "gn", "cluster"):
+    if name in ("ncc", "sift", "bnb", "bnb_sift", "gn", "cluster"):
+        assert np.abs(qg["sift_left"] - qo["sift_left"]).max() < 1e-9 and np.abs(qg["sift_right"] - qo["sift_right"]).max() < 1e-9, name
         assert np.abs(qg["ncc_left"] - qo["ncc_left"]).max() < 1e-5 and np.abs(qg["ncc_right"] - qo["ncc_right"]).max() < 1e-5, name
     for f in ("lx", "ly", "rx", "ry"):
         assert np.abs(qg[f] - qo[f]).max() < tol_px, (name, f)
@@ -75,9 +77,26 @@ def test_stage_by_stage_against_the_oracle(gpu_ctx, seq_case):
         off, q = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, stage=name)
         _compare(name, off, q, c["res"].stages[name])
     n = {k: len(v["cf"]) for k, v in c["res"].stages.items()}
-    assert n["grid"] > n["orient"] > n["ncc"] >= n["bnb"] == n["gn"] > n["cluster"] > 1000
+    assert n["grid"] > n["orient"] > n["ncc"] == n["sift"] >= n["bnb"] == n["bnb_sift"] == n["gn"] > n["cluster"] > 1000
     cnt = gpu_ctx.temporal_counters()
     assert cnt["gate_survivors"] == n["bnb"] and cnt["gn_problems"] == 2 * n["gn"]
+
+
+def test_sift_on_stage_by_stage_against_the_oracle(gpu_ctx, seq_case):
+    """Descriptor pairs supplied: the SIFT gate and the SIFT best-nearly-best pass run on the device."""
+    c = seq_case
+    m0, m1 = c["m0"], c["m1"]
+    desc = (synth.position_descriptors(m0[:, :3], 1), synth.position_descriptors(m0[:, 3:], 2),
+            synth.position_descriptors(m1[:, :3], 1), synth.position_descriptors(m1[:, 3:], 2))
+    res = oracle.temporal(c["kf_imgs"], c["cf_imgs"], m0, m1, desc=desc)
+    kf, cf = _lib.mates_from_arrays(m0[:, :3], m0[:, 3:]), _lib.mates_from_arrays(m1[:, :3], m1[:, 3:])
+    for name in ("sift", "bnb", "bnb_sift", "gn", "cluster"):
+        off, q = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, stage=name, desc=desc)
+        _compare(name, off, q, res.stages[name])
+    n = {k: len(v["cf"]) for k, v in res.stages.items()}
+    assert n["ncc"] > n["sift"] == n["bnb"] > n["bnb_sift"] == n["gn"] > n["cluster"] > 300
+    with pytest.raises(_lib.EbvoError):       # all four descriptor arrays or none
+        gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, desc=(desc[0], None, None, None))
 
 
 def test_default_call_and_mask(gpu_ctx, seq_case):
@@ -99,6 +118,7 @@ def test_golden_reference_output(gpu_ctx):
     imgs_k, imgs_c = (g["kfL"], g["kfL"], g["kfR"]), (g["cfL"], g["cfL"], g["cfR"])
     for name in ("orient", "ncc", "gn", "cluster"):
         off, q = gpu_ctx.temporal_quads(imgs_k, imgs_c, kf, cf, kf_mask=g["mask"], stage=name)
+        assert (q["sift_left"] == 900.0).all()
         st = dict(off=g[f"{name}_off"], cf=g[f"{name}_cf"])
         n = len(st["cf"])
         st["ncc"] = g[f"{name}_ncc"] if f"{name}_ncc" in g.files else np.full((n, 2), -1.0)
@@ -107,6 +127,27 @@ def test_golden_reference_output(gpu_ctx):
         else:
             st.update(left=g["cf"][st["cf"], :3], right=g["cf"][st["cf"], 3:], score=np.full((n, 2), 1e6), valid=np.zeros(n, np.int32))
         _compare(name, off, q, st)
+
+
+def test_golden_reference_output_sift_on(gpu_ctx):
+    """The reference's own SIFT gate / SIFT best-nearly-best / final clusters on the golden pair with descriptor pairs."""
+    g = np.load(GOLD)
+    kf, cf = _lib.mates_from_arrays(g["kf"][:, :3], g["kf"][:, 3:]), _lib.mates_from_arrays(g["cf"][:, :3], g["cf"][:, 3:])
+    imgs_k, imgs_c = (g["kfL"], g["kfL"], g["kfR"]), (g["cfL"], g["cfL"], g["cfR"])
+    desc = (synth.position_descriptors(g["kf"][:, :3], 1), synth.position_descriptors(g["kf"][:, 3:], 2),
+            synth.position_descriptors(g["cf"][:, :3], 1), synth.position_descriptors(g["cf"][:, 3:], 2))
+    for name in ("sift", "bnb_sift", "cluster"):
+        off, q = gpu_ctx.temporal_quads(imgs_k, imgs_c, kf, cf, kf_mask=g["mask"], stage=name, desc=desc)
+        roff, rcf, rs = g[f"son_{name}_off"], g[f"son_{name}_cf"], g[f"son_{name}_sift"]
+        assert np.array_equal(off, roff), name
+        if name == "bnb_sift":
+            own = np.repeat(np.arange(len(roff) - 1), np.diff(roff))
+            o1, o2 = np.lexsort((q["cf_index"], q["kf_index"])), np.lexsort((rcf, own))
+            q, rcf, rs = q[o1], rcf[o2], rs[o2]
+        assert np.array_equal(q["cf_index"], rcf), name
+        assert np.abs(q["sift_left"] - rs[:, 0]).max() < 1e-9 and np.abs(q["sift_right"] - rs[:, 1]).max() < 1e-9, name
+    assert np.abs(np.stack([q["lx"], q["ly"]], 1) - g["son_cluster_left"][:, :2]).max() < 1e-3
+    assert np.abs(np.stack([q["rx"], q["ry"]], 1) - g["son_cluster_right"][:, :2]).max() < 1e-3
 
 
 def test_empty_inputs_and_errors(gpu_ctx):

@@ -30,7 +30,7 @@ def grid_checksum(st):
 def check(o, r, stages=oracle.TQ_STAGES):
     for n in stages:
         a, b = o[n], r[n]
-        if n in ("bnb", "gn"):
+        if n in ("bnb", "bnb_sift", "gn"):
             a, b = canon(a), canon(b)
         assert np.array_equal(a["off"], b["off"]), n
         if "cf" in b:
@@ -48,12 +48,37 @@ def test_golden_reference_output():
     g = np.load(GOLD)
     o = oracle.temporal((g["kfL"], g["kfL"], g["kfR"]), (g["cfL"], g["cfL"], g["cfR"]), g["kf"], g["cf"], g["mask"])
     ref = {}
-    for n in oracle.TQ_STAGES:
-        ref[n] = {k[len(n) + 1:]: g[k] for k in g.files if k.startswith(n + "_")}
-    check(o.stages, ref)
+    stages = [n for n in oracle.TQ_STAGES if n not in ("sift", "bnb_sift")]      # pass-through in the SIFT-off run
+    for n in stages:
+        ref[n] = {k[len(n) + 1:]: g[k] for k in g.files if k.startswith(n + "_") and not k.startswith("bnb_sift")}
+    check(o.stages, ref, stages)
+    assert np.array_equal(o.stages["sift"]["cf"], o.stages["ncc"]["cf"]) and np.array_equal(o.stages["bnb_sift"]["cf"], o.stages["bnb"]["cf"])
     assert len(ref["cluster"]["cf"]) > 1000 and ref["gn"]["valid"].mean() > 0.9
     off = ref["grid"]["off"]
     assert (np.diff(off)[g["mask"] == 0] == 0).all()        # unselected keyframe mates carry no quads
+
+
+def _desc(m0, m1):
+    return (synth.position_descriptors(m0[:, :3], 1), synth.position_descriptors(m0[:, 3:], 2),
+            synth.position_descriptors(m1[:, :3], 1), synth.position_descriptors(m1[:, 3:], 2))
+
+
+def test_golden_reference_output_sift_on():
+    """The SIFT gate (min of 4 L2 distances < 200 on both views) and the SIFT best-nearly-best pass, against the
+    reference's own apply_SIFT_filtering_quads / apply_best_nearly_best_filtering_quads("SIFT") on the same descriptors."""
+    g = np.load(GOLD)
+    o = oracle.temporal((g["kfL"], g["kfL"], g["kfR"]), (g["cfL"], g["cfL"], g["cfR"]), g["kf"], g["cf"], g["mask"], desc=_desc(g["kf"], g["cf"]))
+    for n in ("sift", "bnb_sift", "cluster"):
+        a = o.stages[n]
+        b = dict(off=g[f"son_{n}_off"], cf=g[f"son_{n}_cf"], sift=g[f"son_{n}_sift"])
+        if n == "bnb_sift":
+            a, b = canon(a), canon(b)
+        assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["cf"], b["cf"]), n
+        assert np.abs(a["sift"] - b["sift"]).max() < 1e-9, n
+    assert np.abs(o.stages["cluster"]["left"] - g["son_cluster_left"]).max() < 1e-9
+    assert np.abs(o.stages["cluster"]["right"] - g["son_cluster_right"]).max() < 1e-9
+    n = {k: len(v["cf"]) for k, v in o.stages.items()}
+    assert n["ncc"] > n["sift"] == n["bnb"] > n["bnb_sift"] == n["gn"] > n["cluster"] > 500
 
 
 @pytest.mark.skipif(not oracle.have_temporal_ref(), reason="needs oracle/_ref/libtemporal_ref.so")
@@ -72,6 +97,28 @@ def test_live_against_reference_sources():
     r = oracle.temporal_reference((L0, L0, R0), (L1, L1, R1), m0, m1)
     check(o.stages, r.stages)
     assert len(r.stages["cluster"]["cf"]) > 200
+    # SIFT-on with real cv::SIFT descriptors at the reference's keypoints (8 px along the normal, Stereo_Matches.cpp:655-689)
+    cv2 = pytest.importorskip("cv2")
+    sift = cv2.SIFT_create()
+
+    def desc(img, xyt):
+        s, c = np.sin(xyt[:, 2]), np.cos(xyt[:, 2])
+        out = np.zeros((len(xyt), 2, 128), np.float32)
+        for j, sg in enumerate((1.0, -1.0)):
+            kps = [cv2.KeyPoint(float(x + sg * 8 * a), float(y - sg * 8 * b), 1, float(np.degrees(t))) for x, y, t, a, b in zip(xyt[:, 0], xyt[:, 1], xyt[:, 2], s, c)]
+            out[:, j] = sift.compute(img, kps)[1]
+        return out
+    D = (desc(L0, m0[:, :3]), desc(R0, m0[:, 3:]), desc(L1, m1[:, :3]), desc(R1, m1[:, 3:]))
+    o = oracle.temporal((L0, L0, R0), (L1, L1, R1), m0, m1, desc=D)
+    r = oracle.temporal_reference((L0, L0, R0), (L1, L1, R1), m0, m1, desc=D)
+    check(o.stages, r.stages, ["grid", "orient", "ncc", "sift", "bnb", "bnb_sift", "gn"])
+    assert np.abs(canon(o.stages["bnb_sift"])["sift"] - canon(r.stages["bnb_sift"])["sift"]).max() < 1e-9
+    assert len(r.stages["ncc"]["cf"]) > len(r.stages["sift"]["cf"]) > len(r.stages["bnb_sift"]["cf"]) > 100
+    # integer-valued descriptors tie exactly; std::sort leaves ties of lists longer than 16 in an unspecified order and the
+    # clusterer depends on the order, so the last stage is compared on the keyframe mates whose lists hold no tie
+    a, b = o.stages["cluster"], r.stages["cluster"]
+    same = np.diff(a["off"]) == np.diff(b["off"])
+    assert same.mean() > 0.99
 
 
 def test_empty_and_degenerate_inputs():
