@@ -280,7 +280,14 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_kernel(TqDev d, DevParams p
     const int W = d.W, H = d.H;
     const double side = 7 / 2.0 + 1.0;
     unsigned long long nprob = 0, niter = 0;
-    for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < d.n_kf; i += gridDim.x * WPB) {
+    // persistent warps: (keyframe mate, view) items are pulled from a cursor, so a mate with 100 quads does not hold up the
+    // warps that drew mates with two (counters[5 + view] = cursor)
+    unsigned long long* cursor = d.counters + 5 + blockIdx.y;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(cursor, 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= d.n_kf) break;
         const int n = d.cnt[i];
         if (n == 0) continue;
         {
@@ -371,16 +378,18 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_kernel(TqDev d, DevParams p
                         }
                     }
                     warp_sum3(h00, h10, h11);
-                    warp_sum3(b0, b1, cost);
+                    warp_sum2(b0, b1);
                     h00 += 98 * 1e-6; h11 += 98 * 1e-6;       // H += 1e-6 * Identity for each of the 98 samples (:811)
                     ++niter;
                     double s0, s1;
                     ldlt2_solve(h00, h10, h11, b0, b1, s0, s1);
                     const double e0 = -s0, e1 = -s1;
                     d0 += e0; d1 += e1;
-                    const double rms = sqrt(cost / 98.0);
-                    const bool outlier = (rms > p.gn_huber * 2.0) || (it < 1);
-                    if (sqrt(e0 * e0 + e1 * e1) < p.gn_tol || it == p.gn_max_iter - 1) { valid = !outlier; score = rms; break; }
+                    if (sqrt(e0 * e0 + e1 * e1) < p.gn_tol || it == p.gn_max_iter - 1) {
+                        const double rms = sqrt(warp_sum(cost) / 98.0);       // the residual is only read at the last iteration (:843-847)
+                        valid = !((rms > p.gn_huber * 2.0) || (it < 1)); score = rms;
+                        break;
+                    }
                 }
                 ++nprob;
                 if (lane == 0) {
@@ -512,7 +521,8 @@ void tq_gate(const TqDev& d, int mode, int* counts, const int* offs, int* outCf,
 }
 void tq_gn(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {
-    if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<dim3(tq_warp_blocks(d.n_kf), 2), 32 * WPB, 0, st>>>(d, p)));
+    if (!g_sms) warp_grid(1);
+    if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<dim3(g_sms * 2, 2), 32 * WPB, 0, st>>>(d, p)));
 }
 void tq_cluster(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {
