@@ -412,7 +412,12 @@ __global__ void __launch_bounds__(32 * WPB) tq_cluster_kernel(TqDev d, DevParams
     __shared__ double s_dk[WPB][TQ_CAP], s_gk[WPB][TQ_CAP];
     __shared__ int s_lab[WPB][TQ_CAP], s_csz[WPB][TQ_CAP], s_near[WPB][TQ_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = blockIdx.x * WPB + w; i < d.n_kf; i += gridDim.x * WPB) {
+    unsigned long long* cursor = d.counters + 7;      // keyframe mates are pulled from a cursor: their lists hold 0 .. 128 quads
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(cursor, 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= d.n_kf) break;
         const int n = d.cnt[i];
         const size_t base = (size_t)i * TQ_CAP;
         if (n < 2) {          // :642-643: lists of fewer than two quads are left alone
