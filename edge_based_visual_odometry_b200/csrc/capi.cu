@@ -955,6 +955,8 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
     } else {
         for (int k = 0; k < 4; ++k) { const size_t n = (k < 2) ? n_kf : n_cf; CK(S.get(&d.np[k], n * 98)); CK(S.get(&d.pf[k], n)); }
         CK(S.get(&d.pk16[0], (size_t)w * h)); CK(S.get(&d.pk16[1], (size_t)w * h));
+        CK(S.get(&d.pkh[0], (size_t)w * h)); CK(S.get(&d.pkh[1], (size_t)w * h));
+        d.gn_gather = ctx->params.gn_mode == 1 ? 1 : 0;      // gn_mode 1 selects the gather kernels of both stages
         const size_t pool = (size_t)n_kf * TQ_CAP;
         CK(S.get(&d.cnt, (size_t)n_kf)); CK(S.get(&d.cnt2, (size_t)n_kf));
         CK(S.get(&d.q_cf, pool)); CK(S.get(&d.q_valid, pool)); CK(S.get(&d.q_ncc, 2 * pool)); CK(S.get(&d.q_sift, 2 * pool)); CK(S.get(&d.q_sc, 2 * pool)); CK(S.get(&d.q_l, 3 * pool)); CK(S.get(&d.q_r, 3 * pool));

@@ -129,7 +129,9 @@ struct TqDev {
     const float* desc[4];            // 0 KF left, 1 KF right, 2 CF left, 3 CF right: n x 2 x 128 floats, or all nullptr (SIFT-off)
     int *cellCount, *cellStart, *cellCursor, *cellList, *lcell, *rcx, *rcy;
     float* np[4]; uint8_t* pf[4];    // 0 KF left, 1 KF right, 2 CF left, 3 CF right
-    uint2* pk16[2];                  // CF left / right undistorted view packed with its Sobel gradients (int16)
+    uint2* pk16[2];                  // CF left / right undistorted view packed with its Sobel gradients (int16; gather kernel)
+    uint2* pkh[2];                   // the same as {half I, -, half gx, half gy} (exact; tiled kernel)
+    int gn_gather;                   // 1: tq_gn_kernel (global-memory gathers, cross-check), 0: tq_gn_tile_kernel
     // pool 1 (after gate .. GN) and pool 2 (after clustering): [n_kf][TQ_CAP]
     int *cnt, *cnt2, *q_cf, *q_valid, *r_cf, *r_valid;
     double *q_ncc, *q_sc, *q_l, *q_r, *r_ncc, *r_sc, *r_l, *r_r;   // ncc/sc: 2 per entry, l/r: 3 per entry

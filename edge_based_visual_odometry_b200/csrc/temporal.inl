@@ -93,7 +93,7 @@ __global__ void tq_sort_kernel(TqDev d)    // ascending CF index inside every ce
 }
 
 // {I, 8 gx, 8 gy} as int16 (exact), Sobel 3x3 / 8 with BORDER_REFLECT_101 (utility.h:131-141), for one image
-__global__ void tq_pack_kernel(const uint8_t* I, int W, int H, int pitch, uint2* out)
+__global__ void tq_pack_kernel(const uint8_t* I, int W, int H, int pitch, uint2* out, uint2* outh)
 {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -103,6 +103,9 @@ __global__ void tq_pack_kernel(const uint8_t* I, int W, int H, int pitch, uint2*
     const int gx8 = (at(ym, xp) - at(ym, xm)) + 2 * (at(y, xp) - at(y, xm)) + (at(yp, xp) - at(yp, xm));
     const int gy8 = (at(yp, xm) - at(ym, xm)) + 2 * (at(yp, x) - at(ym, x)) + (at(yp, xp) - at(ym, xp));
     out[(size_t)y * W + x] = make_uint2((uint32_t)at(y, x) | ((uint32_t)(gx8 & 0xffff) << 16), (uint32_t)(gy8 & 0xffff));
+    // 8-bit intensities and Sobel/8 values (k/8, |k| <= 1020) are exact in fp16
+    const __half2 hg = __floats2half2_rn((float)gx8 * 0.125f, (float)gy8 * 0.125f);
+    outh[(size_t)y * W + x] = make_uint2((uint32_t)__half_as_ushort(__float2half_rn((float)at(y, x))), *reinterpret_cast<const uint32_t*>(&hg));
 }
 
 __global__ void __launch_bounds__(32 * WPB) tq_patch_kernel(TqDev d, DevParams p)
@@ -404,6 +407,183 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_kernel(TqDev d, DevParams p
     if (lane == 0 && nprob) { atomicAdd(&d.counters[1], nprob); atomicAdd(&d.counters[2], niter); }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// tq_gn_tile_kernel (default): the 2-D refinement with the data path of gn_lerp64_kernel.  Lanes 0-15 own the "+" patch,
+// 16-31 the "-" patch (3 sample rounds + the cooperative 49th sample); per quad each half-warp stages the pixels its patch
+// can reach while the edge stays within +-R px (both axes) of the build position in a warp-private tile of packed
+// {half I, -, half gx, half gy} pixels; interpolation form on exact fp16 corner differences; FP64 throughout.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TQ_TILE_PX = 320;      // 19 x 16 pixels: reach 2.5 px for every orientation
+__global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevParams p)
+{
+    __shared__ uint2 s_tile[WPB][2][TQ_TILE_PX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int hw = lane >> 4, hl = lane & 15;
+    uint2* tF = s_tile[w][hw];
+    const int u = lane % 12;                                   // cooperative lanes of the two left-over samples
+    const int cRow = u & 1, cCh = (u >> 1) % 3, cSmp = (u >> 1) / 3;
+    const uint2* tC = s_tile[w][cSmp];
+    const int W = d.W, H = d.H;
+    const double side = 7 / 2.0 + 1.0, huber = p.gn_huber;
+    const double MAGIC = 6755399441055744.0;
+    const int sd = blockIdx.y;
+    const uint8_t* Ikf = sd ? d.kfRund : d.kfLund;
+    const uint2* __restrict__ PK = d.pkh[sd];
+    unsigned long long nprob = 0, niter = 0;
+    unsigned long long* cursor = d.counters + 5 + sd;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(cursor, 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= d.n_kf) break;
+        const int n = d.cnt[i];
+        if (n == 0) continue;
+        const double* k = d.kf + 6 * (size_t)i + 3 * sd;
+        const double kx = k[0], ky = k[1];
+        // keyframe patches, once per mate and view (:745-768)
+        double Lc[3], Lc48;
+        {
+            double st_, ct_;
+            sincos(k[2], &st_, &ct_);
+            const double cx = hw ? st_ * side : -st_ * side, cy = hw ? -ct_ * side : ct_ * side;      // +-n*side, n = (-t.y, t.x)
+            double sumL = 0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int t = hl + 16 * m, ii = t / 7 - 3, jj = t % 7 - 3;
+                Lc[m] = sample_u8_exact(Ikf, d.pitch, W, H, (kx + cx) + (ct_ * ii - st_ * jj), (ky + cy) + (st_ * ii + ct_ * jj));
+                sumL += Lc[m];
+            }
+            Lc48 = sample_u8_exact(Ikf, d.pitch, W, H, (kx + cx) + (ct_ * 3 - st_ * 3), (ky + cy) + (st_ * 3 + ct_ * 3));
+            sumL = half_sum(sumL) + Lc48;
+            const double mL = sumL / 49.0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) Lc[m] -= mL;
+            Lc48 -= mL;
+        }
+        for (int q = 0; q < n; ++q) {
+            const size_t e = (size_t)i * TQ_CAP + q;
+            const double* c = d.cf + 6 * (size_t)d.q_cf[e] + 3 * sd;
+            double sc_, cc_;
+            sincos(c[2], &sc_, &cc_);
+            const double cxp = hw ? sc_ * side : -sc_ * side, cyp = hw ? -cc_ * side : cc_ * side;    // this half-warp's patch centre offset
+            double rx[3], ry[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int t = hl + 16 * m, ii = t / 7 - 3, jj = t % 7 - 3;
+                rx[m] = cc_ * ii - sc_ * jj; ry[m] = sc_ * ii + cc_ * jj;
+            }
+            const double rx48 = cc_ * 3 - sc_ * 3, ry48 = sc_ * 3 + cc_ * 3;
+            // tile shape: the patch stays inside while the edge is within +-R px of the build position on both axes
+            const double hext = 3.0 * (fabs(cc_) + fabs(sc_)) + 1e-6;
+            double R = 2.5;
+            int TWp, THp;
+            for (;;) {
+                TWp = (int)ceil(2.0 * (R + hext)) + 2;
+                THp = TWp;
+                while ((0xC107 >> (TWp & 15)) & 1) ++TWp;      // row pitch off the bank-folding residues (see gn_tile64_kernel)
+                if (TWp * THp <= TQ_TILE_PX || R <= 0.0) break;
+                R -= 0.5;
+            }
+            const int npx = TWp * THp;
+            const float invTW = 1.0f / (float)TWp;
+            const double Rv = R - 1e-6, ext = R + hext;
+            double d0 = kx - c[0], d1 = ky - c[1];       // init_disp (:602-603)
+            double lx0 = CUDART_NAN, ly0 = CUDART_NAN, score = 0.0;
+            int ox = 0, oy = 0, oxC = 0, oyC = 0;
+            bool valid = false;
+            for (int it = 0; it < p.gn_max_iter; ++it) {
+                const double lx = kx - d0, ly = ky - d1;
+                const double xs = lx + cxp, ys = ly + cyp;
+                if (!(fabs(lx - lx0) <= Rv && fabs(ly - ly0) <= Rv)) {
+                    lx0 = lx; ly0 = ly;
+                    ox = __double2int_rd(xs - ext); oy = __double2int_rd(ys - ext);
+                    oxC = __shfl_sync(FULL, ox, cSmp << 4); oyC = __shfl_sync(FULL, oy, cSmp << 4);
+                    __syncwarp();
+                    for (int t = hl; t < npx; t += 16) {
+                        const int py = (int)(((float)t + 0.5f) * invTW), px = t - py * TWp;
+                        const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
+                        tF[t] = __ldg(PK + (Y * W + X));
+                    }
+                    __syncwarp();
+                }
+                double vi[3], gxv[3], gyv[3];
+                double sR = 0;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const double x = xs + rx[m], y = ys + ry[m];
+                    const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
+                    const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
+                    const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
+                    const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
+                    const int o = yi * TWp + xi;
+                    const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
+                    const unsigned d0x = hsub2_u32(p10.x, p00.x), d0y = hsub2_u32(p10.y, p00.y);
+                    const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
+                    double top = fma(a, h2d(d0x), h2d(p00.x)), bot = fma(a, h2d(d1x), h2d(p01.x));
+                    vi[m] = round_to_float(fma(bb, bot - top, top));
+                    top = fma(a, h2d(d0y), h2d(p00.y)); bot = fma(a, h2d(d1y), h2d(p01.y));
+                    gxv[m] = round_to_float(fma(bb, bot - top, top));
+                    top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
+                    gyv[m] = round_to_float(fma(bb, bot - top, top));
+                    sR += vi[m];
+                }
+                double vi48, gx48, gy48;
+                {
+                    const double x = shfl_idx_d(xs, cSmp << 4) + rx48, y = shfl_idx_d(ys, cSmp << 4) + ry48;
+                    const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
+                    const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
+                    const int xi = (int)min((unsigned)(__double2loint(tx) - oxC), (unsigned)(TWp - 2));
+                    const int yi = (int)min((unsigned)(__double2loint(ty) - oyC), (unsigned)(THp - 2));
+                    const int o = (yi + cRow) * TWp + xi;
+                    const uint2 p0 = tC[o], p1 = tC[o + 1];
+                    const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
+                    const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
+                    const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));
+                    const double oth = shfl_xor_d(lin, 1);
+                    const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
+                    const double v = round_to_float(fma(bb, bot - top, top));
+                    vi48 = shfl_idx_d(v, 6 * hw); gx48 = shfl_idx_d(v, 6 * hw + 2); gy48 = shfl_idx_d(v, 6 * hw + 4);
+                }
+                sR = half_sum(sR) + vi48;
+                const double mR = div49(sR);
+                double h00 = 0, h10 = 0, h11 = 0, b0 = 0, b1 = 0, cost = 0;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const double r = (m < 3 ? Lc[m] : Lc48) - ((m < 3 ? vi[m] : vi48) - mR);
+                    const double gx = m < 3 ? gxv[m] : gx48, gy = m < 3 ? gyv[m] : gy48;
+                    const double ar = fabs(r);
+                    double wgt = (ar < huber) ? 1.0 : huber * rcp_fast(ar);              // strict <, :808
+                    if (m == 3 && hl != 0) wgt = 0.0;                                     // sample 48 counts once per patch
+                    const double wjx = wgt * gx, wjy = wgt * gy;
+                    h00 = fma(wjx, gx, h00); h10 = fma(wjy, gx, h10); h11 = fma(wjy, gy, h11);
+                    b0 = fma(wjx, r, b0); b1 = fma(wjy, r, b1); cost = fma(wgt * r, r, cost);
+                }
+                warp_sum3(h00, h10, h11);
+                warp_sum2(b0, b1);
+                h00 += 98 * 1e-6; h11 += 98 * 1e-6;       // H += 1e-6 * Identity for each of the 98 samples (:811)
+                ++niter;
+                double s0, s1;
+                ldlt2_solve(h00, h10, h11, b0, b1, s0, s1);
+                const double e0 = -s0, e1 = -s1;
+                d0 += e0; d1 += e1;
+                if (sqrt(e0 * e0 + e1 * e1) < p.gn_tol || it == p.gn_max_iter - 1) {
+                    const double rms = sqrt(warp_sum(cost) / 98.0);
+                    valid = !((rms > huber * 2.0) || (it < 1)); score = rms;
+                    break;
+                }
+            }
+            ++nprob;
+            if (lane == 0) {
+                d.q_sc[2 * e + sd] = score;
+                if (valid) { double* o = (sd ? d.q_r : d.q_l) + 3 * e; o[0] = kx - d0; o[1] = ky - d1; }     // :623-632
+                if (valid) atomicOr(&d.q_valid[e], 1 << sd);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && nprob) { atomicAdd(&d.counters[1], nprob); atomicAdd(&d.counters[2], niter); }
+}
+
 // Temporal_Matches.cpp:636-733
 __global__ void __launch_bounds__(32 * WPB) tq_cluster_kernel(TqDev d, DevParams p)
 {
@@ -517,8 +697,8 @@ void tq_patches(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
     const int n = d.n_kf > d.n_cf ? d.n_kf : d.n_cf;
     if (n > 0) EBVO_KERNEL(prof, "tq_patch", st, (tq_patch_kernel<<<dim3(tq_warp_blocks(n), 4), 32 * WPB, 0, st>>>(d, p)));
     const dim3 g((d.W + 31) / 32, (d.H + 7) / 8), t(32, 8);
-    EBVO_KERNEL(prof, "tq_pack", st, (tq_pack_kernel<<<g, t, 0, st>>>(d.cfLund, d.W, d.H, d.pitch, d.pk16[0])));
-    EBVO_KERNEL(prof, "tq_pack", st, (tq_pack_kernel<<<g, t, 0, st>>>(d.cfRund, d.W, d.H, d.pitch, d.pk16[1])));
+    EBVO_KERNEL(prof, "tq_pack", st, (tq_pack_kernel<<<g, t, 0, st>>>(d.cfLund, d.W, d.H, d.pitch, d.pk16[0], d.pkh[0])));
+    EBVO_KERNEL(prof, "tq_pack", st, (tq_pack_kernel<<<g, t, 0, st>>>(d.cfRund, d.W, d.H, d.pitch, d.pk16[1], d.pkh[1])));
 }
 void tq_gate(const TqDev& d, int mode, int* counts, const int* offs, int* outCf, cudaStream_t st, Prof* prof)
 {
@@ -527,7 +707,8 @@ void tq_gate(const TqDev& d, int mode, int* counts, const int* offs, int* outCf,
 void tq_gn(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {
     if (!g_sms) warp_grid(1);
-    if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<dim3(g_sms * 2, 2), 32 * WPB, 0, st>>>(d, p)));
+    if (d.n_kf > 0 && d.gn_gather) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_kernel<<<dim3(g_sms * 2, 2), 32 * WPB, 0, st>>>(d, p)));
+    else if (d.n_kf > 0) EBVO_KERNEL(prof, "tq_gn", st, (tq_gn_tile_kernel<<<dim3(g_sms * 2, 2), 32 * WPB, 0, st>>>(d, p)));
 }
 void tq_cluster(const TqDev& d, const DevParams& p, cudaStream_t st, Prof* prof)
 {

@@ -99,6 +99,22 @@ def test_sift_on_stage_by_stage_against_the_oracle(gpu_ctx, seq_case):
         gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, desc=(desc[0], None, None, None))
 
 
+def test_gather_kernel_cross_checks_the_tiled_refinement(gpu_ctx, seq_case):
+    """gn_mode 1 selects tq_gn_kernel (global-memory gathers, four-weight blend); the default tq_gn_tile_kernel (shared-memory
+    tiles, interpolation form, cooperative 49th sample) implements the same FP64 arithmetic on another data path."""
+    c = seq_case
+    kf, cf = _lib.mates_from_arrays(c["m0"][:, :3], c["m0"][:, 3:]), _lib.mates_from_arrays(c["m1"][:, :3], c["m1"][:, 3:])
+    prm = _lib.default_params(); prm.gn_mode = 1
+    ctx = _lib.Context(0, 480, 300, max_batch=1, max_edges=65536, params=prm)
+    off1, q1 = ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, stage="gn")
+    ctx.close()
+    off0, q0 = gpu_ctx.temporal_quads(c["kf_imgs"], c["cf_imgs"], kf, cf, stage="gn")
+    assert np.array_equal(off0, off1) and np.array_equal(q0["cf_index"], q1["cf_index"]) and np.array_equal(q0["valid"], q1["valid"])
+    for f in ("lx", "ly", "rx", "ry"):
+        assert np.abs(q0[f] - q1[f]).max() < 1e-4, f
+    assert np.abs(q0["score_left"] - q1["score_left"]).max() < 1e-5 and np.abs(q0["score_right"] - q1["score_right"]).max() < 1e-5
+
+
 def test_default_call_and_mask(gpu_ctx, seq_case):
     c = seq_case
     kf, cf = _lib.mates_from_arrays(c["m0"][:, :3], c["m0"][:, 3:]), _lib.mates_from_arrays(c["m1"][:, :3], c["m1"][:, 3:])
