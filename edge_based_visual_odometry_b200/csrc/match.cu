@@ -1683,34 +1683,43 @@ __global__ void __launch_bounds__(32 * WPB, 6) ncc2_best_kernel(DevBatch b, DevP
 // S13: ordered compaction of the per-left-edge staging slots into the mate list (one CTA per frame)
 __global__ void __launch_bounds__(1024) compact_kernel(DevBatch b, ebvo_mate* out, int outStride)
 {
-    const int f = blockIdx.x, tid = threadIdx.x;
+    // one CTA per frame walks the left-edge list in chunks of 1024 (coalesced flag reads and record copies): ballot + popc
+    // inside a warp, the 32 warp totals scanned through shared memory, a running base across chunks
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nL = b.nE[2 * f];
     const int* flag = b.mateFlag + (size_t)f * b.E;
-    const ebvo_mate* stg = b.mates + (size_t)f * b.E;
-    ebvo_mate* dst = out + (size_t)f * outStride;
-    const int per = (nL + 1023) / 1024;
-    const int i0 = tid * per;
-    int local = 0;
-    for (int k = 0; k < per; ++k) { int i = i0 + k; if (i < nL) local += flag[i]; }
+    const uint4* stg = reinterpret_cast<const uint4*>(b.mates + (size_t)f * b.E);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)f * outStride);
     __shared__ int s_w[32];
-    int v = local;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, v, d); if ((tid & 31) >= d) v += t; }
-    if ((tid & 31) == 31) s_w[tid >> 5] = v;
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
     __syncthreads();
-    if (tid < 32) {
-        int x = s_w[tid];
+    for (int c0 = 0; c0 < nL; c0 += 1024) {
+        const int i = c0 + tid;
+        const bool keep = i < nL && flag[i];
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (lane == 0) s_w[w] = __popc(m);
+        __syncthreads();
+        if (w == 0) {
+            const int v = s_w[lane];
+            int x = v;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(FULL, x, d); if (tid >= d) x += t; }
-        s_w[tid] = x;
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, x, d); if (lane >= d) x += t; }
+            s_w[lane] = x - v;                                  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int base = s_base;
+        const int pos = base + s_w[w] + __popc(m & ((1u << lane) - 1));
+        if (keep && pos < outStride) {
+            const uint4* r = stg + 4 * (size_t)i;               // 64-byte records
+            uint4* o = dst + 4 * (size_t)pos;
+            o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        }
+        __syncthreads();
+        if (tid == 1023) s_base = base + s_w[31] + __popc(m);   // total of this chunk (warp 31's prefix + its count)
+        __syncthreads();
     }
-    __syncthreads();
-    int pos = v - local + ((tid >> 5) ? s_w[(tid >> 5) - 1] : 0);
-    for (int k = 0; k < per; ++k) {
-        int i = i0 + k;
-        if (i < nL && flag[i]) { if (pos < outStride) dst[pos] = stg[i]; ++pos; }
-    }
-    if (tid == 1023) b.nMates[f] = pos < outStride ? pos : outStride;
+    if (tid == 0) b.nMates[f] = s_base < outStride ? s_base : outStride;
 }
 
 // debug: copy frame 0's live pool (src < 0) or dump[src] into compact arrays at host-scanned offsets
