@@ -166,6 +166,26 @@ def test_golden_reference_output_sift_on(gpu_ctx):
     assert np.abs(np.stack([q["rx"], q["ry"]], 1) - g["son_cluster_right"][:, :2]).max() < 1e-3
 
 
+def test_full_size_pair_end_to_end(gpu_ctx):
+    """BASELINE configs[3] at the ETH3D cables_2 shape (742x464): both frames through ebvo_stereo_frame, then the quad
+    tracking, against the oracle run on the same mates (identical final quads, order included)."""
+    cal = synth.kitti_calib(742, 464)   # the cables_2 YAML calibration yields no stereo mates in the reference itself
+    calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    fr = []
+    for k in (0, 1):
+        L, R, _ = synth.stereo_sequence_pair(cal, k)
+        fr.append((L, R, gpu_ctx.stereo_frame(calib, L, R, want_edges=False)))
+    (L0, R0, m0), (L1, R1, m1) = fr
+    assert len(m0) > 10000 and len(m1) > 10000
+    off, q = gpu_ctx.temporal_quads((L0, L0, R0), (L1, L1, R1), m0, m1)
+    as6 = lambda m: np.stack([m[k] for k in ("lx", "ly", "ltheta", "rx", "ry", "rtheta")], 1)
+    o = oracle.temporal((L0, L0, R0), (L1, L1, R1), as6(m0), as6(m1))
+    _compare("cluster", off, q, o.stages["cluster"])
+    cnt = gpu_ctx.temporal_counters()
+    assert cnt["grid_candidates"] == len(o.stages["grid"]["cf"]) and cnt["orient_survivors"] == len(o.stages["orient"]["cf"])
+    assert cnt["gate_survivors"] == len(o.stages["bnb"]["cf"]) and len(q) > 30000
+
+
 def test_empty_inputs_and_errors(gpu_ctx):
     img = np.full((64, 96), 100, np.uint8)
     none = np.zeros(0, _lib.MATE_DTYPE)
