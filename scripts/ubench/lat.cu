@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/ubench/lat scripts/ubench/lat.cu   (run: scripts/ubench/lat on a B200)
 // Dependent-chain latencies on sm_100a (cycles per instruction, one warp): DFMA, DADD, DMUL, F2F.F64.F16, 64-bit SHFL + DADD, LDS.64.
 #include <cstdio>
 #include <cuda_fp16.h>
