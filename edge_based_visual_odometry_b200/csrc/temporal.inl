@@ -207,13 +207,13 @@ __global__ void __launch_bounds__(32 * WPB) tq_gate_kernel(TqDev d, int mode, in
                             const float4* cl = reinterpret_cast<const float4*>(d.desc[2] + (size_t)c2 * 256);
                             const float4 b1 = cl[lane], b2 = cl[32 + lane];
                             double d11 = d2(kl1, b1), d12 = d2(kl1, b2), d21 = d2(kl2, b1), d22 = d2(kl2, b2);
-                            warp_sum2(d11, d12); warp_sum2(d21, d22);
+                            warp_sum4(d11, d12, d21, d22, lane);
                             fl = fmin(fmin(sqrt(d11), sqrt(d12)), fmin(sqrt(d21), sqrt(d22)));
                             if (!(fl < d.sift_thresh)) continue;
                             const float4* cr = reinterpret_cast<const float4*>(d.desc[3] + (size_t)c2 * 256);
                             const float4 c1 = cr[lane], c2_ = cr[32 + lane];
                             d11 = d2(kr1, c1); d12 = d2(kr1, c2_); d21 = d2(kr2, c1); d22 = d2(kr2, c2_);
-                            warp_sum2(d11, d12); warp_sum2(d21, d22);
+                            warp_sum4(d11, d12, d21, d22, lane);
                             fr = fmin(fmin(sqrt(d11), sqrt(d12)), fmin(sqrt(d21), sqrt(d22)));
                             if (!(fr < d.sift_thresh)) continue;
                         }
@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevPar
                     h00 = fma(wjx, gx, h00); h10 = fma(wjy, gx, h10); h11 = fma(wjy, gy, h11);
                     b0 = fma(wjx, r, b0); b1 = fma(wjy, r, b1); cost = fma(wgt * r, r, cost);
                 }
-                warp_sum3(h00, h10, h11);
-                warp_sum2(b0, b1);
+                warp_sum4(h00, h10, h11, b0, lane);
+                b1 = warp_sum(b1);
                 h00 += 98 * 1e-6; h11 += 98 * 1e-6;       // H += 1e-6 * Identity for each of the 98 samples (:811)
                 ++niter;
                 double s0, s1;
