@@ -1071,8 +1071,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, D
 //    instead of 4 + the shared weight products; the corner differences are exact in fp16 (|dI| <= 255,
 //    |8 dg| <= 2040 < 2^11), taken by HSUB2 on the packed pixels before widening;
 //  * a half-warp owns 49 samples = 3 full rounds + ONE sample.  gn_tile64_kernel spends a whole fourth round on
-//    it (2 active lanes of 32).  Here the two left-over samples of a candidate (cell (3,3) of each patch) are
-//    evaluated cooperatively: lane u < 12 handles (patch, channel, cell row), the pairs meet by one shuffle;
+//    it (2 active lanes of 32).  Here the left-over sample of each patch (cell (3,3)) is evaluated cooperatively by
+//    its own half-warp: lane hl < 6 handles (channel, cell row), the pairs meet by one shuffle;
 //  * the patch centre + shift is added once per iteration, the rotated cell offset once per sample.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned hsub2_u32(unsigned a, unsigned b)   // a - b on both halves
@@ -1088,10 +1088,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int hw = lane >> 4, hl = lane & 15;
     uint2* tF = s_tile[w][hw];
-    // cooperative lanes of the left-over samples: u = 2 (3 patch + channel) + row
-    const int u = lane % 12;
-    const int cRow = u & 1, cCh = (u >> 1) % 3, cSmp = (u >> 1) / 3;
-    const uint2* tC = s_tile[w][cSmp];
+    // cooperative lanes of the left-over sample of THIS half-warp's patch: lane hl < 6 = (channel, cell row), u = 2 channel + row
+    // (lanes 6-15 repeat them), so every lane works on its own half-warp's tile and patch centre
+    const int u = hl % 6;
+    const int cRow = u & 1, cCh = u >> 1;
     const int W = b.W, H = b.H;
     const double huber = p.gn_huber;
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
@@ -1118,7 +1118,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
             int Rint = 0;
             bool tileValid = false;
             double rx[3], ry[3], Lc[3], rx48 = 0, ry48 = 0, Lc48 = 0;
-            int TWp = 0, THp = 0, npx = 0, ox = 0, oy = 0, oxC = 0, oyC = 0;
+            int TWp = 0, THp = 0, npx = 0, ox = 0, oy = 0;
             float invTW = 0.f;
             for (int q = q0; q < q1; ++q) {
                 const int i = c_owner[q];
@@ -1186,7 +1186,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         alpha0 = alpha; Rv = (double)Rint - 1e-6; tileValid = true;
                         ox = __double2int_rd(xs - (Rint * fabs(dirx) + hext));
                         oy = __double2int_rd(ys - (Rint * fabs(diry) + hext));
-                        oxC = __shfl_sync(FULL, ox, cSmp << 4); oyC = __shfl_sync(FULL, oy, cSmp << 4);
                         ++nbuilds;
                         __syncwarp();
                         for (int e = hl; e < npx; e += 16) {
@@ -1222,21 +1221,21 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
                     double vi48, vg48;
                     {
-                        const double x = shfl_idx_d(xs, cSmp << 4) + rx48, y = shfl_idx_d(ys, cSmp << 4) + ry48;
+                        const double x = xs + rx48, y = ys + ry48;
                         const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
-                        const int xi = (int)min((unsigned)(__double2loint(tx) - oxC), (unsigned)(TWp - 2));
-                        const int yi = (int)min((unsigned)(__double2loint(ty) - oyC), (unsigned)(THp - 2));
+                        const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
+                        const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                         const int o = (yi + cRow) * TWp + xi;
-                        const uint2 p0 = tC[o], p1 = tC[o + 1];
+                        const uint2 p0 = tF[o], p1 = tF[o + 1];
                         const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                         const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
                         const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));       // top (row 0) or bottom (row 1)
                         const double oth = shfl_xor_d(lin, 1);
                         const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
                         const double v = round_to_float(fma(bb, bot - top, top));
-                        vi48 = shfl_idx_d(v, 6 * hw);
-                        const double gx = shfl_idx_d(v, 6 * hw + 2), gy = shfl_idx_d(v, 6 * hw + 4);
+                        vi48 = shfl_idx_d(v, hw << 4);
+                        const double gx = shfl_idx_d(v, (hw << 4) + 2), gy = shfl_idx_d(v, (hw << 4) + 4);
                         vg48 = -gx * dirx + gy * diry;
                     }
                     sR = half_sum(sR) + vi48;

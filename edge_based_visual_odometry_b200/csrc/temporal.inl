@@ -420,9 +420,8 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevPar
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int hw = lane >> 4, hl = lane & 15;
     uint2* tF = s_tile[w][hw];
-    const int u = lane % 12;                                   // cooperative lanes of the two left-over samples
-    const int cRow = u & 1, cCh = (u >> 1) % 3, cSmp = (u >> 1) / 3;
-    const uint2* tC = s_tile[w][cSmp];
+    const int u = hl % 6;                                      // cooperative lanes of this half-warp's left-over sample
+    const int cRow = u & 1, cCh = u >> 1;
     const int W = d.W, H = d.H;
     const double side = 7 / 2.0 + 1.0, huber = p.gn_huber;
     const double MAGIC = 6755399441055744.0;
@@ -489,7 +488,7 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevPar
             const double Rv = R - 1e-6, ext = R + hext;
             double d0 = kx - c[0], d1 = ky - c[1];       // init_disp (:602-603)
             double lx0 = CUDART_NAN, ly0 = CUDART_NAN, score = 0.0;
-            int ox = 0, oy = 0, oxC = 0, oyC = 0;
+            int ox = 0, oy = 0;
             bool valid = false;
             for (int it = 0; it < p.gn_max_iter; ++it) {
                 const double lx = kx - d0, ly = ky - d1;
@@ -497,7 +496,6 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevPar
                 if (!(fabs(lx - lx0) <= Rv && fabs(ly - ly0) <= Rv)) {
                     lx0 = lx; ly0 = ly;
                     ox = __double2int_rd(xs - ext); oy = __double2int_rd(ys - ext);
-                    oxC = __shfl_sync(FULL, ox, cSmp << 4); oyC = __shfl_sync(FULL, oy, cSmp << 4);
                     __syncwarp();
                     for (int t = hl; t < npx; t += 16) {
                         const int py = (int)(((float)t + 0.5f) * invTW), px = t - py * TWp;
@@ -529,20 +527,20 @@ __global__ void __launch_bounds__(32 * WPB, 4) tq_gn_tile_kernel(TqDev d, DevPar
                 }
                 double vi48, gx48, gy48;
                 {
-                    const double x = shfl_idx_d(xs, cSmp << 4) + rx48, y = shfl_idx_d(ys, cSmp << 4) + ry48;
+                    const double x = xs + rx48, y = ys + ry48;
                     const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
                     const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
-                    const int xi = (int)min((unsigned)(__double2loint(tx) - oxC), (unsigned)(TWp - 2));
-                    const int yi = (int)min((unsigned)(__double2loint(ty) - oyC), (unsigned)(THp - 2));
+                    const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
+                    const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                     const int o = (yi + cRow) * TWp + xi;
-                    const uint2 p0 = tC[o], p1 = tC[o + 1];
+                    const uint2 p0 = tF[o], p1 = tF[o + 1];
                     const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                     const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
                     const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));
                     const double oth = shfl_xor_d(lin, 1);
                     const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
                     const double v = round_to_float(fma(bb, bot - top, top));
-                    vi48 = shfl_idx_d(v, 6 * hw); gx48 = shfl_idx_d(v, 6 * hw + 2); gy48 = shfl_idx_d(v, 6 * hw + 4);
+                    vi48 = shfl_idx_d(v, hw << 4); gx48 = shfl_idx_d(v, (hw << 4) + 2); gy48 = shfl_idx_d(v, (hw << 4) + 4);
                 }
                 sR = half_sum(sR) + vi48;
                 const double mR = div49(sR);
