@@ -199,3 +199,46 @@ def test_empty_inputs_and_errors(gpu_ctx):
     assert len(q) == 0
     with pytest.raises(_lib.EbvoError):
         gpu_ctx.temporal_quads((img,) * 3, (img,) * 3, one, one, stage="grid", cap=0)
+
+
+def test_sift_on_with_device_descriptors_end_to_end():
+    """The reference's default flow entirely through the C ABI: stereo frames with sift_mode = 1, the mates' descriptor
+    pairs from ebvo_sift_descriptors (left edges on the left view, right edges on the right view: Stereo_Matches.cpp:655-689,
+    1627-1635), then the quad tracking SIFT-on - against the oracle fed with cv2 descriptors at the same keypoints.
+    Device descriptors equal cv2's on 99.97 % of the entries (off by one elsewhere), so quads whose SIFT distance lies
+    within a few units of the 200 gate may flip: <= 0.5 % of the lists."""
+    cv2 = pytest.importorskip("cv2")
+    cal = synth.kitti_calib(480, 300)
+    calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    prm = _lib.default_params(); prm.sift_mode = 1
+    ctx = _lib.Context(0, 480, 300, max_batch=1, max_edges=65536, params=prm)
+    sift = cv2.SIFT_create()
+
+    def cv_desc(img, xyt):
+        kps = []
+        for x, y, t in xyt:
+            for s in (1, -1):
+                kps.append(cv2.KeyPoint(float(x + s * 8 * np.sin(t)), float(y - s * 8 * np.cos(t)), 1, float(180 / np.pi * t)))
+        return sift.compute(img, kps)[1].reshape(len(xyt), 2, 128).astype(np.float32)
+
+    fr = []
+    for k in (0, 1):
+        L, R, _ = synth.stereo_sequence_pair(cal, k, scene_seed=31)
+        m = ctx.stereo_frame(calib, L, R, want_edges=False)
+        l3 = np.stack([m["lx"], m["ly"], m["ltheta"]], 1); r3 = np.stack([m["rx"], m["ry"], m["rtheta"]], 1)
+        dev = (ctx.sift_descriptors(L, _lib.edges_from_xyt(l3)), ctx.sift_descriptors(R, _lib.edges_from_xyt(r3)))
+        ref = (cv_desc(L, l3), cv_desc(R, r3))
+        assert np.mean(dev[0] == ref[0]) > 0.999 and np.abs(dev[0] - ref[0]).max() <= 1
+        fr.append((L, R, m, np.concatenate([l3, r3], 1), dev, ref))
+    (L0, R0, m0, a0, d0, c0), (L1, R1, m1, a1, d1, c1) = fr
+    off, q = ctx.temporal_quads((L0, L0, R0), (L1, L1, R1), m0, m1, desc=(d0[0], d0[1], d1[0], d1[1]))
+    ctx.close()
+    o = oracle.temporal((L0, L0, R0), (L1, L1, R1), a0, a1, desc=(c0[0], c0[1], c1[0], c1[1])).stages["cluster"]
+    assert len(o["cf"]) > 300
+    same = np.diff(off) == np.diff(o["off"])
+    assert same.mean() >= 0.995, same.mean()
+    # on the keyframe mates whose lists have the same length: same quads, same places
+    og, oo = np.repeat(same, np.diff(off)), np.repeat(same, np.diff(o["off"]))
+    assert np.mean(q["cf_index"][og] == o["cf"][oo]) >= 0.995
+    ok = q["cf_index"][og] == o["cf"][oo]
+    assert np.abs(q["lx"][og][ok] - o["left"][oo][ok, 0]).max() < 1e-3 and np.abs(q["ly"][og][ok] - o["left"][oo][ok, 1]).max() < 1e-3
