@@ -760,8 +760,16 @@ __device__ __forceinline__ double sample_u8_exact(const uint8_t* __restrict__ I,
 // Valid for |v| in the float normal range, which holds for 8-bit image samples and their Sobel responses.
 __device__ __forceinline__ double round_to_float(double v)
 {
+#ifdef GN_RINT
+    // the same rounding on the bit pattern (integer pipe instead of three FP64 instructions): drop the low 29 mantissa bits
+    // to nearest, ties to even; a mantissa carry runs into the exponent, which is the correct result
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+    return __longlong_as_double((long long)(u & ~0x1FFFFFFFull));
+#else
     const double c = __dmul_rn(v, 536870913.0);   // 2^29 + 1
     return __dsub_rn(c, __dsub_rn(c, v));
+#endif
 }
 // exact integer -> double without conversion instructions (2^52 magic); fields of the packed right-view pixel
 __device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x43300000, (int)(u.x & 0xffffu)) - 4503599627370496.0; }
@@ -876,10 +884,15 @@ __device__ __forceinline__ double rcp_fast(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#ifdef GN_RCP3
+    const double e = fma(-x, y, 1.0);        // one third-order step: y (1 + e + e^2), |e| < 2^-20 => error 2^-60
+    return fma(y, fma(e, e, e), y);
+#else
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
+#endif
 }
 // a / b (b finite, positive, normal) correctly rounded in all but pathological cases, without the division sequence
 __device__ __forceinline__ double div_fast(double a, double b)
@@ -892,6 +905,9 @@ __device__ __forceinline__ double div_fast(double a, double b)
 // exact fp16 -> fp64 (one F2F.F64.F16, the half selected in place from the low 16 bits of the argument)
 __device__ __forceinline__ double h2d(unsigned int lo16)
 {
+#ifdef WI_NOF2F
+    return __hiloint2double((int)(lo16 << 16) | 0x3ff00000, 0);
+#endif
     double d;
     asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"((unsigned short)lo16));
     return d;
@@ -1084,10 +1100,17 @@ __device__ __forceinline__ unsigned hsub2_u32(unsigned a, unsigned b)   // a - b
 template <int GT64_MAXPX, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
 {
+#ifdef GN_REC16
+    // 16-byte records {half I, half dI | half gx, half gy | half dgx, half dgy | -}: d* = value at x + 1 minus value at x (exact in
+    // fp16), taken when the tile is built, so that a sample is two LDS.128 (rows y0, y0 + 1) and no HSUB2
+    __shared__ uint4 s_tile[WPB][2][GT64_MAXPX];
+    uint4* tF = s_tile[threadIdx.x >> 5][(threadIdx.x & 31) >> 4];
+#else
     __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint2* tF = s_tile[threadIdx.x >> 5][(threadIdx.x & 31) >> 4];
+#endif
+    const int lane = threadIdx.x & 31;
     const int hw = lane >> 4, hl = lane & 15;
-    uint2* tF = s_tile[w][hw];
     // cooperative lanes of the left-over sample of THIS half-warp's patch: lane hl < 6 = (channel, cell row), u = 2 channel + row
     // (lanes 6-15 repeat them), so every lane works on its own half-warp's tile and patch centre
     const int u = hl % 6;
@@ -1191,7 +1214,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         for (int e = hl; e < npx; e += 16) {
                             const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
                             const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
+#ifdef GN_REC16
+                            const int X1 = min(max(ox + px + 1, 0), W - 1);
+                            const uint2 P = __ldg(PK + (Y * W + X)), Q = __ldg(PK + (Y * W + X1));
+                            tF[e] = make_uint4((P.x & 0xffffu) | (hsub2_u32(Q.x, P.x) << 16), P.y, hsub2_u32(Q.y, P.y), 0u);
+#else
                             tF[e] = __ldg(PK + (Y * W + X));
+#endif
                         }
                         __syncwarp();
                     }
@@ -1204,7 +1233,21 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
+#ifdef WI_NOCONFLICT
+                        const int o = (yi * TWp + xi) & 0;
+#else
                         const int o = yi * TWp + xi;
+#endif
+#ifdef GN_REC16
+                        const uint4 r0 = tF[o], r1 = tF[o + TWp];
+                        // FP64 interpolation rounded to float = util_bilinear_Sample_F (utility.h:159-172) per channel
+                        double top = fma(a, h2d(r0.x >> 16), h2d(r0.x)), bot = fma(a, h2d(r1.x >> 16), h2d(r1.x));
+                        vi[m] = round_to_float(fma(bb, bot - top, top));
+                        top = fma(a, h2d(r0.z), h2d(r0.y)); bot = fma(a, h2d(r1.z), h2d(r1.y));
+                        const double gx = round_to_float(fma(bb, bot - top, top));
+                        top = fma(a, h2d(r0.z >> 16), h2d(r0.y >> 16)); bot = fma(a, h2d(r1.z >> 16), h2d(r1.y >> 16));
+                        const double gy = round_to_float(fma(bb, bot - top, top));
+#else
                         const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
                         const unsigned d0x = hsub2_u32(p10.x, p00.x), d0y = hsub2_u32(p10.y, p00.y);
                         const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
@@ -1215,6 +1258,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double gx = round_to_float(fma(bb, bot - top, top));
                         top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
                         const double gy = round_to_float(fma(bb, bot - top, top));
+#endif
                         vg[m] = -gx * dirx + gy * diry;                                   // :1240
                         sR += vi[m];
                     }
@@ -1227,10 +1271,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                         const int o = (yi + cRow) * TWp + xi;
+#ifdef GN_REC16
+                        const uint4 rc = tF[o];
+                        const unsigned s0 = cCh == 0 ? rc.x : (cCh == 1 ? rc.y : rc.y >> 16);
+                        const unsigned sd = cCh == 0 ? rc.x >> 16 : (cCh == 1 ? rc.z : rc.z >> 16);
+                        const double lin = fma(a, h2d(sd), h2d(s0));                      // top (row 0) or bottom (row 1)
+#else
                         const uint2 p0 = tF[o], p1 = tF[o + 1];
                         const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                         const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
                         const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));       // top (row 0) or bottom (row 1)
+#endif
                         const double oth = shfl_xor_d(lin, 1);
                         const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
                         const double v = round_to_float(fma(bb, bot - top, top));
@@ -1238,7 +1289,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double gx = shfl_idx_d(v, (hw << 4) + 2), gy = shfl_idx_d(v, (hw << 4) + 4);
                         vg48 = -gx * dirx + gy * diry;
                     }
+#ifdef WI_NOREDUCE
+                    sR = sR + vi48;
+#else
                     sR = half_sum(sR) + vi48;
+#endif
                     const double mR = div49(sR);
                     double Hh = 0, bb_ = 0, cost = 0;
 #pragma unroll
@@ -1250,18 +1305,30 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         double wgt = huber * rcp_fast(fmax(ar, huber));
                         if (ar <= huber) wgt = 1.0;
 #else
+#ifdef WI_NOHUBER
+                        double wgt = (ar <= huber) ? 1.0 : huber;
+#else
                         double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
+#endif
 #endif
                         if (m == 3 && hl != 0) wgt = 0.0;                                 // sample 48 counts once per patch
                         const double wg = wgt * gg;
                         Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
                     }
+#ifndef WI_NOREDUCE
                     warp_sum2t(Hh, bb_, lane);
+#endif
                     ++niters;
+#ifdef WI_FIXED
+                    const double delta = -div_fast(bb_, fabs(Hh) + 1.0) * 1e-3;
+                    alpha += delta;
+                    if (it == WI_FIXED - 1) {
+#else
                     if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
                     const double delta = -div_fast(bb_, Hh);
                     alpha += delta;
                     if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
+#endif
                         cost = warp_sum(cost);
                         const double rms = sqrt(cost / 98.0);
                         score = rms; conf = exp(-rms / p.gn_huber);
