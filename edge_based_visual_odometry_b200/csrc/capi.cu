@@ -379,7 +379,7 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     if (ctx->params.gn_mode == 2) CK(dalloc(ctx, &b.pk, b.gStride * B));
     else if (ctx->params.gn_mode == 1) CK(dalloc(ctx, &b.pk16, b.gStride * B));
     else CK(dalloc(ctx, &b.pkh, b.gStride * B));
-    CK(dalloc(ctx, &b.npatch, (size_t)b.E * 98 * nImg)); CK(dalloc(ctx, &b.pflag, (size_t)b.E * nImg));
+    CK(dalloc(ctx, &b.npatch, (size_t)b.E * NPF * nImg)); CK(dalloc(ctx, &b.pflag, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.blk, (size_t)b.NB * B)); CK(dalloc(ctx, &b.pmax, (size_t)b.NB * B)); CK(dalloc(ctx, &b.smin, (size_t)b.NB * B));
     CK(dalloc(ctx, &b.lines, (size_t)b.E * 8 * B));
     CK(dalloc(ctx, &b.cstart, (size_t)b.E * B)); CK(dalloc(ctx, &b.ccount, (size_t)b.E * B));
@@ -565,7 +565,7 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     if (v.pkh) v.pkh += F0 * b.gStride;
     if (v.pk16) v.pk16 += F0 * b.gStride;
     if (v.pk) v.pk += F0 * b.gStride;
-    v.npatch += i0 * E * 98; v.pflag += i0 * E;
+    v.npatch += i0 * E * NPF; v.pflag += i0 * E;
     v.blk += F0 * b.NB; v.pmax += F0 * b.NB; v.smin += F0 * b.NB;
     v.lines += F0 * E * 8;
     v.cstart += F0 * E; v.ccount += F0 * E; v.poolUsed += F0;

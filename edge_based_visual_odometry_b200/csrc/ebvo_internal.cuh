@@ -19,6 +19,7 @@ constexpr int OH = TH + 2;
 constexpr int IW = 2 * OW;         // interp samples per tile incl. ring: 68
 constexpr int IH = 2 * OH;
 constexpr int TOED_THREADS = 256;
+constexpr int NPF = 104;           // floats per edge in DevBatch::npatch: "+" cells at 0..48, "-" cells at 52..100, zero padding (16-byte rows)
 
 // Debug stage dumps (frame 0 only): in-kernel snapshots of lists that do not survive the fused kernels.
 // Every buffer is addressed with the left edge's pool segment offset (cstart[i]); n[i] = entries of edge i.
@@ -51,7 +52,7 @@ struct DevBatch {
     uint2* pk16;   // {I, 8gx, 8gy} as int16           FP64 GN kernel
     float4* pk;    // {I, gx, gy, 0} floats            FP32 GN kernel
     size_t gStride;
-    float* npatch; uint8_t* pflag;        // normalised NCC patches [img][E][98] + flat flags [img][E]           // packed {I, gx, gy, 0} of the undistorted RIGHT images, [frame][H*W] (Sobel 3x3 / 8)
+    float* npatch; uint8_t* pflag;        // normalised NCC patches [img][E][NPF] + flat flags [img][E]
     float4* blk; float* pmax; float* smin;  // right-edge block bounds [frame][NB]
     double* lines;                        // [frame][E][8]: a, b, c, dirx, diry, sin(thL), cos(thL), pad
     int *cstart, *ccount;                 // [frame][E]

@@ -34,6 +34,10 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m)
 {
     return __hiloint2double(__shfl_xor_sync(FULL, __double2hiint(v), m), __shfl_xor_sync(FULL, __double2loint(v), m));
 }
+__device__ __forceinline__ double shfl_xor_dm(double v, int m, unsigned mask)   // for code that only part of the warp executes
+{
+    return __hiloint2double(__shfl_xor_sync(mask, __double2hiint(v), m), __shfl_xor_sync(mask, __double2loint(v), m));
+}
 __device__ __forceinline__ double shfl_idx_d(double v, int src)
 {
     return __hiloint2double(__shfl_sync(FULL, __double2hiint(v), src), __shfl_sync(FULL, __double2loint(v), src));
@@ -169,23 +173,32 @@ __global__ void __launch_bounds__(1024) bounds_kernel(DevBatch b)
 struct GateCtx {
     double a, b, c, nrm, xL, yL, thL;
     double ylo, yhi, xlo, xhi;
+    double qlo, qhi, m2lo, m2hi;   // guard bands of the division- and sqrt-free forms of the S1 / S2 tests
     int blo, bhi;
 };
 
+// The reference's tests are fabs(a x + b y + c) / nrm < epi (Stereo_Matches.cpp:99) and sqrt(dx^2 + dy^2) <= maxdisp (:545-546).
+// t / nrm < epi is decided by t against epi * nrm and sqrt(s) <= maxdisp by s against maxdisp^2 whenever the value lies
+// outside a 2^-50 relative band around the threshold (a correctly rounded quotient / root cannot cross it there); inside
+// the band (probability ~1e-15 per test) the reference's own expression is evaluated.  Decisions are identical by construction.
 __device__ __forceinline__ bool gate_test(const GateCtx& g, const DevParams& p, int mode, double xr, double yr, double thr)
 {
-    double d = fabs(g.a * xr + g.b * yr + g.c) / g.nrm;   // Stereo_Matches.cpp:99
-    if (!(d < p.epi)) return false;
+    const double t = fabs(g.a * xr + g.b * yr + g.c);
+    bool ok = t < g.qlo;
+    if (!ok && !(t > g.qhi)) ok = (t / g.nrm) < p.epi;
     if (mode >= 1) {
-        double dx = g.xL - xr, dy = g.yL - yr;
-        if (!(sqrt(dx * dx + dy * dy) <= p.maxdisp)) return false;   // :545-546
+        const double dx = g.xL - xr, dy = g.yL - yr;
+        const double s2 = dx * dx + dy * dy;
+        bool ok2 = s2 < g.m2lo;
+        if (!ok2 && !(s2 > g.m2hi)) ok2 = sqrt(s2) <= p.maxdisp;
+        ok = ok && ok2;
     }
     if (mode >= 2) {
         double od = fabs((g.thL - thr) * (180.0 / 3.14159265358979323846));   // :887-901
         if (od > 180.0) od = 360.0 - od;
-        if (!(od < p.orient_deg || fabs(od - 180.0) < p.orient_deg)) return false;
+        ok = ok && (od < p.orient_deg || fabs(od - 180.0) < p.orient_deg);
     }
-    return true;
+    return ok;
 }
 
 __device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const DevParams& p, const double* F, int f, int i, int mode)
@@ -196,6 +209,10 @@ __device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const 
     g.b = F[3] * g.xL + F[4] * g.yL + F[5] * 1.0;
     g.c = F[6] * g.xL + F[7] * g.yL + F[8] * 1.0;
     g.nrm = sqrt((g.a * g.a) + (g.b * g.b));
+    {
+        const double q = p.epi * g.nrm, m2 = p.maxdisp * p.maxdisp, eps = 8.8817841970012523e-16;   // 2^-50
+        g.qlo = q * (1.0 - eps); g.qhi = q * (1.0 + eps); g.m2lo = m2 * (1.0 - eps); g.m2hi = m2 * (1.0 + eps);
+    }
     // conservative search window
     if (mode >= 1) { g.xlo = g.xL - p.maxdisp - 1e-6; g.xhi = g.xL + p.maxdisp + 1e-6; g.ylo = g.yL - p.maxdisp - 1e-6; g.yhi = g.yL + p.maxdisp + 1e-6; }
     else { g.xlo = -1.0; g.xhi = (double)b.W + 1.0; g.ylo = -1.0; g.yhi = (double)b.H + 1.0; }
@@ -466,28 +483,116 @@ __device__ __forceinline__ void dump_put(const DumpBuf& d, int o, int ridx, doub
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Quarter-warp (8-lane) helpers of the patch / NCC kernels: lane q of a group owns cells t = q + 8 r, r < 7 (t < 49) of
+// both the "+" and the "-" patch; four items (edges, candidate pairs, cluster centres) advance per warp instruction and
+// a reduction is 3 butterfly steps.  A full warp per item left a third of the lanes idle in the second round of cells
+// and paid 5-step reductions per item.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group8_sum2(double& a, double& b, int q, int base)   // sums over the 8 lanes; both results in every lane
+{
+    const bool h = q & 4;
+    double k = h ? b : a;
+    k += shfl_xor_d(h ? a : b, 4);
+    k += shfl_xor_d(k, 2); k += shfl_xor_d(k, 1);
+    a = shfl_idx_d(k, base); b = shfl_idx_d(k, base + 4);
+}
+__device__ __forceinline__ void group8_sum4(double& a, double& b, double& c, double& d, int q, int base)
+{
+    const bool h4 = q & 4, h2 = q & 2;
+    double k0 = h4 ? c : a, k1 = h4 ? d : b;
+    k0 += shfl_xor_d(h4 ? a : c, 4); k1 += shfl_xor_d(h4 ? b : d, 4);
+    double k = h2 ? k1 : k0;
+    k += shfl_xor_d(h2 ? k0 : k1, 2);
+    k += shfl_xor_d(k, 1);
+    a = shfl_idx_d(k, base); b = shfl_idx_d(k, base + 2); c = shfl_idx_d(k, base + 4); d = shfl_idx_d(k, base + 6);
+}
+
+// raw "+"/"-" samples of the cells this lane owns (utility.cpp:82-93, 141-159); act = false leaves zeros
+__device__ __forceinline__ void raw_patches8(const uint8_t* I, int pitch, int W, int H, double x, double y, double s, double c, double shift,
+                                             int q, bool act, float (&vp)[7], float (&vm)[7])
+{
+    const double pxp = x + shift * s, pyp = y + shift * (-c), pxm = x + shift * (-s), pym = y + shift * c;   // utility.cpp:84-87
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int t = q + 8 * r;
+        vp[r] = 0.f; vm[r] = 0.f;
+        if (act && t < 49) {
+            const int i = t / 7 - 3, j = t % 7 - 3;
+            const double ox = c * (double)i - s * (double)j, oy = s * (double)i + c * (double)j;   // utility.cpp:151
+            vp[r] = bilinear_u8(I, pitch, W, H, ox + pxp, oy + pyp);
+            vm[r] = bilinear_u8(I, pitch, W, H, ox + pxm, oy + pym);
+        }
+    }
+}
+// utility.cpp:165-178 with OpenCV's CV_32F type mix (double mean / sums, float centred and normalised values); in place
+__device__ __forceinline__ void normalise_patches8(float (&vp)[7], float (&vm)[7], int q, int base, bool& flatP, bool& flatM)
+{
+    const int nr = q == 0 ? 7 : 6;
+    double sp = 0, sm = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) if (r < nr) { sp += (double)vp[r]; sm += (double)vm[r]; }
+    group8_sum2(sp, sm, q, base);
+    const float mp = (float)(sp / 49.0), mm = (float)(sm / 49.0);
+    double ssp = 0, ssm = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        if (r < nr) { vp[r] -= mp; vm[r] -= mm; ssp += (double)(vp[r] * vp[r]); ssm += (double)(vm[r] * vm[r]); }
+    }
+    group8_sum2(ssp, ssm, q, base);
+    flatP = ssp < 1e-10; flatM = ssm < 1e-10;          // => similarity -1 (utility.cpp:170-172)
+    const float ip = (float)(1.0 / sqrt(ssp)), im = (float)(1.0 / sqrt(ssm));
+#pragma unroll
+    for (int r = 0; r < 7; ++r) if (r < nr) { vp[r] *= ip; vm[r] *= im; }
+}
+// max of the four similarities with std::max({..}) NaN semantics (Stereo_Matches.cpp:592-596); sums already reduced
+__device__ __forceinline__ double ncc_max4(double pp, double nn, double pn, double np, bool aP, bool aM, bool bP, bool bM)
+{
+    if (aP || bP) pp = -1.0;
+    if (aM || bM) nn = -1.0;
+    if (aP || bM) pn = -1.0;
+    if (aM || bP) np = -1.0;
+    double m = pp;
+    if (m < nn) m = nn;
+    if (m < pn) m = pn;
+    if (m < np) m = np;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // S5: the "+"/"-" patches of EVERY edge of both views, sampled from the RAW image (Stereo_Matches.cpp:562-563)
 // and normalised once.  A right edge is a candidate of ~5 left edges; the reference re-samples it for each pair.
-// Layout: npatch[img][e][0..48] = "+" cells, [49..97] = "-" cells (zero-mean, unit-norm floats); pflag bit0/bit1 =
-// flat "+"/"-" patch (sum of squares < 1e-10 => similarity -1).  One warp per edge.
+// Layout: npatch[img][e][0..48] = "+" cells, [52..100] = "-" cells (zero-mean, unit-norm floats, zero padding to
+// 16-byte rows); pflag bit0/bit1 = flat "+"/"-" patch.  A warp takes 32 edges: every lane evaluates sincos for one
+// of them (one pass of the FP64 trigonometry per 32 edges), then four edges at a time are sampled by a quarter-warp each.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * WPB) patch_kernel(DevBatch b, DevParams p)
 {
     const int img = blockIdx.y, lane = threadIdx.x & 31;
+    const int g = lane >> 3, q = lane & 7, base = lane & ~7;
     const int n = b.nE[img];
     const uint8_t* I = b.raw + (size_t)img * b.imgStride;
     const double *ex = b.ex + (size_t)img * b.E, *ey = b.ey + (size_t)img * b.E, *eth = b.eth + (size_t)img * b.E;
-    float* np_ = b.npatch + (size_t)img * b.E * 98;
+    float* np_ = b.npatch + (size_t)img * b.E * NPF;
     uint8_t* pf = b.pflag + (size_t)img * b.E;
-    for (int e = blockIdx.x * WPB + (threadIdx.x >> 5); e < n; e += gridDim.x * WPB) {
-        float vp[2], vm[2];
-        Patches P;
-        raw_patches(I, b.pitch, b.W, b.H, ex[e], ey[e], eth[e], p.shift_mag, lane, vp, vm);
-        normalise_patches(vp, vm, lane, P);
-        float* o = np_ + (size_t)e * 98;
-        o[lane] = P.p[0]; o[49 + lane] = P.m[0];
-        if (lane + 32 < 49) { o[lane + 32] = P.p[1]; o[49 + lane + 32] = P.m[1]; }
-        if (lane == 0) pf[e] = (P.flatP ? 1 : 0) | (P.flatM ? 2 : 0);
+    for (int e0 = (blockIdx.x * WPB + (threadIdx.x >> 5)) * 32; e0 < n; e0 += gridDim.x * WPB * 32) {
+        double xl = 0, yl = 0, sl = 0, cl = 0;
+        if (e0 + lane < n) { xl = ex[e0 + lane]; yl = ey[e0 + lane]; sincos(eth[e0 + lane], &sl, &cl); }
+        for (int k = 0; k < 8 && e0 + 4 * k < n; ++k) {
+            const int src = 4 * k + g, e = e0 + src;
+            const double x = shfl_idx_d(xl, src), y = shfl_idx_d(yl, src), s = shfl_idx_d(sl, src), c = shfl_idx_d(cl, src);
+            const bool act = e < n;
+            float vp[7], vm[7];
+            bool flatP, flatM;
+            raw_patches8(I, b.pitch, b.W, b.H, x, y, s, c, p.shift_mag, q, act, vp, vm);
+            normalise_patches8(vp, vm, q, base, flatP, flatM);
+            if (act) {
+                float* o = np_ + (size_t)e * NPF;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) { o[q + 8 * r] = vp[r]; o[52 + q + 8 * r] = vm[r]; }
+                if (q == 0) { o[48] = vp[6]; o[100] = vm[6]; pf[e] = (flatP ? 1 : 0) | (flatM ? 2 : 0); }
+                else if (q < 4) { o[48 + q] = 0.f; o[100 + q] = 0.f; }
+            }
+        }
     }
 }
 
@@ -501,6 +606,19 @@ __device__ __forceinline__ void load_patches(const float* __restrict__ np_, cons
     P.flatP = fl & 1; P.flatM = fl & 2;
 }
 
+// S6 + S7 (+ S7'): one warp per left edge, four candidates at a time (a quarter-warp per pair).  Lane q owns the float4
+// chunks q and q + 8 (< 13) of each 52-float half of a patch row, so the four cross dot products are lane-local FP64
+// sums of exact products before a 3-step reduction; the right patches of the next four candidates are in flight while
+// the current four are scored.
+struct PatchRegs { float4 p0, p1, m0, m1; int flags; };
+__device__ __forceinline__ void load_patch_row(const float* __restrict__ np_, const uint8_t* __restrict__ pf, int e, int q, PatchRegs& P)
+{
+    const float4* o = reinterpret_cast<const float4*>(np_ + (size_t)e * NPF);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.p0 = __ldg(o + q); P.m0 = __ldg(o + 13 + q);
+    P.p1 = q < 5 ? __ldg(o + 8 + q) : z; P.m1 = q < 5 ? __ldg(o + 21 + q) : z;
+    P.flags = pf[e];
+}
 __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams p, int use_sift)
 {
     __shared__ double s_sc[WPB][MAXC];
@@ -511,9 +629,10 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
     __shared__ int s_or2[WPB][MAXC];
     __shared__ int s_or3[WPB][MAXC];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 3, q = lane & 7, base = lane & ~7;
     const int imgL = 2 * f, imgR = 2 * f + 1;
     const int nL = b.nE[imgL];
-    const float *npL = b.npatch + (size_t)imgL * b.E * 98, *npR = b.npatch + (size_t)imgR * b.E * 98;
+    const float *npL = b.npatch + (size_t)imgL * b.E * NPF, *npR = b.npatch + (size_t)imgR * b.E * NPF;
     const uint8_t *pfL = b.pflag + (size_t)imgL * b.E, *pfR = b.pflag + (size_t)imgR * b.E;
     const double *exR = b.ex + (size_t)imgR * b.E, *eyR = b.ey + (size_t)imgR * b.E, *ethR = b.eth + (size_t)imgR * b.E;
     const int* cstart = b.cstart + (size_t)f * b.E;
@@ -528,23 +647,38 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
         const int n = ccount[i];
         if (n == 0) { if (dumps && lane == 0) { b.dump[DUMP_S6].n[i] = 0; b.dump[DUMP_S7].n[i] = 0; } continue; }
         const int st = cstart[i];
-        Patches PL, PR, PN;
-        load_patches(npL, pfL, i, lane, PL);
+        PatchRegs L, R, N;
+        load_patch_row(npL, pfL, i, q, L);
+        const double lp[8] = {L.p0.x, L.p0.y, L.p0.z, L.p0.w, L.p1.x, L.p1.y, L.p1.z, L.p1.w};
+        const double lm[8] = {L.m0.x, L.m0.y, L.m0.z, L.m0.w, L.m1.x, L.m1.y, L.m1.z, L.m1.w};
+        const bool lP = L.flags & 1, lM = L.flags & 2;
         int ns = 0;
-        int rn = c_ridx[st];
-        load_patches(npR, pfR, rn, lane, PN);
-        for (int j = 0; j < n; ++j) {
+        int rn = g < n ? c_ridx[st + g] : -1;
+        N = L;
+        if (rn >= 0) load_patch_row(npR, pfR, rn, q, N);
+        for (int j0 = 0; j0 < n; j0 += 4) {
             const int r = rn;
-            PR = PN;
-            if (j + 1 < n) { rn = c_ridx[st + j + 1]; load_patches(npR, pfR, rn, lane, PN); }   // prefetch: the loads overlap the reductions below
-            const double s = ncc_score(PL, PR);
-            if (s > p.ncc_thresh) {      // NCC_THRESH gate, :597
-                if (ns < MAXC) {
-                    if (lane == 0) { s_sc[w][ns] = s; s_ri[w][ns] = r; s_cf[w][ns] = use_sift ? c_conf[st + j] : 0.0; }
-                    ++ns;
-                } else if (lane == 0) atomicExch(b.errFlag, 3);
+            R = N;
+            if (j0 + 4 < n) {      // prefetch: the loads overlap the sums and reductions below
+                rn = j0 + 4 + g < n ? c_ridx[st + j0 + 4 + g] : -1;
+                if (rn >= 0) load_patch_row(npR, pfR, rn, q, N);
             }
+            const double rp[8] = {R.p0.x, R.p0.y, R.p0.z, R.p0.w, R.p1.x, R.p1.y, R.p1.z, R.p1.w};
+            const double rm[8] = {R.m0.x, R.m0.y, R.m0.z, R.m0.w, R.m1.x, R.m1.y, R.m1.z, R.m1.w};
+            double pp = 0, nn = 0, pn = 0, np = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { pp = fma(lp[u], rp[u], pp); nn = fma(lm[u], rm[u], nn); pn = fma(lp[u], rm[u], pn); np = fma(lm[u], rp[u], np); }
+            group8_sum4(pp, nn, pn, np, q, base);
+            const double sc = ncc_max4(pp, nn, pn, np, lP, lM, R.flags & 1, R.flags & 2);
+            const bool pass = r >= 0 && sc > p.ncc_thresh;       // NCC_THRESH gate, :597
+            const unsigned m = __ballot_sync(FULL, pass && q == 0);
+            if (pass && q == 0) {
+                const int o = ns + __popc(m & ((1u << lane) - 1));
+                if (o < MAXC) { s_sc[w][o] = sc; s_ri[w][o] = r; s_cf[w][o] = use_sift ? c_conf[st + j0 + g] : 0.0; }
+            }
+            ns += __popc(m);
         }
+        if (ns > MAXC) { if (lane == 0) atomicExch(b.errFlag, 3); ns = MAXC; }
         __syncwarp();
         if (dumps) {
             for (int k = lane; k < ns; k += 32) { int r = s_ri[w][k]; dump_put(b.dump[DUMP_S6], st + k, r, exR[r], eyR[r], ethR[r], s_sc[w][k]); }
@@ -713,12 +847,11 @@ __global__ void __launch_bounds__(128) shift_kernel(DevBatch b, DevParams p, int
 }
 
 // ------------------------------------------------------------------------------------------------------
-// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  Four kernels (ebvo_params.gn_mode):
+// S9 Gauss-Newton along the epipolar line (Stereo_Matches.cpp:1159-1358).  Three kernels (ebvo_params.gn_mode):
 //   gn_lerp64_kernel (0, default)  reference arithmetic (FP64 blends rounded to float, FP64 residuals / weights /
 //                              normal equations); persistent warps pulling pool-slot chunks, right-view samples
 //                              served from warp-private shared-memory tiles that are kept across the candidates
 //                              of a left edge, 3 sample rounds + a cooperative 49th sample
-//   gn_tile64_kernel (3)       the round-1 form of the same kernel (four-weight blend, 4 sample rounds); cross-check
 //   gn64_kernel (1)            the same arithmetic, one warp per candidate, samples gathered from global memory
 //                              (the simple form; kept as the cross-check of the tiled kernel)
 //   gn32_kernel (2)            everything FP32: 0.02 % of the mates move by > 1e-3 px (non-converging GN); opt-in
@@ -760,16 +893,11 @@ __device__ __forceinline__ double sample_u8_exact(const uint8_t* __restrict__ I,
 // Valid for |v| in the float normal range, which holds for 8-bit image samples and their Sobel responses.
 __device__ __forceinline__ double round_to_float(double v)
 {
-#ifdef GN_RINT
     // the same rounding on the bit pattern (integer pipe instead of three FP64 instructions): drop the low 29 mantissa bits
     // to nearest, ties to even; a mantissa carry runs into the exponent, which is the correct result
     unsigned long long u = (unsigned long long)__double_as_longlong(v);
     u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
     return __longlong_as_double((long long)(u & ~0x1FFFFFFFull));
-#else
-    const double c = __dmul_rn(v, 536870913.0);   // 2^29 + 1
-    return __dsub_rn(c, __dsub_rn(c, v));
-#endif
 }
 // exact integer -> double without conversion instructions (2^52 magic); fields of the packed right-view pixel
 __device__ __forceinline__ double pk_i(uint2 u) { return __hiloint2double(0x43300000, (int)(u.x & 0xffffu)) - 4503599627370496.0; }
@@ -837,20 +965,23 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 }
 
 // ------------------------------------------------------------------------------------------------------
-// gn_tile64_kernel (default).  One warp per LEFT EDGE (dynamic chunks of the frame's left-edge list), looping over
-// that edge's surviving candidates: the left patches are sampled once per left edge, not once per candidate.
-// Lanes 0-15 own the "+" patch, lanes 16-31 the "-" patch (cell t = hl + 16 m, m < 4, t < 49), so the two patch
-// means reduce inside half-warps.  Per candidate each half-warp stages the pixels its patch can reach while alpha
-// stays within +-R px of the build position into a warp-private tile of packed {half I, half gx, half gy} pixels
-// (exact values, 8 B each, widened to double per corner).  Coordinates beyond the image read the clamped border
-// pixel, which is what util_bilinear_Sample_F's coordinate clamp produces (utility.h:161-166).  The four corners
-// of a sample are then 4 LDS.64 instead of 12 scattered global loads (the gather kernel is bound by
-// L1 wavefronts: ~10 cache lines per load instruction).  The tile is rebuilt when alpha leaves the +-R window
-// (3 % of the candidates).  Arithmetic: FP64 four-corner blends of I, gx and gy, each rounded to float
-// (util_bilinear_Sample_F returns float); FP64 residuals, Huber weights and normal equations; the divisions by
-// 49, by |r| and by H are evaluated by reciprocal + FMA correction (within 1 ulp; same class as the summation
-// order).  Measured against the reference: identical to gn64_kernel (max 9e-7 px at the GN stage on 128 913
-// candidates, 6e-8 px on the final mates).
+// gn_lerp64_kernel (gn_mode 0, default).  Persistent warps pull chunks of pool slots from per-frame cursors; a warp works
+// on one candidate at a time and samples the left patches once per LEFT EDGE (consecutive slots belong to one edge).
+// Lanes 0-15 own the "+" patch, lanes 16-31 the "-" patch (cell t = hl + 16 m, m < 3), so the two patch means reduce
+// inside half-warps; the 49th cell (3,3) of each patch is evaluated cooperatively by its own half-warp: lane hl < 6
+// handles (channel, cell row), the pairs meet by one shuffle.  Per candidate each half-warp stages the pixels its
+// patch can reach while alpha stays within +-R px of the build position into a warp-private tile of packed
+// {half I, -, half gx, half gy} pixels (exact values, 8 B each, widened to double per corner by F2F.F64.F16).
+// Coordinates beyond the image read the clamped border pixel, which is what util_bilinear_Sample_F's coordinate clamp
+// produces (utility.h:161-166).  The tile is rebuilt when alpha leaves the window (3 % of the candidates) and SURVIVES
+// to the next candidate of the same left edge when that one's patch fits in it.  Arithmetic: the four-corner blend as
+// two horizontal interpolations and one vertical one, top = v00 + a (v10 - v00), bot = v01 + a (v11 - v01),
+// v = top + b (bot - top), per channel in FP64 (corner differences exact in fp16: |dI| <= 255, |8 dg| <= 2040 < 2^11,
+// taken by HSUB2 on the packed pixels), each rounded to float (util_bilinear_Sample_F returns float) on the integer
+// pipe; FP64 residuals, Huber weights and normal equations; divisions by 49, |r| and H by reciprocal + FMA
+// correction (within 1 ulp; same class as the summation order).  Against the reference: 9e-7 px at the GN stage
+// over 128 913 candidates (one non-converging candidate; p99.9 7e-13), 6e-8 px on the final mates.
+// What bounds it and what was tried in round 2: profiles/r02_gn_whatif.md, profiles/r02_gn_pair_experiment.md.
 // ------------------------------------------------------------------------------------------------------
 #ifndef GNL_MINB
 #define GNL_MINB 4
@@ -884,15 +1015,8 @@ __device__ __forceinline__ double rcp_fast(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#ifdef GN_RCP3
     const double e = fma(-x, y, 1.0);        // one third-order step: y (1 + e + e^2), |e| < 2^-20 => error 2^-60
     return fma(y, fma(e, e, e), y);
-#else
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-#endif
 }
 // a / b (b finite, positive, normal) correctly rounded in all but pathological cases, without the division sequence
 __device__ __forceinline__ double div_fast(double a, double b)
@@ -905,192 +1029,10 @@ __device__ __forceinline__ double div_fast(double a, double b)
 // exact fp16 -> fp64 (one F2F.F64.F16, the half selected in place from the low 16 bits of the argument)
 __device__ __forceinline__ double h2d(unsigned int lo16)
 {
-#ifdef WI_NOF2F
-    return __hiloint2double((int)(lo16 << 16) | 0x3ff00000, 0);
-#endif
     double d;
     asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"((unsigned short)lo16));
     return d;
 }
-template <int GT64_MAXPX, int MINB>
-__global__ void __launch_bounds__(32 * WPB, MINB) gn_tile64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
-{
-    // pixels are staged in the packed global format {half I, -, half gx, half gy} (exact values) and widened to double per
-    // corner (one F2F.F64.F16 each on the XU pipe): 8 B instead of 24 B per corner through the shared-memory pipe, which is
-    // what binds this kernel, and the tile fill is a plain copy
-    __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int hw = lane >> 4, hl = lane & 15;
-    uint2* tF = s_tile[w][hw];
-    const int W = b.W, H = b.H;
-    const double huber = p.gn_huber;
-    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: a round-down add leaves floor(x) in the low word
-    // Persistent CTAs: every warp walks all frames (starting at a CTA-dependent one) and pulls chunks of GN_CHUNK
-    // consecutive pool slots from the frame's cursor, so the only tail is at the very end of the launch; a left edge
-    // with 40 candidates is spread over several warps instead of serialising 800 iterations on one.
-    const int f0 = (int)(((long long)blockIdx.x * nFrames) / gridDim.x);
-    for (int ff = 0; ff < nFrames; ++ff) {
-        const int f = (f0 + ff) % nFrames;
-        const int imgL = 2 * f;
-        const uint8_t* IL = b.und + (size_t)imgL * b.imgStride;         // GN uses the UNDISTORTED images (:1293-1294)
-        const uint2* __restrict__ PK = b.pkh + (size_t)f * b.gStride;   // right view: {half I, -, half gx, half gy}
-        const int* c_owner = b.c_owner + (size_t)f * b.P;
-        double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P;
-        double *c_score = b.c_score + (size_t)f * b.P, *c_conf = b.c_conf + (size_t)f * b.P;
-        unsigned long long* cursor = b.counters + (size_t)f * 8 + 7;
-        const int used = min(b.poolUsed[f], b.P);
-        unsigned long long npairs = 0, niters = 0, nbuilds = 0;
-        for (;;) {
-            int q0 = 0;
-            if (lane == 0) q0 = (int)atomicAdd(cursor, (unsigned long long)GN_CHUNK);
-            q0 = __shfl_sync(FULL, q0, 0);
-            if (q0 >= used) break;
-            const int q1 = min(q0 + GN_CHUNK, used);
-            // per-left-edge state, recomputed when the owner of the slot changes (slots of one left edge are contiguous)
-            int owner = -1;
-            double dirx = 0, diry = 0, cx = 0, cy = 0, ex = 0, ey = 0, Rv = 0;
-            double rx[4], ry[4], Lc[4];
-            int TWp = 0, THp = 0, npx = 0;
-            float invTW = 0.f;
-            for (int q = q0; q < q1; ++q) {
-                const int i = c_owner[q];
-                if (i < 0) continue;          // dead slot (dropped by NCC / best-nearly-best)
-                if (i != owner) {
-                    owner = i;
-                    // ---- per left edge: geometry, centred left samples, tile shape ----
-                    const double* ln = b.lines + ((size_t)f * b.E + i) * GEO;
-                    dirx = ln[3]; diry = ln[4];
-                    const double st_ = ln[5], ct_ = ln[6];
-                    const double xL = b.ex[(size_t)imgL * b.E + i], yL = b.ey[(size_t)imgL * b.E + i];
-                    const double side = 7 / 2.0 + 1.0;                               // :1171
-                    cx = hw ? st_ * side : -st_ * side;                              // +-n*side, n = (-t.y, t.x) (:1169-1170)
-                    cy = hw ? -ct_ * side : ct_ * side;
-                    double sumL = 0;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        const int t = hl + 16 * m;
-                        const int ii = t / 7 - 3, jj = t % 7 - 3;
-                        rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
-                        Lc[m] = 0.0;
-                        if (t < 49) { Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m]; }
-                    }
-                    sumL = half_sum(sumL);
-                    const double mL = sumL / 49.0;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) if (hl + 16 * m < 49) Lc[m] -= mL;
-                    // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
-                    const double hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
-                    int R = Rmax;
-                    for (;;) {
-                        TWp = (int)ceil(2.0 * (R * fabs(dirx) + hext)) + 2;
-                        THp = (int)ceil(2.0 * (R * fabs(diry) + hext)) + 2;
-                        // row pitch in 8-byte pixels: residues 0, +-1, +-2 and 8 (mod 16 bank pairs) fold neighbouring rows onto the same banks
-                        while ((0xC107 >> (TWp & 15)) & 1) ++TWp;
-                        if (TWp * THp <= GT64_MAXPX || R == 0) break;
-                        --R;
-                    }
-                    ex = R * fabs(dirx) + hext; ey = R * fabs(diry) + hext;
-                    npx = TWp * THp;
-                    invTW = 1.0f / (float)TWp;
-                    Rv = (double)R - 1e-6;
-                }
-                {
-                const double xr = c_x[q], yr = c_y[q];
-                const double xc = xr + cx, yc = yr + cy;      // patch centre at alpha = 0 (:1203-1204)
-                double alpha = 0.0, score = 0.0, conf = 0.0, alpha0 = CUDART_NAN;
-                int ox = 0, oy = 0;
-                for (int it = 0; it < p.gn_max_iter; ++it) {
-                    const double sx = alpha * dirx, sy = alpha * diry;
-                    if (!(fabs(alpha - alpha0) <= Rv)) {
-                        // ---- (re)build this half-warp's sub-tile around the current position ----
-                        alpha0 = alpha;
-                        ox = __double2int_rd((xc + sx) - ex);
-                        oy = __double2int_rd((yc + sy) - ey);
-                        ++nbuilds;
-                        __syncwarp();
-                        for (int e = hl; e < npx; e += 16) {
-                            const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
-                            const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
-                            tF[e] = __ldg(PK + (Y * W + X));
-                        }
-                        __syncwarp();
-                    }
-                    double vi[4], vg[4];
-                    double sR = 0;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        vi[m] = 0.0; vg[m] = 0.0;
-                        if (hl + 16 * m < 49) {
-                            const double x = (xc + rx[m]) + sx, y = (yc + ry[m]) + sy;
-                            const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
-                            const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
-                            const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
-                            const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
-                            const int o = yi * TWp + xi;
-                            // FP64 blends rounded to float, exactly util_bilinear_Sample_F (utility.h:159-172) per channel
-                            const double w00 = (1 - a) * (1 - bb), w10 = a * (1 - bb), w01 = (1 - a) * bb, w11 = a * bb;
-                            const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
-                            vi[m] = round_to_float(w00 * h2d(p00.x) + w10 * h2d(p10.x) + w01 * h2d(p01.x) + w11 * h2d(p11.x));
-                            const double gx = round_to_float(w00 * h2d(p00.y) + w10 * h2d(p10.y) + w01 * h2d(p01.y) + w11 * h2d(p11.y));
-                            const double gy = round_to_float(w00 * h2d(p00.y >> 16) + w10 * h2d(p10.y >> 16) + w01 * h2d(p01.y >> 16) + w11 * h2d(p11.y >> 16));
-                            vg[m] = -gx * dirx + gy * diry;                                   // :1240
-                            sR += vi[m];
-                        }
-                    }
-                    sR = half_sum(sR);
-                    const double mR = div49(sR);
-                    double Hh = 0, bb_ = 0, cost = 0;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        if (hl + 16 * m < 49) {
-                            const double r = Lc[m] - (vi[m] - mR);
-                            const double gg = vg[m];
-                            const double ar = fabs(r);
-                            const double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
-                            const double wg = wgt * gg;
-                            Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
-                        }
-                    }
-                    warp_sum2(Hh, bb_);
-                    ++niters;
-                    if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
-                    const double delta = -div_fast(bb_, Hh);
-                    alpha += delta;
-                    if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
-                        cost = warp_sum(cost);
-                        const double rms = sqrt(cost / 98.0);
-                        score = rms; conf = exp(-rms / p.gn_huber);
-                        break;
-                    }
-                }
-                ++npairs;
-                if (lane == 0) {
-                    c_x[q] = xr + alpha * dirx;          // :1350-1352 (moved regardless of validity)
-                    c_y[q] = yr + alpha * diry;
-                    c_score[q] = score; c_conf[q] = conf;
-                }
-                }
-            }
-        }
-        if (lane == 0 && npairs) {
-            atomicAdd(&b.counters[(size_t)f * 8 + 2], npairs); atomicAdd(&b.counters[(size_t)f * 8 + 3], niters);
-            atomicAdd(&b.counters[(size_t)f * 8 + 5], nbuilds);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// gn_lerp64_kernel (gn_mode 0, default).  Same decomposition, tiles and arithmetic class as gn_tile64_kernel, with three
-// changes that cut the instruction stream (FP64, XU and issue slots alike):
-//  * the four-corner blend is evaluated as two horizontal interpolations and one vertical one,
-//    top = v00 + a (v10 - v00), bot = v01 + a (v11 - v01), v = top + b (bot - top): 4 FP64 operations per channel
-//    instead of 4 + the shared weight products; the corner differences are exact in fp16 (|dI| <= 255,
-//    |8 dg| <= 2040 < 2^11), taken by HSUB2 on the packed pixels before widening;
-//  * a half-warp owns 49 samples = 3 full rounds + ONE sample.  gn_tile64_kernel spends a whole fourth round on
-//    it (2 active lanes of 32).  Here the left-over sample of each patch (cell (3,3)) is evaluated cooperatively by
-//    its own half-warp: lane hl < 6 handles (channel, cell row), the pairs meet by one shuffle;
-//  * the patch centre + shift is added once per iteration, the rotated cell offset once per sample.
-// ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned hsub2_u32(unsigned a, unsigned b)   // a - b on both halves
 {
     unsigned d;
@@ -1100,15 +1042,8 @@ __device__ __forceinline__ unsigned hsub2_u32(unsigned a, unsigned b)   // a - b
 template <int GT64_MAXPX, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
 {
-#ifdef GN_REC16
-    // 16-byte records {half I, half dI | half gx, half gy | half dgx, half dgy | -}: d* = value at x + 1 minus value at x (exact in
-    // fp16), taken when the tile is built, so that a sample is two LDS.128 (rows y0, y0 + 1) and no HSUB2
-    __shared__ uint4 s_tile[WPB][2][GT64_MAXPX];
-    uint4* tF = s_tile[threadIdx.x >> 5][(threadIdx.x & 31) >> 4];
-#else
     __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
     uint2* tF = s_tile[threadIdx.x >> 5][(threadIdx.x & 31) >> 4];
-#endif
     const int lane = threadIdx.x & 31;
     const int hw = lane >> 4, hl = lane & 15;
     // cooperative lanes of the left-over sample of THIS half-warp's patch: lane hl < 6 = (channel, cell row), u = 2 channel + row
@@ -1214,13 +1149,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         for (int e = hl; e < npx; e += 16) {
                             const int py = (int)(((float)e + 0.5f) * invTW), px = e - py * TWp;
                             const int X = min(max(ox + px, 0), W - 1), Y = min(max(oy + py, 0), H - 1);
-#ifdef GN_REC16
-                            const int X1 = min(max(ox + px + 1, 0), W - 1);
-                            const uint2 P = __ldg(PK + (Y * W + X)), Q = __ldg(PK + (Y * W + X1));
-                            tF[e] = make_uint4((P.x & 0xffffu) | (hsub2_u32(Q.x, P.x) << 16), P.y, hsub2_u32(Q.y, P.y), 0u);
-#else
                             tF[e] = __ldg(PK + (Y * W + X));
-#endif
                         }
                         __syncwarp();
                     }
@@ -1233,21 +1162,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
-#ifdef WI_NOCONFLICT
-                        const int o = (yi * TWp + xi) & 0;
-#else
                         const int o = yi * TWp + xi;
-#endif
-#ifdef GN_REC16
-                        const uint4 r0 = tF[o], r1 = tF[o + TWp];
-                        // FP64 interpolation rounded to float = util_bilinear_Sample_F (utility.h:159-172) per channel
-                        double top = fma(a, h2d(r0.x >> 16), h2d(r0.x)), bot = fma(a, h2d(r1.x >> 16), h2d(r1.x));
-                        vi[m] = round_to_float(fma(bb, bot - top, top));
-                        top = fma(a, h2d(r0.z), h2d(r0.y)); bot = fma(a, h2d(r1.z), h2d(r1.y));
-                        const double gx = round_to_float(fma(bb, bot - top, top));
-                        top = fma(a, h2d(r0.z >> 16), h2d(r0.y >> 16)); bot = fma(a, h2d(r1.z >> 16), h2d(r1.y >> 16));
-                        const double gy = round_to_float(fma(bb, bot - top, top));
-#else
                         const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
                         const unsigned d0x = hsub2_u32(p10.x, p00.x), d0y = hsub2_u32(p10.y, p00.y);
                         const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
@@ -1258,7 +1173,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double gx = round_to_float(fma(bb, bot - top, top));
                         top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
                         const double gy = round_to_float(fma(bb, bot - top, top));
-#endif
                         vg[m] = -gx * dirx + gy * diry;                                   // :1240
                         sR += vi[m];
                     }
@@ -1271,17 +1185,10 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                         const int o = (yi + cRow) * TWp + xi;
-#ifdef GN_REC16
-                        const uint4 rc = tF[o];
-                        const unsigned s0 = cCh == 0 ? rc.x : (cCh == 1 ? rc.y : rc.y >> 16);
-                        const unsigned sd = cCh == 0 ? rc.x >> 16 : (cCh == 1 ? rc.z : rc.z >> 16);
-                        const double lin = fma(a, h2d(sd), h2d(s0));                      // top (row 0) or bottom (row 1)
-#else
                         const uint2 p0 = tF[o], p1 = tF[o + 1];
                         const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                         const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
                         const double lin = fma(a, h2d(hsub2_u32(s1, s0)), h2d(s0));       // top (row 0) or bottom (row 1)
-#endif
                         const double oth = shfl_xor_d(lin, 1);
                         const double top = cRow ? oth : lin, bot = cRow ? lin : oth;
                         const double v = round_to_float(fma(bb, bot - top, top));
@@ -1289,11 +1196,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double gx = shfl_idx_d(v, (hw << 4) + 2), gy = shfl_idx_d(v, (hw << 4) + 4);
                         vg48 = -gx * dirx + gy * diry;
                     }
-#ifdef WI_NOREDUCE
-                    sR = sR + vi48;
-#else
                     sR = half_sum(sR) + vi48;
-#endif
                     const double mR = div49(sR);
                     double Hh = 0, bb_ = 0, cost = 0;
 #pragma unroll
@@ -1301,34 +1204,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const double r = (m < 3 ? Lc[m] : Lc48) - ((m < 3 ? vi[m] : vi48) - mR);
                         const double gg = m < 3 ? vg[m] : vg48;
                         const double ar = fabs(r);
-#ifdef GN_HUBER_BF
-                        double wgt = huber * rcp_fast(fmax(ar, huber));
-                        if (ar <= huber) wgt = 1.0;
-#else
-#ifdef WI_NOHUBER
-                        double wgt = (ar <= huber) ? 1.0 : huber;
-#else
                         double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
-#endif
-#endif
                         if (m == 3 && hl != 0) wgt = 0.0;                                 // sample 48 counts once per patch
                         const double wg = wgt * gg;
                         Hh = fma(wg, gg, Hh); bb_ = fma(wg, r, bb_); cost = fma(wgt * r, r, cost);
                     }
-#ifndef WI_NOREDUCE
                     warp_sum2t(Hh, bb_, lane);
-#endif
                     ++niters;
-#ifdef WI_FIXED
-                    const double delta = -div_fast(bb_, fabs(Hh) + 1.0) * 1e-3;
-                    alpha += delta;
-                    if (it == WI_FIXED - 1) {
-#else
                     if (Hh < 1e-8) break;                          // :1253 (outputs stay at their initial values)
                     const double delta = -div_fast(bb_, Hh);
                     alpha += delta;
                     if (fabs(delta) < p.gn_tol || it == p.gn_max_iter - 1) {
-#endif
                         cost = warp_sum(cost);
                         const double rms = sqrt(cost / 98.0);
                         score = rms; conf = exp(-rms / p.gn_huber);
@@ -1663,10 +1549,113 @@ __device__ int warp_cluster(const double* sx, const double* sy, const double* st
     return ncl;
 }
 
-// CAP = shared-memory capacity per warp.  Two instantiations: <48> (3.4 KB per warp, 8 CTAs per SM) takes every set with
-// n <= 48 - all but a handful - and appends the others to a per-frame work list that <MAXC> processes afterwards.
+// Sets of at most 8 candidates (the usual case: ~4 per left edge after best-nearly-best) are clustered by a QUARTER-warp each,
+// four left edges per warp in lock step: a full warp per set left 75 % of the lanes idle and spent ~1000 warp instructions per
+// set on serial phases.  Same merges, same order, same summation order as warp_cluster (lane gl owns point gl; "label L
+// exists" <=> lab[L] == L; first feasible point in index order wins the ballot).  Larger sets are appended to a per-frame
+// work list (indices in mateFlag, free until ncc2_best; count in counters[6]) for the warp-per-set launches below.
+__global__ void __launch_bounds__(32 * WPB, 8) cluster8_kernel(DevBatch b, DevParams p)
+{
+    __shared__ double s_x[WPB][4][8], s_y[WPB][4][8], s_t[WPB][4][8];
+    __shared__ double s_ox[WPB][4][8], s_oy[WPB][4][8], s_om[WPB][4][8], s_dk[WPB][4][8], s_gk[WPB][4][8];
+    __shared__ int s_lab[WPB][4][8], s_csz[WPB][4][8];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 3, gl = lane & 7;
+    const int nL = b.nE[2 * f];
+    const int* cstart = b.cstart + (size_t)f * b.E;
+    int* ccount = b.ccount + (size_t)f * b.E;
+    double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
+    const bool dumps = b.dumps && f == 0;
+    int* big = b.mateFlag + (size_t)f * b.E;
+    unsigned long long* nbig = b.counters + (size_t)f * 8 + 6;
+    const int small = min(8, p.clus_small);
+    const double d2max = p.clus_dist * p.clus_dist;
+    double *X = s_x[w][g], *Y = s_y[w][g], *T = s_t[w][g], *OX = s_ox[w][g], *OY = s_oy[w][g], *OM = s_om[w][g], *DK = s_dk[w][g], *GK = s_gk[w][g];
+    int *LAB = s_lab[w][g], *CSZ = s_csz[w][g];
+    for (int i0 = (blockIdx.x * WPB + w) * 4; i0 < nL; i0 += gridDim.x * WPB * 4) {      // warp-uniform trip count
+        const int i = i0 + g;
+        int n = i < nL ? ccount[i] : 0;
+        if (n > small) { if (gl == 0) big[(int)atomicAdd(nbig, 1ull)] = i; n = 0; }      // left for the warp-per-set launches
+        else if (n == 0 && i < nL && dumps && gl == 0) b.dump[DUMP_S10].n[i] = 0;
+        const int st = n ? cstart[i] : 0;
+        const bool valid = gl < n;
+        double xi = 0, yi = 0, ti = 0;
+        if (valid) { xi = c_x[st + gl]; yi = c_y[st + gl]; ti = c_th[st + gl]; }        // after the second shift
+        X[gl] = xi; Y[gl] = yi; T[gl] = ti; LAB[gl] = gl; CSZ[gl] = 1;
+        __syncwarp();
+        int li = gl;
+        for (;;) {
+            int bj = -1;
+            if (valid) {
+                double best = CUDART_INF;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j >= n || LAB[j] == li) continue;
+                    const double dx = xi - X[j], dy = yi - Y[j];
+                    const double d2 = dx * dx + dy * dy;
+                    if (d2 < best && d2 < d2max && fabs(ti - T[j]) < p.clus_orient_rad) { best = d2; bj = j; }
+                }
+                if (bj >= 0 && CSZ[li] + CSZ[LAB[bj]] > p.clus_max) bj = -1;             // MAX_CLUSTER_SIZE, EdgeClusterer.cpp:179
+            }
+            const unsigned m = __ballot_sync(FULL, bj >= 0);
+            if (!m) break;
+            const unsigned mg = (m >> (8 * g)) & 0xffu;
+            const int src = mg ? __ffs(mg) - 1 : 0;
+            const int pj = __shfl_sync(FULL, bj, 8 * g + src);
+            int lnew = 0, lold = -1, merged = 0;
+            if (mg) { lnew = LAB[src]; lold = LAB[pj]; merged = CSZ[lnew] + CSZ[lold]; }
+            __syncwarp();
+            if (mg) {
+                if (valid && li == lold) { li = lnew; LAB[gl] = lnew; }
+                if (gl == 0) CSZ[lnew] = merged;
+            }
+            __syncwarp();
+        }
+        // Gaussian-weighted centre of every cluster (EdgeClusterer.cpp:43-117), sums in member index order
+        const bool isL = valid && li == gl;
+        if (isL) {
+            double sxx = 0, syy = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < n && LAB[k] == gl) { sxx += X[k]; syy += Y[k]; }
+            OX[gl] = sxx / CSZ[gl]; OY[gl] = syy / CSZ[gl];
+        }
+        __syncwarp();
+        double dk = 0;
+        if (valid) { const double dx = xi - OX[li], dy = yi - OY[li]; dk = sqrt(dx * dx + dy * dy); DK[gl] = dk; }
+        __syncwarp();
+        if (isL) {
+            double tot = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < n && LAB[k] == gl) tot += DK[k];
+            OM[gl] = tot / CSZ[gl];
+        }
+        __syncwarp();
+        if (valid) { const double z = (dk - OM[li]) / p.clus_sigma; GK[gl] = exp(-0.5 * (z * z)); }   // :103
+        __syncwarp();
+        double vx = 0, vy = 0, vt = 0;
+        if (isL) {
+            double wx = 0, wy = 0, wt = 0, ww = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < n && LAB[k] == gl) { const double gg = GK[k]; wx += gg * X[k]; wy += gg * Y[k]; wt += gg * T[k]; ww += gg; }
+            vx = wx / ww; vy = wy / ww; vt = wt / ww;
+        }
+        // clusters in ascending label order (std::map, :209-222)
+        const unsigned ml = (__ballot_sync(FULL, isL) >> (8 * g)) & 0xffu;
+        if (isL) {
+            const int c = __popc(ml & ((1u << gl) - 1));
+            c_x[st + c] = vx; c_y[st + c] = vy; c_th[st + c] = vt;
+            if (dumps) dump_put(b.dump[DUMP_S10], st + c, -1, vx, vy, vt, CUDART_NAN);
+        }
+        if (gl == 0 && n > 0) { ccount[i] = __popc(ml); if (dumps) b.dump[DUMP_S10].n[i] = __popc(ml); }
+        __syncwarp();
+    }
+}
+
+// The warp-per-set launches work through the list cluster8_kernel left behind.  CAP = shared-memory capacity per warp.
+// <48> (3.4 KB per warp, 8 CTAs per SM) takes the sets with n <= min(48, clus_small); <MAXC> takes the others (it
+// recognises the sets the first launch has already replaced by their clusters: their count is small now).
 template <int CAP, int MINB>
-__global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, DevParams p, int second)
+__global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, DevParams p)
 {
     __shared__ double s_x[WPB][CAP], s_y[WPB][CAP], s_t[WPB][CAP];
     __shared__ double s_ox[WPB][CAP], s_oy[WPB][CAP], s_ot[WPB][CAP];
@@ -1674,24 +1663,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
     __shared__ double s_dk[WPB][CAP], s_gk[WPB][CAP];
     __shared__ unsigned long long s_adm[CAP == MAXC ? WPB : 1][CAP == MAXC ? 2 * MAXC : 1];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nL = b.nE[2 * f];
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
     double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
     const bool dumps = b.dumps && f == 0;
-    // work list of the sets the first launch could not hold: indices in mateFlag (free until ncc2_best), count in counters[6]
-    int* big = b.mateFlag + (size_t)f * b.E;
-    unsigned long long* nbig = b.counters + (size_t)f * 8 + 6;
-    const int nwork = second ? (int)*nbig : nL;
+    const int* big = b.mateFlag + (size_t)f * b.E;
+    const int nwork = (int)b.counters[(size_t)f * 8 + 6];
+    const int small = min(8, p.clus_small);
     for (int wi = blockIdx.x * WPB + w; wi < nwork; wi += gridDim.x * WPB) {
-        const int i = second ? big[wi] : wi;
+        const int i = big[wi];
         int n = ccount[i];
-        if (n == 0) { if (dumps && lane == 0) b.dump[DUMP_S10].n[i] = 0; continue; }
-        if (n > CAP || (CAP < MAXC && n > p.clus_small)) {
-            if (CAP < MAXC) { if (lane == 0) big[(int)atomicAdd(nbig, 1ull)] = i; continue; }   // left for the MAXC instantiation
-            if (lane == 0) atomicExch(b.errFlag, 4);
-            n = CAP;
-        }
+        const bool mid = n <= 48 && n <= p.clus_small;
+        if (CAP < MAXC ? !mid : (mid || n <= small)) continue;      // the other launch's set (or already clustered by it)
+        if (n > CAP) { if (lane == 0) atomicExch(b.errFlag, 4); n = CAP; }
         const int st = cstart[i];
         for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
         __syncwarp();
@@ -1707,14 +1691,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
     }
 }
 
-// S11 NCC of every cluster centre against the left patches (raw images, :1500) + S12 arg-max (first maximum wins, :941-951)
-__global__ void __launch_bounds__(32 * WPB, 6) ncc2_best_kernel(DevBatch b, DevParams p)
+// S11 NCC of every cluster centre against the left patches (raw images, :1500) + S12 arg-max (first maximum wins, :941-951).
+// A quarter-warp per LEFT EDGE, four left edges per warp in lock step (a left edge has one or two cluster centres, so a
+// full warp per edge idles on memory latency and a quarter-warp per centre of one edge finds nothing to do).
+__global__ void __launch_bounds__(32 * WPB, 4) ncc2_best_kernel(DevBatch b, DevParams p)
 {
-    const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int g = lane >> 3, q = lane & 7, base = lane & ~7;
     const int imgL = 2 * f, imgR = 2 * f + 1;
     const int nL = b.nE[imgL];
     const uint8_t* IR = b.raw + (size_t)imgR * b.imgStride;
-    const float* npL = b.npatch + (size_t)imgL * b.E * 98;
+    const float* npL = b.npatch + (size_t)imgL * b.E * NPF;
     const uint8_t* pfL = b.pflag + (size_t)imgL * b.E;
     const double *exL = b.ex + (size_t)imgL * b.E, *eyL = b.ey + (size_t)imgL * b.E, *ethL = b.eth + (size_t)imgL * b.E;
     const int* cstart = b.cstart + (size_t)f * b.E;
@@ -1725,30 +1712,55 @@ __global__ void __launch_bounds__(32 * WPB, 6) ncc2_best_kernel(DevBatch b, DevP
     ebvo_mate* mates = b.mates + (size_t)f * b.E;   // staging: slot i
     const bool dumps = b.dumps && f == 0;
     unsigned long long n2 = 0;
-    (void)w;
-    for (int i = blockIdx.x * WPB + (threadIdx.x >> 5); i < nL; i += gridDim.x * WPB) {
-        const int ncl = ccount[i];
-        if (ncl == 0) { if (lane == 0) { mateFlag[i] = 0; if (dumps) b.dump[DUMP_S11].n[i] = 0; } continue; }
-        const int st = cstart[i];
-        Patches PL, PR;
-        load_patches(npL, pfL, i, lane, PL);
+    for (int i0 = (blockIdx.x * WPB + (threadIdx.x >> 5)) * 4; i0 < nL; i0 += gridDim.x * WPB * 4) {     // warp-uniform trip count
+        const int i = i0 + g;
+        const int ncl = i < nL ? ccount[i] : 0;
+        if (i < nL && ncl == 0 && q == 0) { mateFlag[i] = 0; if (dumps) b.dump[DUMP_S11].n[i] = 0; }
+        const int maxn = __reduce_max_sync(FULL, ncl);
+        if (maxn == 0) continue;
+        const int st = ncl ? cstart[i] : 0;
+        double lp[7], lm[7];      // left patches: the cells this lane owns, as doubles
+        bool lP = false, lM = false;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) { lp[r] = 0.0; lm[r] = 0.0; }
+        if (ncl) {
+            const float* o = npL + (size_t)i * NPF;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) if (r < 6 || q == 0) { lp[r] = (double)o[q + 8 * r]; lm[r] = (double)o[52 + q + 8 * r]; }
+            const int fl = pfL[i];
+            lP = fl & 1; lM = fl & 2;
+        }
         double bestS = -1.0, bx = 0, by = 0, bt = 0;
         int bestK = -1, nsurv = 0;
-        for (int k = 0; k < ncl; ++k) {
-            const double cx = c_x[st + k], cy = c_y[st + k], ct = c_th[st + k];
-            float vp[2], vm[2];
-            raw_patches(IR, b.pitch, b.W, b.H, cx, cy, ct, p.shift_mag, lane, vp, vm);
-            normalise_patches(vp, vm, lane, PR);
-            const double s = ncc_score(PL, PR);
-            ++n2;
-            if (s > p.ncc_thresh) {
-                if (dumps && lane == 0) dump_put(b.dump[DUMP_S11], st + nsurv, -1, cx, cy, ct, s);
-                ++nsurv;
-                if (s > bestS) { bestS = s; bestK = k; bx = cx; by = cy; bt = ct; }
+        for (int k = 0; k < maxn; ++k) {
+            const bool act = k < ncl;
+            double cx = 0, cy = 0, ct = 0, sn = 0, cs = 1;
+            if (act) { cx = c_x[st + k]; cy = c_y[st + k]; ct = c_th[st + k]; sincos(ct, &sn, &cs); }
+            float vp[7], vm[7];
+            bool rP, rM;
+            raw_patches8(IR, b.pitch, b.W, b.H, cx, cy, sn, cs, p.shift_mag, q, act, vp, vm);
+            normalise_patches8(vp, vm, q, base, rP, rM);
+            double pp = 0, nn = 0, pn = 0, np = 0;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                if (r < 6 || q == 0) {
+                    const double rp = (double)vp[r], rm = (double)vm[r];
+                    pp = fma(lp[r], rp, pp); nn = fma(lm[r], rm, nn); pn = fma(lp[r], rm, pn); np = fma(lm[r], rp, np);
+                }
+            }
+            group8_sum4(pp, nn, pn, np, q, base);
+            const double sc = ncc_max4(pp, nn, pn, np, lP, lM, rP, rM);
+            if (act) {
+                ++n2;
+                if (sc > p.ncc_thresh) {
+                    if (dumps && q == 0) dump_put(b.dump[DUMP_S11], st + nsurv, -1, cx, cy, ct, sc);
+                    ++nsurv;
+                    if (sc > bestS) { bestS = sc; bestK = k; bx = cx; by = cy; bt = ct; }
+                }
             }
         }
         __syncwarp();
-        if (lane == 0) {
+        if (q == 0 && ncl) {
             if (dumps) b.dump[DUMP_S11].n[i] = nsurv;
             if (bestK >= 0) {
                 ebvo_mate m;
@@ -1764,7 +1776,7 @@ __global__ void __launch_bounds__(32 * WPB, 6) ncc2_best_kernel(DevBatch b, DevP
         }
         __syncwarp();
     }
-    if (lane == 0 && n2) atomicAdd(&b.counters[(size_t)f * 8 + 4], n2);
+    if (q == 0 && n2) atomicAdd(&b.counters[(size_t)f * 8 + 4], n2);
 }
 
 // S13: ordered compaction of the per-left-edge staging slots into the mate list (one CTA per frame)
@@ -1831,7 +1843,6 @@ static int g_sms = 0;     // SM count (every GPU of a box is the same model)
 
 void init_match_device()   // per-device function attributes, called by ebvo_create after cudaSetDevice
 {
-    cudaFuncSetAttribute(gn_tile64_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(gn_lerp64_kernel<GNL_PX, GNL_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1890,10 +1901,7 @@ void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t s
     EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 0)));
     if (p.gn_mode == 2) EBVO_KERNEL(prof, "gn32", st, (gn32_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
     else if (p.gn_mode == 1) EBVO_KERNEL(prof, "gn64", st, (gn64_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
-    else if (p.gn_mode == 3) {   // the round-1 tiled kernel (weights form, 4 sample rounds), kept as a cross-check
-        if (!g_sms) warp_grid(1);
-        EBVO_KERNEL(prof, "gn", st, (gn_tile64_kernel<256, 4><<<g_sms * 4, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
-    } else {
+    else {
         if (!g_sms) warp_grid(1);
         EBVO_KERNEL(prof, "gn", st, (gn_lerp64_kernel<GNL_PX, GNL_MINB><<<g_sms * GNL_MINB, 32 * WPB, 0, st>>>(b, p, GN_R, nFrames)));
     }
@@ -1902,8 +1910,9 @@ void match_cluster(const DevBatch& b, const DevParams& p, int nFrames, cudaStrea
 {
     EBVO_KERNEL(prof, "shift", st, (shift_kernel<<<slot_grid(nFrames), 128, 0, st>>>(b, p, 1)));
     constexpr int CL_SMALL = 48;
-    EBVO_KERNEL(prof, "cluster", st, (cluster_kernel<CL_SMALL, 8><<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, 0)));
-    EBVO_KERNEL(prof, "cluster_big", st, (cluster_kernel<MAXC, 4><<<dim3(16, nFrames), 32 * WPB, 0, st>>>(b, p, 1)));
+    EBVO_KERNEL(prof, "cluster8", st, (cluster8_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    EBVO_KERNEL(prof, "cluster", st, (cluster_kernel<CL_SMALL, 8><<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
+    EBVO_KERNEL(prof, "cluster_big", st, (cluster_kernel<MAXC, 4><<<dim3(16, nFrames), 32 * WPB, 0, st>>>(b, p)));
     EBVO_KERNEL(prof, "ncc2_best", st, (ncc2_best_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p)));
 }
 

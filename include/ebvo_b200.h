@@ -63,8 +63,7 @@ typedef struct ebvo_params {
     double toed_mag_thresh;           /* "I_grad_mag <= 2" cpu_toed.cpp:406 */
     int32_t toed_border;              /* 10, cpu_toed.cpp:401-403,553 */
     int32_t gn_mode;                  /* Gauss-Newton kernel: 0 (default) reference arithmetic (FP64), shared-memory tiles;
-                                         1: the same arithmetic, global-memory gathers (cross-check); 2: all FP32 (looser parity);
-                                         3: the earlier tiled kernel (four-weight blend), kept as a cross-check of 0 */
+                                         1: the same arithmetic, global-memory gathers (cross-check); 2: all FP32 (looser parity) */
     int32_t sift_mode;                /* 0 (default): the SIFT gate / BNB-SIFT run only with caller-supplied descriptors ("SIFT-off" otherwise);
                                          1: descriptors computed on the device (cv::SIFT::compute at the reference's keypoints, restated),
                                             S4 and S7' always run (Stereo_Matches.cpp:655-787,1452) */
