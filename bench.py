@@ -4,10 +4,13 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
 One "step" = one pass of the whole hot path (TOED on both views + stereo matching S1..S13, SIFT-off) over
-one batch of B synthetic KITTI-shape stereo pairs per GPU.  `value` is measured with the batch resident in
+one batch of B DISTINCT synthetic KITTI-shape stereo pairs per GPU.  `value` is measured with the batch resident in
 HBM (CUDA events on the library's stream); `e2e` goes through the C-ABI batch call with pinned HOST buffers
 (H2D of the images and D2H of the mates inside the timed region).  Frames are independent, so N GPUs each
-process their own batch (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+process their own batch (weak scaling, no data-path collective); rank 0 prints ONE JSON line.  The same line carries
+`strong_scaling`: BASELINE.json configs[2] as written - ONE 1000-frame batch split over the N ranks
+(sharding.shard_range), host images in, and the final gather of the unpadded mate records to rank 0 (device to device
+over NCCL, then one D2H) INSIDE the timed region.
 
 `--impl reference` times the reference's own CPU implementation on the host cores: the unmodified reference
 TOED compiled in place (oracle/_ref) + the C++ port of the stereo stage (the reference stereo sources need
@@ -29,7 +32,31 @@ sys.path.insert(0, ROOT)
 FP32_LANES_PER_SM = 128
 TOED_FLOP_PER_PX = 1636.0      # 818 MAC per input pixel, separable form
 GN_FLOP_PER_ITER = 5300.0      # 98 samples x 54 FP64 flop per Gauss-Newton iteration
-GN_DRAM_BYTES_PER_FRAME = 82.6e6 / 8   # ncu dram__bytes_{read,write}.sum of one gn launch over 8 frames (profiles/r01_ncu_gn_lerp64.txt)
+GN_NCU_SUMMARY = os.path.join("profiles", "r02_ncu_gn_lerp64.txt")   # ncu --set full capture of the dominant kernel (committed summary)
+FMA_PEAKS = os.path.join("profiles", "r02_fma_peaks.json")           # scripts/ubench/fma_peak.cu on this pool's B200
+
+
+def read_fma_peaks():
+    """Measured DFMA / FFMA throughput (TFLOP/s) from the committed microbenchmark record; None when it is missing."""
+    try:
+        d = json.load(open(os.path.join(ROOT, FMA_PEAKS)))
+        return float(d["fp64_fma_tflops"]), float(d["fp32_fma_tflops"])
+    except Exception:
+        return None, None
+
+
+def read_gn_traffic_per_frame():
+    """DRAM bytes (read + write) per frame of one launch of the Gauss-Newton kernel, parsed from the committed ncu summary;
+    None when the summary is missing (no constant is substituted)."""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, GN_NCU_SUMMARY)).read()
+        frames = int(re.search(r"\((\d+) KITTI-shape frames per launch", txt).group(1))
+        rd = float(re.search(r"dram__bytes_read\.sum\s+([0-9.]+) Mbyte", txt).group(1))
+        wr = float(re.search(r"dram__bytes_write\.sum\s+([0-9.]+) Mbyte", txt).group(1))
+        return (rd + wr) * 1e6 / frames
+    except Exception:
+        return None
 
 
 def read_peaks():
@@ -40,6 +67,39 @@ def read_peaks():
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def _gen_pair(a):
+    """(workload, seed, density) -> cached synthetic stereo pair (uint8 L, R); generated once per box into /tmp."""
+    workload, seed, density = a
+    from edge_based_visual_odometry_b200 import synth
+    cal = {"kitti": synth.kitti_calib, "euroc": synth.CALIBS["euroc"], "4k": synth.kitti4k_calib}[workload]()
+    d = os.path.join("/tmp", "ebvo_synth_cache")
+    os.makedirs(d, exist_ok=True)
+    f = os.path.join(d, f"{workload}_{cal.width}x{cal.height}_s{seed}_d{density:g}.npz")
+    if os.path.exists(f):
+        try:
+            z = np.load(f)
+            return z["L"], z["R"]
+        except Exception:
+            pass
+    L, R = synth.stereo_pair(cal, seed, density=density)
+    tmp = f + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, L=L, R=R)
+    os.replace(tmp, f)
+    return L, R
+
+
+def synth_frames(workload, seeds, density, world):
+    """Distinct synthetic frames (seed = frame id), generated in parallel on the host cores this rank may use and cached in /tmp."""
+    jobs = [(workload, int(sd), float(density)) for sd in seeds]
+    workers = max(1, min(len(jobs), (os.cpu_count() or 4) // max(1, world)))
+    if workers == 1 or len(jobs) < 4:
+        return [_gen_pair(j) for j in jobs]
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    with cf.ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+        return list(ex.map(_gen_pair, jobs, chunksize=max(1, len(jobs) // (4 * workers))))
 
 
 class ClockSampler(threading.Thread):
@@ -149,13 +209,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="stereo frames per GPU per step (default 160; 4 for the 4K workload)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic frames generated (cycled to fill the batch)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic frames per GPU (default: the batch size, i.e. every frame of the "
+                    "batch is its own scene; smaller values are cycled to fill the batch)")
+    ap.add_argument("--strong-frames", type=int, default=1000, help="frames of the ONE batch that the strong-scaling leg splits over the ranks (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="kitti", choices=["kitti", "euroc", "4k"],
                     help="kitti = the BASELINE.json metric (default); euroc / 4k = BASELINE configs[1] / configs[4] shapes (extra measurements)")
     ap.add_argument("--density", type=float, default=1.0, help="synthetic scene density (objects per area), the 4K stress sweep varies it")
     ap.add_argument("--sift", action="store_true", help="SIFT-on: descriptors, SIFT gate and BNB-SIFT on the device (sift_mode 1)")
-    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32, 3 the round-1 tiled kernel")
+    ap.add_argument("--gn-mode", type=int, default=0, help="Gauss-Newton kernel: 0 FP64 tiled (default), 1 FP64 gather, 2 FP32")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -197,9 +259,11 @@ def main():
     max_edges = (1 << 21) if big else 65536
     CAP = (1 << 20) if big else 49152   # mates per frame returned to the host
     # distinct frames per rank (different seeds per rank), cycled to fill the batch
+    if not args.distinct:
+        args.distinct = B
     if args.workload == "4k":
         args.distinct = min(args.distinct, 2)
-    base = [synth.stereo_pair(cal, rank * 1000 + f, density=args.density) for f in range(min(args.distinct, B))]
+    base = synth_frames(args.workload, [rank * 1000 + f for f in range(min(args.distinct, B))], args.density, world)
     # pinned host staging for the e2e path
     hL = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
     hR = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
@@ -274,10 +338,57 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---------------- strong scaling: ONE batch of --strong-frames frames split over the ranks, final gather timed ----------------
+    strong = None
+    if args.strong_frames > 0 and args.workload == "kitti" and not args.sift:
+        from edge_based_visual_odometry_b200 import sharding
+        FS = args.strong_frames
+        lo, hi = sharding.shard_range(FS, world, rank)
+        nloc = hi - lo
+        dev = torch.device("cuda", local_rank)
+        per_frame = float(nM.mean()) * 1.25 + 1024
+        cap_rec = int(max(nloc, 1) * per_frame)
+        packed = torch.empty((cap_rec, 64), dtype=torch.uint8, device=dev)
+        offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        h_res = torch.empty((int(FS * per_frame), 64), dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def strong_pass():
+            pos, counts = 0, []
+            for s0 in range(0, nloc, B):          # this rank's block, in sub-batches of the context's capacity
+                n = min(B, nloc - s0)
+                nm = ctx.stereo_batch_device(calib, nL_imgs[:n], nR_imgs[:n])
+                pos += ctx.batch_pack(packed[pos:].data_ptr(), cap_rec - pos, offs.data_ptr())
+                counts.append(torch.from_numpy(nm.copy()))
+            ct = (torch.cat(counts) if counts else torch.zeros(0, dtype=torch.int32)).to(dev)
+            torch.cuda.synchronize()
+            tg = time.perf_counter()
+            if world > 1:
+                allp, allc = sharding.gather_packed(packed[:pos], ct, FS, dist)
+            else:
+                allp, allc = packed[:pos], ct
+            nrec = 0
+            if rank == 0:
+                nrec = int(allp.shape[0])
+                h_res[:nrec].copy_(allp, non_blocking=True)
+                allc.cpu()
+            torch.cuda.synchronize()
+            return time.perf_counter() - tg, nrec
+
+        strong_pass()                              # untimed: NCCL point-to-point connections, allocator
+        barrier()
+        t0 = time.perf_counter()
+        reps, g_s, nrec = 2, 0.0, 0
+        for _ in range(reps):
+            gs, nrec = strong_pass()
+            g_s += gs
+        barrier()
+        strong = [(time.perf_counter() - t0) / reps, g_s / reps, nrec]
+        del packed, h_res
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, (strong[0] if strong else 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = t.tolist()
+    ms_total, e2e_ms, strong_ms = t.tolist()
     sampler.join(timeout=2)
 
     if rank == 0:
@@ -296,8 +407,14 @@ def main():
         dom = max(ktimes.items(), key=lambda kv: kv[1][0])
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        fp32_peak = sms * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12      # TFLOP/s, nominal FP32 FMA peak at max clock
-        fp64_peak = fp32_peak / 2                                          # 64 FP64 lanes per SM per clock (measured: ncu pipe_fp64)
+        fp32_nom = sms * FP32_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12       # TFLOP/s, nominal FP32 FMA peak at max clock
+        m64, m32 = read_fma_peaks()                                        # measured on this pool (scripts/ubench/fma_peak.cu)
+        fp32_peak = m32 if m32 else fp32_nom
+        fp64_peak = m64 if m64 else fp32_nom / 2                           # nominal: 64 FP64 lanes per SM per clock
+        fma_src = (f"MEASURED FMA throughput, {FMA_PEAKS} (scripts/ubench/fma_peak.cu: DFMA {m64} / FFMA {m32} TFLOP/s; nominal "
+                   f"{fp32_nom / 2:.1f} / {fp32_nom:.1f} at {sm_max:.0f} MHz)") if m64 and m32 else \
+                  f"nominal FMA peak = {sms} SM x 64 (FP64) / 128 (FP32) lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock); {FMA_PEAKS} missing"
+        gn_traffic = read_gn_traffic_per_frame()
         c = counters.sum(axis=0)
         toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_orient", (0, 1))[0]
         toed_flops = TOED_FLOP_PER_PX * W * H * 2 * B * args.steps
@@ -319,14 +436,14 @@ def main():
         peak = gn_peak if dom_is_gn else fp32_peak
         roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": ("fp64" if gn_peak == fp64_peak else "fp32") if dom_is_gn else "fp32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
-                # DRAM bytes of one launch of the dominant kernel: ncu --set full capture profiles/r01_ncu_gn_lerp64.txt
-                # (dram__bytes_read.sum + dram__bytes_write.sum = 78.9 MB for 8 frames), scaled to this batch
-                "traffic": GN_DRAM_BYTES_PER_FRAME * B if dom_is_gn else None,
+                # DRAM bytes of one launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu
+                # --set full capture (parsed from its summary, per frame), scaled to this batch; null when no summary is present
+                "traffic": gn_traffic * B if (dom_is_gn and gn_traffic and gn_name == "gn") else None,
+                "traffic_source": GN_NCU_SUMMARY if (dom_is_gn and gn_traffic and gn_name == "gn") else None,
                 "algorithmic_flop_per_launch": gn_flops / args.steps if dom_is_gn else toed_flops / args.steps,
                 "avg_launch_ms": (gn_ms if dom_is_gn else toed_ms) / args.steps,
-                "peak_source": f"nominal {'FP64' if peak == fp64_peak else 'FP32'} FMA peak = {sms} SM x {64 if peak == fp64_peak else 128} lanes x 2 x sm_max_mhz "
-                               f"({peak_src} MEASURED_PEAKS.json clock); neither HBM nor tensor bound: no dense contraction on this path (tensor cores "
-                               "unused) and the kernel's DRAM traffic is 0.1 % of HBM peak",
+                "peak_source": fma_src + "; neither HBM nor tensor bound: no dense contraction on this path (tensor cores unused) and the "
+                               "kernel's DRAM traffic is 0.2 % of HBM peak",
                 "dominant_kernel_by_time": dom[0], "dominant_kernel_share": dom[1][0] / ksum if ksum else None,
                 "per_stage": {"toed": {"bound": "fp32", "algorithmic_flop_per_px": TOED_FLOP_PER_PX, "achieved_tflops": tf(toed_flops, toed_ms),
                                        "frac": (tf(toed_flops, toed_ms) or 0) / fp32_peak},
@@ -342,7 +459,7 @@ def main():
         line = {"metric": "stereo frames/s (TOED+NCC stereo match) at " + shape, "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TOED) / f64 (matching)", "data": "synthetic",
-                "config": {"workload": cfgname + ", TOED x2 + stereo match S1-S13 (" + ("SIFT-on, device descriptors" if args.sift else "SIFT-off") + ")",
+                "config": {"workload": cfgname + ", TOED x2 + stereo match S1-S13 (" + ("SIFT-on, device descriptors" if args.sift else "SIFT-off: the S4 / S7' SIFT stages need cv::SIFT, which is not part of the reference tree; --sift runs them on device descriptors") + ")",
                            "frames_per_gpu_per_step": B, "distinct_frames": len(base), "l2": "batch inputs (%.0f MB u8 images + per-frame "
                            "intermediates) exceed the 126 MB L2" % (2 * B * W * H / 1e6),
                            "edges_per_image": float(nL.mean()), "mates_per_frame": float(nM.mean())},
@@ -362,6 +479,17 @@ def main():
                                     "sample": "2 frames of the same workload: reference TOED (oracle/_ref, OpenMP all cores) %.2f s + reference "
                                               "stereo sources compiled in place (oracle/_ref, shimmed OpenCV/Eigen) %.2f s per frame; the leaner "
                                               "C++ port of the stereo stage takes %.2f s" % ((ttoed + ttoed2) / 2, (tst + tst2) / 2, tport)}
+        if strong:
+            FS = args.strong_frames
+            line["strong_scaling"] = {
+                "workload": "configs[2]: ONE %d-frame KITTI-shape batch split into contiguous blocks of ceil(F/N) frames per rank "
+                            "(sharding.shard_range; %d distinct scenes per rank cycled), host images in (ebvo_stereo_batch, pipelined H2D), results packed "
+                            "on the device (ebvo_batch_pack), gathered to rank 0 at their exact size (counts all_gather + NCCL send/recv, "
+                            "sharding.gather_packed) and copied to pinned host memory - all inside the timed region" % (FS, len(base)),
+                "frames": FS, "n_gpus": world, "frames_per_gpu": -(-FS // world), "value": FS / (strong_ms / 1e3), "unit": "frames/s",
+                "ms": strong_ms, "gather_ms_rank0": strong[1] * 1e3, "gather_share": strong[1] * 1e3 / strong_ms if strong_ms else None,
+                "mate_records_gathered": strong[2], "bytes_gathered": strong[2] * 64,
+                "timing": "host clock between barrier + cudaDeviceSynchronize on both sides, max over ranks, mean of 2 passes after one untimed pass"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -18,7 +18,7 @@ STAGES = ["epi", "disp", "orient", "sift", "ncc", "bnb_ncc", "bnb_sift", "shift"
 EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
     "ebvo_stereo_match", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
-    "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
+    "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_batch_pack", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
     "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_launch_count", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
     "ebvo_temporal_quads", "ebvo_temporal_quads_stage", "ebvo_temporal_counters",
@@ -248,6 +248,23 @@ class Context:
         self._ck(self.L.ebvo_stereo_batch(self.h, C.byref(calib), F, self._ptr_array(L_imgs), self._ptr_array(R_imgs), w, h,
                                           L_imgs[0].strides[0], _p(out), cap, _p(n_mates)))
         return out, n_mates
+
+    def stereo_batch_device(self, calib, L_imgs, R_imgs, n_mates=None):
+        """ebvo_stereo_batch with out = NULL: host images in (pipelined H2D), results stay on the device for batch_pack()."""
+        F = len(L_imgs)
+        h, w = L_imgs[0].shape
+        if n_mates is None:
+            n_mates = np.zeros(F, np.int32)
+        self._ck(self.L.ebvo_stereo_batch(self.h, C.byref(calib), F, self._ptr_array(L_imgs), self._ptr_array(R_imgs), w, h,
+                                          L_imgs[0].strides[0], None, 0x7fffffff, _p(n_mates)))
+        self._nframes = F
+        return n_mates
+
+    def batch_pack(self, dst_ptr: int, cap_records: int, offsets_ptr: int) -> int:
+        """Pack the last batch's mates (device-resident) back to back into a caller-owned DEVICE buffer; returns the record count."""
+        tot = C.c_longlong()
+        self._ck(self.L.ebvo_batch_pack(self.h, C.c_void_p(dst_ptr), C.c_longlong(cap_records), C.c_void_p(offsets_ptr), C.byref(tot)))
+        return tot.value
 
     def batch_upload(self, L_imgs, R_imgs):
         h, w = L_imgs[0].shape

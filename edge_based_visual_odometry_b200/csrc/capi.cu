@@ -658,6 +658,21 @@ int ebvo_batch_download(ebvo_ctx* ctx, ebvo_mate* out, int cap, int* n_mates)
     return download_mates(ctx, ctx->curFrames, out, cap, n_mates);
 }
 
+int ebvo_batch_pack(ebvo_ctx* ctx, void* d_dst, long long cap_records, int* d_offsets, long long* total)
+{
+    if (!ctx || !d_dst || !d_offsets || ctx->curFrames < 1) return EBVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int F = ctx->curFrames;
+    launch_pack(ctx->d_out, ctx->b.E, ctx->b.nMates, F, (ebvo_mate*)d_dst, cap_records, d_offsets, ctx->st, &ctx->prof);
+    CK(cudaGetLastError());
+    int tot = 0;
+    CK(cudaMemcpyAsync(&tot, d_offsets + F, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (total) *total = tot;
+    if (tot > cap_records) { ctx->err = "packed mate buffer too small"; return EBVO_ERR_CAPACITY; }
+    return EBVO_OK;
+}
+
 int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* stage_counts)
 {
     if (!ctx) return EBVO_ERR_INVALID;

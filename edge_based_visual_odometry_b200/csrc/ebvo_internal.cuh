@@ -102,6 +102,7 @@ void launch_gate_fill(const DevBatch& b, const DevParams& p, const double* F21, 
 // src < 0: live pool (counts = ccount); else dump[src]
 void launch_snapshot(const DevBatch& b, int src, const int* d_offsets, int* ridx, double* x, double* y, double* th, double* score, cudaStream_t st);
 void launch_compact(const DevBatch& b, int nFrames, ebvo_mate* d_out, int stride, cudaStream_t st, struct Prof* prof);
+void launch_pack(const ebvo_mate* src, int srcStride, const int* nMates, int nFrames, ebvo_mate* dst, long long cap, int* offsets, cudaStream_t st, struct Prof* prof);
 // individual matching stages (used by the stage-dump path, which snapshots between them)
 void match_prologue(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, struct Prof* prof);
 void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);

@@ -1932,6 +1932,35 @@ void launch_compact(const DevBatch& b, int nFrames, ebvo_mate* d_out, int stride
     EBVO_KERNEL(prof, "compact", st, (compact_kernel<<<nFrames, 1024, 0, st>>>(b, d_out, stride)));
 }
 
+// Unpadded result of a batch: the mates of frames 0 .. nFrames-1 back to back in `dst` (64-byte records), offsets[f] = first
+// record of frame f, offsets[nFrames] = total.  One CTA per frame; every CTA sums the counts before its own frame (<= a few
+// hundred ints).  This is what travels in the final gather of a sharded batch (sharding.gather_packed).
+__global__ void __launch_bounds__(256) pack_kernel(const ebvo_mate* src, int srcStride, const int* nMates, int nFrames, ebvo_mate* dst,
+                                                    long long cap, int* offsets)
+{
+    __shared__ int s_off;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid < 32) {
+        int acc = 0;
+        for (int g = tid; g < f; g += 32) acc += nMates[g];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (tid == 0) s_off = acc;
+    }
+    __syncthreads();
+    const int off = s_off, n = nMates[f];
+    if (tid == 0) { offsets[f] = off; if (f == nFrames - 1) offsets[nFrames] = off + n; }
+    const uint4* r = reinterpret_cast<const uint4*>(src + (size_t)f * srcStride);
+    uint4* o = reinterpret_cast<uint4*>(dst + off);
+    const long long room = cap - off;                          // records that still fit
+    const int m = (int)max(0ll, min((long long)n, room));
+    for (int k = tid; k < 4 * m; k += 256) o[k] = r[k];
+}
+void launch_pack(const ebvo_mate* src, int srcStride, const int* nMates, int nFrames, ebvo_mate* dst, long long cap, int* offsets, cudaStream_t st, Prof* prof)
+{
+    if (nFrames > 0) EBVO_KERNEL(prof, "pack", st, (pack_kernel<<<nFrames, 256, 0, st>>>(src, srcStride, nMates, nFrames, dst, cap, offsets)));
+}
+
 void launch_gate_count(const DevBatch& b, const DevParams& p, const double* F21, int mode, int* d_counts, cudaStream_t st)
 {
     const double* dF = upload_F(b, F21, st);

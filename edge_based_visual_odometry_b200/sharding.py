@@ -2,8 +2,10 @@
 
 Frames are independent for detection and stereo matching (reference src/Pipeline.cpp:64-145 reads nothing from
 previous frames), so a batch of F frames is split into contiguous blocks, one per rank, and there is NO
-collective on the data path.  The only exchange is the final result gather, done here with torch.distributed
-(NCCL on GPUs, gloo in the CPU tests): per-frame mate counts first, then the padded mate records.
+collective on the data path.  The only exchange is the final result gather - what the reference's frame loop
+(cmd/main_VO.cpp:99-113) accumulates on one host - done here with torch.distributed (NCCL on GPUs, gloo in the CPU
+tests): the per-frame mate counts first (one small all_gather), then every rank's mate records at their exact size
+(point-to-point sends into the destination's buffer: no padding, no host bounce when the tensors are on the device).
 """
 from __future__ import annotations
 
@@ -18,34 +20,62 @@ def shard_range(n_frames: int, world: int, rank: int):
     return lo, hi
 
 
-def gather_mates(local_mates, local_counts, n_frames: int, dist=None, device=None):
-    """Gather per-frame results to rank 0, indexed by global frame id.
+def gather_packed(packed, counts, n_frames: int, dist, dst: int = 0):
+    """Final gather of a sharded batch.
 
-    local_mates: [f_local, cap] structured array (MATE_DTYPE, 64 B records); local_counts: [f_local] int32.
-    Returns (mates[n_frames, cap], counts[n_frames]) on rank 0 and (None, None) elsewhere.
+    packed: torch uint8 tensor [n_local, 64], this rank's mate records back to back in frame order (ebvo_batch_pack output,
+    on the device under NCCL; CPU tensors under gloo); counts: torch int32 tensor [f_local] on the same device.
+    Returns (packed_all [n_total, 64], counts_all [n_frames]) in global frame order on rank `dst`, (None, None) elsewhere.
     """
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = (n_frames + world - 1) // world
+    dev = packed.device
+    pad = torch.zeros(per, dtype=torch.int32, device=dev)
+    pad[:counts.numel()] = counts
+    allc = torch.empty(world * per, dtype=torch.int32, device=dev)
+    dist.all_gather(list(allc.view(world, per).unbind(0)), pad)
+    per_rank = allc.view(world, per).sum(dim=1).cpu().tolist()      # records held by every rank (the one host read of the exchange)
+    if rank != dst:
+        if per_rank[rank]:
+            dist.send(packed[:per_rank[rank]].contiguous(), dst=dst)
+        return None, None
+    out = torch.empty((sum(per_rank), 64), dtype=torch.uint8, device=dev)
+    pos = 0
+    for r in range(world):
+        n = per_rank[r]
+        if n:
+            if r == rank:
+                out[pos:pos + n].copy_(packed[:n])
+            else:
+                dist.recv(out[pos:pos + n], src=r)
+        pos += n
+    return out, allc[:n_frames]
+
+
+def gather_mates(local_mates, local_counts, n_frames: int, dist=None, device=None):
+    """Padded convenience form for host arrays: local_mates [f_local, cap] (MATE_DTYPE), local_counts [f_local] int32.
+    Returns (mates[n_frames, cap], counts[n_frames]) on rank 0 and (None, None) elsewhere; the exchange itself is
+    gather_packed (exact sizes)."""
     import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return local_mates, local_counts
-    world, rank = dist.get_world_size(), dist.get_rank()
     cap = local_mates.shape[1]
-    per = (n_frames + world - 1) // world
-    pad_m = np.zeros((per, cap, 64), np.uint8)
-    pad_c = np.zeros(per, np.int32)
     nloc = len(local_counts)
-    if nloc:
-        pad_m[:nloc] = local_mates.view(np.uint8).reshape(nloc, cap, 64)
-        pad_c[:nloc] = local_counts
-    tm = torch.from_numpy(pad_m)
-    tc = torch.from_numpy(pad_c)
+    rows = [local_mates[k, :local_counts[k]] for k in range(nloc)]
+    flat = np.concatenate(rows) if rows else np.zeros(0, local_mates.dtype)
+    tp = torch.from_numpy(np.ascontiguousarray(flat).view(np.uint8).reshape(-1, 64).copy())
+    tc = torch.from_numpy(np.asarray(local_counts, np.int32).copy())
     if device is not None:
-        tm, tc = tm.to(device), tc.to(device)
-    gm = [torch.empty_like(tm) for _ in range(world)] if rank == 0 else None
-    gc = [torch.empty_like(tc) for _ in range(world)] if rank == 0 else None
-    dist.gather(tm, gm, dst=0)
-    dist.gather(tc, gc, dst=0)
-    if rank != 0:
+        tp, tc = tp.to(device), tc.to(device)
+    allp, allc = gather_packed(tp, tc, n_frames, dist)
+    if allp is None:
         return None, None
-    allm = torch.stack(gm).cpu().numpy().reshape(world * per, cap, 64)[:n_frames]
-    allc = torch.stack(gc).cpu().numpy().reshape(world * per)[:n_frames]
-    return np.ascontiguousarray(allm).view(local_mates.dtype).reshape(n_frames, cap), allc
+    allc = allc.cpu().numpy()
+    rec = allp.cpu().numpy().reshape(-1).view(local_mates.dtype)
+    out = np.zeros((n_frames, cap), local_mates.dtype)
+    pos = 0
+    for f in range(n_frames):
+        out[f, :allc[f]] = rec[pos:pos + allc[f]]
+        pos += allc[f]
+    return out, allc

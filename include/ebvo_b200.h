@@ -216,6 +216,12 @@ int ebvo_batch_run(ebvo_ctx* ctx, const ebvo_calib* calib, int do_match); /* asy
 int ebvo_batch_sync(ebvo_ctx* ctx);
 int ebvo_batch_download(ebvo_ctx* ctx, ebvo_mate* out, int cap, int* n_mates);
 int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* stage_counts /* n_frames*8 or NULL */);
+/* The results of the last batch (ebvo_batch_run, or ebvo_stereo_batch called with out = NULL), still on the device, packed
+ * back to back without padding into the caller's DEVICE buffer d_dst (cap_records ebvo_mate records); d_offsets (device,
+ * n_frames + 1 ints) receives the first record of every frame and the total.  This is the payload of the one exchange a
+ * sharded batch has - the final gather of the per-frame results that the reference's frame loop accumulates on one host
+ * (cmd/main_VO.cpp:99-113 -> Pipeline::ProcessStereoFrame) - so that it can go GPU to GPU (NCCL) at its real size. */
+int ebvo_batch_pack(ebvo_ctx* ctx, void* d_dst, long long cap_records, int* d_offsets, long long* total);
 
 /* Utility::get_edge_patches (src/utility.cpp:182-212): 7x7 "+" and "-" patches of n edges of one image. */
 int ebvo_edge_patches(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n,

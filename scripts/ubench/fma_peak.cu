@@ -21,23 +21,23 @@ __global__ void __launch_bounds__(128) tput(double* out, double seed, int n)
     for (int i = 0; i < n; ++i) {
         if (OP == 0) {
 #define X(k) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d##k) : "d"(db), "d"(dc));
-            REP8(X) REP8(X)
+            REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X)
 #undef X
         } else if (OP == 1) {
 #define X(k) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d##k) : "d"(dc));
-            REP8(X) REP8(X)
+            REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X)
 #undef X
         } else if (OP == 2) {
 #define X(k) asm volatile("add.rm.f64 %0, %0, %1;" : "+d"(d##k) : "d"(dc));
-            REP8(X) REP8(X)
+            REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X)
 #undef X
         } else if (OP == 3) {
 #define X(k) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d##k) : "d"(db));
-            REP8(X) REP8(X)
+            REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X)
 #undef X
         } else if (OP == 4) {
 #define X(k) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f##k) : "f"(fb), "f"(fc));
-            REP8(X) REP8(X)
+            REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X) REP8(X)
 #undef X
         } else if (OP == 5) {          // F2F.F64.F16 (independent: the source is an integer register that a cheap IADD advances)
 #define X(k) { double t; asm volatile("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f64.f16 %0, lo; }" : "=d"(t) : "r"(u##k)); d##k += 0; u##k ^= __double2hiint(t) & 1; }
@@ -102,21 +102,21 @@ int main()
     double* out; cudaMalloc(&out, sizeof(double) * sms * cps * 128);
     const char* names[13] = {"dfma", "dadd", "dadd_rm", "dmul", "ffma", "f2f_f64_f16", "f2f_f32_f64_roundtrip", "mufu_rcp64h", "shfl_bfly_b32", "hadd2",
                              "mix_16dfma_5f2f", "mix_16dfma_16alu", "alu_xor"};
-    const double per_iter[13] = {16, 16, 16, 16, 16, 16, 32, 16, 16, 16, 21, 32, 16};
+    const double per_iter[13] = {64, 64, 64, 64, 64, 16, 32, 16, 16, 16, 21, 32, 16};
     double ms[13];
     ms[0] = run<0>(out, sms, n, cps); ms[1] = run<1>(out, sms, n, cps); ms[2] = run<2>(out, sms, n, cps); ms[3] = run<3>(out, sms, n, cps);
     ms[4] = run<4>(out, sms, n, cps); ms[5] = run<5>(out, sms, n, cps); ms[6] = run<6>(out, sms, n, cps); ms[7] = run<7>(out, sms, n, cps);
     ms[8] = run<8>(out, sms, n, cps); ms[9] = run<9>(out, sms, n, cps); ms[10] = run<10>(out, sms, n, cps); ms[11] = run<11>(out, sms, n, cps);
     ms[12] = run<12>(out, sms, n, cps);
     const double warps = (double)sms * cps * 4;
-    printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_attr_mhz\": %.0f, \"warps_per_sm\": %d, \"ilp\": 8,\n \"how\": \"scripts/ubench/fma_peak.cu: n=%d loop iterations of 16 (or the stated mix of) independent inline-PTX instructions per thread, CUDA events, second launch timed\",\n \"ops\": {\n",
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_attr_mhz\": %.0f, \"warps_per_sm\": %d, \"ilp\": 8,\n \"how\": \"scripts/ubench/fma_peak.cu: n=%d loop iterations of 64 (FP64 / FP32 arithmetic), 16 (the others) or the stated mix of independent inline-PTX instructions per thread, CUDA events, second launch timed\",\n \"ops\": {\n",
            pr.name, sms, clk_khz / 1e3, cps * 4, n);
     for (int k = 0; k < 13; ++k) {
         const double winst = warps * n * per_iter[k];                 // warp instructions of the named kind(s)
         const double per_sm_clk = winst / (ms[k] * 1e-3) / sms / (clk_khz * 1e3);   // warp instructions per SM per clock (at the attribute clock)
         printf("  \"%s\": {\"ms\": %.3f, \"warp_inst_per_sm_per_clk\": %.3f, \"lane_ops_per_sm_per_clk\": %.1f}%s\n", names[k], ms[k], per_sm_clk, per_sm_clk * 32, k < 12 ? "," : "");
     }
-    const double dfma_tf = warps * n * 16 * 32 * 2 / (ms[0] * 1e-3) / 1e12, ffma_tf = warps * n * 16 * 32 * 2 / (ms[4] * 1e-3) / 1e12;
+    const double dfma_tf = warps * n * 64 * 32 * 2 / (ms[0] * 1e-3) / 1e12, ffma_tf = warps * n * 64 * 32 * 2 / (ms[4] * 1e-3) / 1e12;
     printf(" },\n \"fp64_fma_tflops\": %.2f, \"fp32_fma_tflops\": %.2f\n}\n", dfma_tf, ffma_tf);
     return 0;
 }
