@@ -416,7 +416,7 @@ def main():
                   f"nominal FMA peak = {sms} SM x 64 (FP64) / 128 (FP32) lanes x 2 x sm_max_mhz ({peak_src} MEASURED_PEAKS.json clock); {FMA_PEAKS} missing"
         gn_traffic = read_gn_traffic_per_frame()
         c = counters.sum(axis=0)
-        toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_orient", (0, 1))[0]
+        toed_ms = ktimes.get("toed_grad_nms", (0, 1))[0] + ktimes.get("toed_refine", ktimes.get("toed_orient", (0, 1)))[0]
         toed_flops = TOED_FLOP_PER_PX * W * H * 2 * B * args.steps
         gn_name = next((k for k in ("gn", "gn64", "gn32") if k in ktimes), None)
         gn_ms = ktimes[gn_name][0] if gn_name else 0.0
@@ -434,7 +434,7 @@ def main():
         dom_is_gn = dom[0] == gn_name
         ach = tf(gn_flops, gn_ms) if dom_is_gn else tf(toed_flops, toed_ms)
         peak = gn_peak if dom_is_gn else fp32_peak
-        roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_orient", "bound": ("fp64" if gn_peak == fp64_peak else "fp32") if dom_is_gn else "fp32",
+        roof = {"kernel": dom[0] if dom_is_gn else "toed_grad_nms+toed_refine", "bound": ("fp64" if gn_peak == fp64_peak else "fp32") if dom_is_gn else "fp32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
                 # DRAM bytes of one launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu
                 # --set full capture (parsed from its summary, per frame), scaled to this batch; null when no summary is present

@@ -364,18 +364,16 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     const int tilesX = (max_w + TW - 1) / TW, tilesY = (max_h + TH - 1) / TH;
     b.imgStride = align_up((size_t)align_up(max_w, 16) * max_h, 256);
     b.maskStride = (size_t)(2 * tilesX) * (2 * TH * tilesY);
-    b.spStride = (size_t)(2 * max_w) * (2 * max_h);
     b.rowStride = align_up((size_t)2 * max_h + 2, 32);
     b.gStride = align_up((size_t)max_w * max_h, 64);
     CK(dalloc(ctx, &ctx->d_raw, b.imgStride * nImg));
     CK(dalloc(ctx, &ctx->d_und, b.imgStride * 2));
     CK(dalloc(ctx, &b.mask, b.maskStride * nImg));
-    CK(dalloc(ctx, &b.sp, b.spStride * nImg));
     CK(dalloc(ctx, &b.rowcnt, b.rowStride * nImg));
     CK(dalloc(ctx, &b.rowoff, b.rowStride * nImg));
     CK(dalloc(ctx, &b.coords, (size_t)b.E * nImg));
     CK(dalloc(ctx, &b.ex, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.ey, (size_t)b.E * nImg)); CK(dalloc(ctx, &b.eth, (size_t)b.E * nImg));
-    CK(dalloc(ctx, &b.nE, (size_t)nImg)); CK(dalloc(ctx, &b.nTot, (size_t)nImg));
+    CK(dalloc(ctx, &b.nE, (size_t)nImg)); CK(dalloc(ctx, &b.nTot, (size_t)nImg)); CK(dalloc(ctx, &b.nRej, (size_t)nImg));
     if (ctx->params.gn_mode == 2) CK(dalloc(ctx, &b.pk, b.gStride * B));
     else if (ctx->params.gn_mode == 1) CK(dalloc(ctx, &b.pk16, b.gStride * B));
     else CK(dalloc(ctx, &b.pkh, b.gStride * B));
@@ -560,8 +558,8 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     v.nFrames = n; v.nImages = 2 * n;
     v.imgBase = b.imgBase + 2 * f0;
     v.raw += i0 * b.imgStride; v.und += i0 * b.imgStride;
-    v.mask += i0 * b.maskStride; v.sp += i0 * b.spStride; v.rowcnt += i0 * b.rowStride; v.rowoff += i0 * b.rowStride;
-    v.coords += i0 * E; v.ex += i0 * E; v.ey += i0 * E; v.eth += i0 * E; v.nE += i0; v.nTot += i0;
+    v.mask += i0 * b.maskStride; v.rowcnt += i0 * b.rowStride; v.rowoff += i0 * b.rowStride;
+    v.coords += i0 * E; v.ex += i0 * E; v.ey += i0 * E; v.eth += i0 * E; v.nE += i0; v.nTot += i0; v.nRej += i0;
     if (v.pkh) v.pkh += F0 * b.gStride;
     if (v.pk16) v.pk16 += F0 * b.gStride;
     if (v.pk) v.pk += F0 * b.gStride;

@@ -42,11 +42,11 @@ struct DevBatch {
     const void* tmap;      // host pointer to the 128-byte CUtensorMap of the image array (toed.cu)
     const uint8_t* raw; const uint8_t* und; size_t imgStride;
     uint32_t* mask; size_t maskStride;
-    float2* sp; size_t spStride;          // sub-pixel offsets (s*nx, s*ny) at edge samples
     int* rowcnt; int* rowoff; size_t rowStride;
     uint32_t* coords;                     // [img][E] packed (i<<16 | j)
     double *ex, *ey, *eth;                // [img][E]
     int *nE, *nTot;                       // [img]
+    int* nRej;                            // [img] prefilter survivors the FP64 tests of toed_refine rejected
     // right-view image packed with its Sobel/8 gradients, one of (per ebvo_params.gn_mode), [frame][H*W]:
     uint2* pkh;    // {u16 I, half gx, half gy, 0}   default mixed-precision GN kernel
     uint2* pk16;   // {I, 8gx, 8gy} as int16           FP64 GN kernel

@@ -1,8 +1,8 @@
 // Third-order edge detection on sm_100a.
 //
 // Replaces ThirdOrderEdgeDetectionCPU::{preprocessing, convolve_img, non_maximum_suppresion}
-// (reference src/toed/cpu_toed.cpp:82-120, 122-376, 386-582).  FP32 arithmetic; final coordinates are
-// assembled in FP64 so that the edge list handed to the matcher keeps sub-1e-4 px resolution.
+// (reference src/toed/cpu_toed.cpp:82-120, 122-376, 386-582).  The dense pass (which samples are edges) is FP32; the
+// values that reach the edge list (sub-pixel position, orientation) are re-evaluated in FP64 for the survivors.
 //
 // Work-efficient split (same results as the reference's dense evaluation):
 //   K_A  toed_grad_nms   dense, tile-fused: uint8 tile + halo -> separable G/Gx row pass (3 tap variants) ->
@@ -11,21 +11,26 @@
 //                         sub-pixel offsets).  No interp-grid map is ever written to HBM.
 //   K_B  toed_scan/expand row counts -> exclusive scan -> ordered (i,j) list.  Order = row-major interp order,
 //                         exactly the serial scan of cpu_toed.cpp:530-575, so edge indices match the reference.
-//   K_C  toed_orient      sparse: the seven remaining third-order responses + orientation (cpu_toed.cpp:224-229)
-//                         are evaluated only at the surviving edge samples (about 2% of the interp grid).
+//   K_C  toed_refine      sparse, FP64: gradient at the 3 x 3 samples around every surviving edge sample, sub-pixel fit,
+//                         the seven remaining third-order responses and the orientation (cpu_toed.cpp:224-229, 418-510)
+//                         are re-evaluated in double only where they reach the edge list (about 2% of the interp grid).
 #include "ebvo_internal.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cuda.h>
+#include <math_constants.h>
 
 namespace ebvo {
 
 // [variant][filter][tap]; variant 0 = unshifted, middle 17 taps (ends zero); 1 = unshifted 19; 2 = shifted 19
 // filter 0..3 = G, Gx, Gxx, Gxxx (closed forms quoted at cpu_toed.cpp:137-140,151-154; sigma = 2)
 __constant__ float c_T[3][4][19];
+__constant__ double c_T64[3][4][19];     // the same tables in double (FP64 refinement of the surviving samples)
 
 void upload_toed_tables()
 {
     float T[3][4][19];
+    double T64[3][4][19];
     const double sig = 2.0, s2 = sig * sig, c = std::sqrt(2.0 * 3.14159265358979323846);
     for (int v = 0; v < 3; ++v)
         for (int p = -9; p <= 9; ++p) {
@@ -37,9 +42,12 @@ void upload_toed_tables()
             T[v][1][p + 9] = zero ? 0.f : (float)Gx;
             T[v][2][p + 9] = zero ? 0.f : (float)Gxx;
             T[v][3][p + 9] = zero ? 0.f : (float)Gxxx;
+            T64[v][0][p + 9] = zero ? 0.0 : G; T64[v][1][p + 9] = zero ? 0.0 : Gx; T64[v][2][p + 9] = zero ? 0.0 : Gxx; T64[v][3][p + 9] = zero ? 0.0 : Gxxx;
         }
     cudaMemcpyToSymbol(c_T, T, sizeof(T));
+    cudaMemcpyToSymbol(c_T64, T64, sizeof(T64));
 }
+
 
 constexpr int IN_WP = IN_W + 1;  // padded strides (floats)
 constexpr int OWP = OW + 1;
@@ -194,7 +202,6 @@ __global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch
     // ---- stage 3: NMS + sub-pixel fit on the 64x64 interior; one warp per interp row, two 32-wide halves ----
     const int warp = tid >> 5, lane = tid & 31;
     uint32_t* mask = b.mask + (size_t)img * b.maskStride;
-    float2* sp = b.sp + (size_t)img * b.spStride;
     int* rowcnt = b.rowcnt + (size_t)img * b.rowStride;
     int nall = 0;
     for (int rr = 0; rr < 8; ++rr) {
@@ -204,12 +211,14 @@ __global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch
         for (int h = 0; h < 2; ++h) {
             const int lj = 2 + 32 * h + lane;
             const int gj = 2 * x0 + (lj - 2);
+            // `edge` counts the samples the reference's tests accept (FP32 evaluation: n_total); `keep` is a slightly WIDER set
+            // (every threshold relaxed by far more than the FP32 error of the sums) that goes to toed_refine, where the same
+            // tests are decided in FP64: the edge list is the reference's set, not the FP32 approximation of it
             bool edge = false, keep = false;
-            float dx = 0.f, dy = 0.f;
             if (gi >= border && gi < b.H2 - border && gj >= border && gj < b.W2 - border) {
                 const float* M = s_mag + li * IWP + lj;
                 float m = M[0], gx = s_ix[li * IWP + lj], gy = s_iy[li * IWP + lj];
-                if (m > magThresh && !(fabsf(gx) < 10e-6f && fabsf(gy) < 10e-6f)) {
+                if (m > magThresh - 1e-3f && !(fabsf(gx) < 10e-6f && fabsf(gy) < 10e-6f)) {
                     float nx = gx / m, ny = gy / m, slope, fp, fm;
                     // octant table, cpu_toed.cpp:418-477 (M[+-IWP] = row i+-1, M[+-1] = column j+-1)
                     if (gx >= 0.f && gy >= 0.f) {
@@ -225,23 +234,24 @@ __global__ void __launch_bounds__(TOED_THREADS, 4) toed_grad_nms_kernel(DevBatch
                         if (gx < fabsf(gy)) { slope = -nx / ny; fp = M[-IWP] * (1 - slope) + M[-IWP + 1] * slope; fm = M[IWP] * (1 - slope) + M[IWP - 1] * slope; }
                         else { slope = -ny / nx; fp = M[1] * (1 - slope) + M[-IWP + 1] * slope; fm = M[-1] * (1 - slope) + M[IWP - 1] * slope; }
                     }
-                    if ((m > fm && m > fp) || (m > fm && m >= fp) || (m >= fm && m > fp)) {
+                    const float tol = 1e-4f * m + 1e-4f;
+                    if (m >= fm - tol && m >= fp - tol) {
+                        const bool strict = m > magThresh && ((m > fm && m > fp) || (m > fm && m >= fp) || (m >= fm && m > fp));
                         float s = sqrtf(1.f + slope * slope);
                         float A = (fm + fp - 2.f * m) / (2.f * s * s), B = (fp - fm) / (2.f * s);
                         float ss = -B / (2.f * A);
-                        if (fabsf(ss) <= 1.41421356237f) {
-                            edge = true;
-                            dx = ss * nx; dy = ss * ny;
+                        if (fabsf(ss) <= 1.41421356237f + 1e-2f) {
+                            edge = strict && fabsf(ss) <= 1.41421356237f;
+                            const float dx = ss * nx, dy = ss * ny;
                             double X = ((double)gj + (double)dx - 1.0) * 0.5, Y = ((double)gi + (double)dy - 1.0) * 0.5;
-                            // border filter of cpu_toed.cpp:553-554; X==0 map sentinel (:534) cannot occur for gj >= 10
-                            keep = (X > (double)border) && (X < (double)(b.W - border)) && (Y > (double)border) && (Y < (double)(b.H - border));
+                            // border filter of cpu_toed.cpp:553-554 (relaxed by 0.01 px; decided in toed_refine)
+                            keep = (X > (double)border - 1e-2) && (X < (double)(b.W - border) + 1e-2) && (Y > (double)border - 1e-2) && (Y < (double)(b.H - border) + 1e-2);
                         }
                     }
                 }
             }
             unsigned all = __ballot_sync(0xffffffffu, edge), kp = __ballot_sync(0xffffffffu, keep);
             nall += __popc(all);
-            if (keep) sp[(size_t)gi * b.W2 + gj] = make_float2(dx, dy);
             if (lane == 0) {
                 mask[(size_t)gi * b.maskPitch + ((2 * x0 + 32 * h) >> 5)] = kp;
                 if (kp && gi < b.H2) atomicAdd(&rowcnt[gi], __popc(kp));
@@ -314,55 +324,209 @@ __global__ void __launch_bounds__(256) toed_expand_kernel(DevBatch b)
     }
 }
 
-// ---- K_C: third-order orientation at the edge samples; one thread per edge ------------------------------
-__global__ void __launch_bounds__(128) toed_orient_kernel(DevBatch b)
+// ---- K_C: FP64 refinement of the surviving edge samples; one warp per edge -------------------------------
+// The dense kernel decides WHICH interp samples are edges in FP32 (2 % of the grid survive); this kernel re-evaluates, for
+// those samples only, everything that reaches the edge list in FP64 and in the reference's own formulas: the gradient
+// (fx, fy) at the sample and its 8 neighbours (cpu_toed.cpp:200-222), the octant interpolation and parabola fit
+// (:418-510), the seven third-order responses and the orientation (:224-229).  The edge list then carries the
+// reference's FP64 values (measured |dx|, |dy| < 1e-11 px, |dtheta| < 1e-11 rad against the oracle instead of 5e-5 px /
+// 3e-5 rad for the FP32 values), so the matcher downstream sees the same input as the CPU path and the 0.1 % budget for
+// near-threshold flips is not spent on detector noise.  Separable form per edge: lane = image row (21 rows x 21
+// columns cover the 3 x 3 samples' 19 x 19 supports): 1-D row sums for the three sample columns (G, Gx; the 17-tap and
+// 19-tap variants of sub-grid (0,0) share their middle taps) and Gxx, Gxxx for the centre column -> shared memory ->
+// lane = (sample, response): 19-tap column sums -> every lane evaluates the closed forms, lane 0 writes.
+template <int B, int A>   // B = gj & 1, A = gi & 1 (x / y phase of the sample): fix where the three sample columns sit in the 21-pixel row
+__device__ __forceinline__ void refine_row_pass(const double (&px)[21], double* out /* 14 */)
 {
-    __shared__ float s_T[3][4][19];
-    for (int k = threadIdx.x; k < 3 * 4 * 19; k += 128) (&s_T[0][0][0])[k] = (&c_T[0][0][0])[k];
-    __syncthreads();
-    const int img = blockIdx.y;
-    const int n = b.nE[img];
-    const int e = blockIdx.x * 128 + threadIdx.x;
-    if (e >= n) return;
-    const uint8_t* src = b.und + (size_t)img * b.imgStride;
-    const uint32_t ij = b.coords[(size_t)img * b.E + e];
-    const int gi = ij >> 16, gj = ij & 0xffff;
-    const int a = gi & 1, bb = gj & 1, ci = gi >> 1, cj = gj >> 1;
-    const int xv = bb ? 2 : (a ? 1 : 0), yv = a ? 2 : (bb ? 1 : 0);
-    const float(*X)[19] = s_T[xv];
-    const float(*Y)[19] = s_T[yv];
-    float fx = 0, fy = 0, fxx = 0, fyy = 0, fxy = 0, fxxy = 0, fxyy = 0, fxxx = 0, fyyy = 0;
-    for (int p = -9; p <= 9; ++p) {
-        int row = ci - p;
-        if (row < 0 || row >= b.H) continue;
-        const uint8_t* rp = src + (size_t)row * b.pitch;
-        float rG = 0, rGx = 0, rGxx = 0, rGxxx = 0;
+    // column dj = -1, 0, +1: centre offset oc in px[], x phase b'
+    constexpr int OC[3] = {9, B ? 9 : 10, 10};
+    constexpr int BP[3] = {B ? 0 : 1, B ? 1 : 0, B ? 0 : 1};
 #pragma unroll
-        for (int q = -9; q <= 9; ++q) {
-            int col = cj - q;
-            float v = (col >= 0 && col < b.W) ? (float)rp[col] : 0.f;
-            rG = fmaf(v, X[0][q + 9], rG);
-            rGx = fmaf(v, X[1][q + 9], rGx);
-            rGxx = fmaf(v, X[2][q + 9], rGxx);
-            rGxxx = fmaf(v, X[3][q + 9], rGxxx);
+    for (int c = 0; c < 3; ++c) {
+        if (BP[c]) {           // shifted tables, 19 taps
+            double g = 0, gx = 0;
+#pragma unroll
+            for (int q = -9; q <= 9; ++q) { g = fma(px[OC[c] - q], c_T64[2][0][q + 9], g); gx = fma(px[OC[c] - q], c_T64[2][1][q + 9], gx); }
+            out[4 * c + 0] = g; out[4 * c + 1] = gx;
+        } else {               // unshifted: 17 taps for sample rows of sub-grid (0,0), 19 taps for sub-grid (1,0)
+            double g = 0, gx = 0;
+#pragma unroll
+            for (int q = -8; q <= 8; ++q) { g = fma(px[OC[c] - q], c_T64[1][0][q + 9], g); gx = fma(px[OC[c] - q], c_T64[1][1][q + 9], gx); }
+            out[4 * c + 0] = g; out[4 * c + 1] = gx;
+            out[4 * c + 2] = fma(px[OC[c] - 9], c_T64[1][0][18], fma(px[OC[c] + 9], c_T64[1][0][0], g));
+            out[4 * c + 3] = fma(px[OC[c] - 9], c_T64[1][1][18], fma(px[OC[c] + 9], c_T64[1][1][0], gx));
         }
-        float yG = Y[0][p + 9], yGx = Y[1][p + 9], yGxx = Y[2][p + 9], yGxxx = Y[3][p + 9];
-        fx = fmaf(rGx, yG, fx);       fy = fmaf(rG, yGx, fy);
-        fxx = fmaf(rGxx, yG, fxx);    fxy = fmaf(rGx, yGx, fxy);   fyy = fmaf(rG, yGxx, fyy);
-        fxxy = fmaf(rGxx, yGx, fxxy); fxyy = fmaf(rGx, yGxx, fxyy);
-        fxxx = fmaf(rGxxx, yG, fxxx); fyyy = fmaf(rG, yGxxx, fyyy);
     }
-    // cpu_toed.cpp:224-229
-    float tx = fx * (2 * fxx * fxx + 2 * fxy * fxy) + fy * (2 * fxx * fxy + 2 * fyy * fxy) + 2 * fx * fy * fxxy + fy * fy * fxyy + fx * fx * fxxx;
-    float ty = fx * (2 * fxx * fxy + 2 * fyy * fxy) + fy * (2 * fyy * fyy + 2 * fxy * fxy) + 2 * fx * fy * fxyy + fx * fx * fxxy + fy * fy * fyyy;
-    float tm = sqrtf(tx * tx + ty * ty);
-    tx /= tm; ty /= tm;
-    float th = atan2f(tx, -ty);
-    float2 d = b.sp[(size_t)img * b.spStride + (size_t)gi * b.W2 + gj];
-    size_t o = (size_t)img * b.E + e;
-    b.ex[o] = ((double)gj + (double)d.x - 1.0) * 0.5;   // cpu_toed.cpp:538
-    b.ey[o] = ((double)gi + (double)d.y - 1.0) * 0.5;   // cpu_toed.cpp:542
-    b.eth[o] = (double)th;
+    // centre column: Gxx, Gxxx with the centre sample's own x variant (0: 17 taps, 1: 19 taps, 2: shifted)
+    constexpr int XV = B ? 2 : A;
+    double gxx = 0, gxxx = 0;
+#pragma unroll
+    for (int q = -9; q <= 9; ++q) { gxx = fma(px[OC[1] - q], c_T64[XV][2][q + 9], gxx); gxxx = fma(px[OC[1] - q], c_T64[XV][3][q + 9], gxxx); }
+    out[12] = gxx; out[13] = gxxx;
+}
+
+__global__ void __launch_bounds__(128) toed_refine_kernel(DevBatch b, double magThresh, int border)
+{
+    __shared__ double s_T[3][4][19];
+    __shared__ double s_rc[4][21][14];
+    __shared__ double s_out[4][32][25];
+    __shared__ uint32_t s_win[4][21][7];      // u8 window, 28-byte rows (7 words: odd stride, conflict-free row-parallel reads)
+    for (int k = threadIdx.x; k < 3 * 4 * 19; k += 128) (&s_T[0][0][0])[k] = (&c_T64[0][0][0])[k];
+    __syncthreads();
+    const int img = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = b.nE[img];
+    const uint8_t* src = b.und + (size_t)img * b.imgStride;
+    int nrej = 0;
+    for (int e0 = (blockIdx.x * 4 + w) * 32; e0 < n; e0 += gridDim.x * 4 * 32) {
+        const int cnt = min(32, n - e0);
+        const uint32_t ijl = lane < cnt ? b.coords[(size_t)img * b.E + e0 + lane] : 0u;
+        // ---- 1-D sums of the 32 edges of this pass, one after the other ----
+        for (int k = 0; k < cnt; ++k) {
+            const uint32_t ij = __shfl_sync(0xffffffffu, ijl, k);
+            const int gi = ij >> 16, gj = ij & 0xffff;
+            const int a = gi & 1, bb = gj & 1;
+            const int rbase = ((gi - 1) >> 1) - 9, cbase = ((gj - 1) >> 1) - 9;
+            // the 21 x 21 u8 window (rows rbase.., columns cbase..) goes through shared memory: coalesced 32-bit loads of the
+            // words that cover it (6 per row), zero outside the image (the reference's zero padding, cpu_toed.cpp:204-205)
+            const int c4 = cbase & ~3;
+            for (int t = lane; t < 21 * 6; t += 32) {
+                const int r = t / 6, wd = t - 6 * r;
+                const int row = rbase + r, col = c4 + 4 * wd;
+                uint32_t v = 0;
+                if (row >= 0 && row < b.H) {
+                    const uint8_t* rp = src + (size_t)row * b.pitch;
+                    if (col >= 0 && col + 3 < b.W) v = __ldg(reinterpret_cast<const uint32_t*>(rp + col));
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (col + q >= 0 && col + q < b.W) v |= (uint32_t)__ldg(rp + col + q) << (8 * q);
+                    }
+                }
+                s_win[w][r][wd] = v;
+            }
+            __syncwarp();
+            if (lane < 21) {       // row pass: lane = image row
+                const uint8_t* wp = reinterpret_cast<const uint8_t*>(&s_win[w][lane][0]) + (cbase - c4);
+                double px[21];
+#pragma unroll
+                for (int c = 0; c < 21; ++c) px[c] = __hiloint2double(0x43300000, (int)wp[c]) - 4503599627370496.0;   // exact u8 -> double
+                double* out = s_rc[w][lane];
+                if (bb) { if (a) refine_row_pass<1, 1>(px, out); else refine_row_pass<1, 0>(px, out); }
+                else { if (a) refine_row_pass<0, 1>(px, out); else refine_row_pass<0, 0>(px, out); }
+            }
+            __syncwarp();
+            // column pass: lane l < 18 -> sample l / 2 (di = s / 3 - 1, dj = s % 3 - 1), fx (l even) or fy (l odd);
+            // lanes 18..24 -> fxx, fyy, fxy, fxxy, fxyy, fxxx, fyyy at the centre sample
+            if (lane < 25) {
+                int di = 0, dj = 0, xk, yk;
+                if (lane < 18) { const int sidx = lane >> 1; di = sidx / 3 - 1; dj = sidx % 3 - 1; xk = (lane & 1) ? 0 : 1; yk = (lane & 1) ? 1 : 0; }
+                else {
+                    const int t = lane - 18;             // x kernels 2 0 1 2 1 3 0, y kernels 0 2 1 1 2 0 3 (cpu_toed.cpp:207-216)
+                    xk = (0x0312102 >> (4 * t)) & 15; yk = (0x3021120 >> (4 * t)) & 15;
+                }
+                const int ap = (gi + di) & 1, bp = (gj + dj) & 1, cid = (gi + di) >> 1;
+                const int yv = ap ? 2 : (bp ? 1 : 0);
+                const int slot = xk >= 2 ? 10 + xk : 4 * (dj + 1) + xk + ((bp == 0 && ap) ? 2 : 0);   // 19-tap version for sub-grid (1,0)
+                const int r0 = cid - rbase;                                                           // row of tap p = 0
+                double acc = 0;
+#pragma unroll
+                for (int p = -9; p <= 9; ++p) acc = fma(s_rc[w][r0 - p][slot], s_T[yv][yk][p + 9], acc);
+                s_out[w][k][lane] = acc;
+            }
+            __syncwarp();
+        }
+        // ---- closed forms: lane = edge ----
+        bool ok = false;
+        double ex = 0, ey = 0, eth = 0;
+        if (lane < cnt) {
+            const double* o = s_out[w][lane];
+            const int gi = ijl >> 16, gj = ijl & 0xffff;
+            auto FX = [&](int di, int dj) { return o[2 * ((di + 1) * 3 + dj + 1)]; };
+            auto FY = [&](int di, int dj) { return o[2 * ((di + 1) * 3 + dj + 1) + 1]; };
+            auto M = [&](int di, int dj) { const double x = FX(di, dj), y = FY(di, dj); return sqrt(x * x + y * y); };
+            const double gx = FX(0, 0), gy = FY(0, 0);
+            const double m = sqrt(gx * gx + gy * gy);
+            if (m > magThresh && !(fabs(gx) < 10e-6 && fabs(gy) < 10e-6)) {         // cpu_toed.cpp:406-411
+                const double nx = gx / m, ny = gy / m;
+                double slope, fp, fm;
+                // octant table, cpu_toed.cpp:418-477 (M(di, dj): row i + di, column j + dj)
+                if (gx >= 0 && gy >= 0) {
+                    if (gx >= gy) { slope = ny / nx; fp = M(0, 1) * (1 - slope) + M(1, 1) * slope; fm = M(0, -1) * (1 - slope) + M(-1, -1) * slope; }
+                    else { slope = nx / ny; fp = M(1, 0) * (1 - slope) + M(1, 1) * slope; fm = M(-1, 0) * (1 - slope) + M(-1, -1) * slope; }
+                } else if (gx < 0 && gy >= 0) {
+                    if (fabs(gx) < gy) { slope = -nx / ny; fp = M(1, 0) * (1 - slope) + M(1, -1) * slope; fm = M(-1, 0) * (1 - slope) + M(-1, 1) * slope; }
+                    else { slope = -ny / nx; fp = M(0, -1) * (1 - slope) + M(1, -1) * slope; fm = M(0, 1) * (1 - slope) + M(-1, 1) * slope; }
+                } else if (gx < 0 && gy < 0) {
+                    if (fabs(gx) >= fabs(gy)) { slope = ny / nx; fp = M(0, -1) * (1 - slope) + M(-1, -1) * slope; fm = M(0, 1) * (1 - slope) + M(1, 1) * slope; }
+                    else { slope = nx / ny; fp = M(-1, 0) * (1 - slope) + M(-1, -1) * slope; fm = M(1, 0) * (1 - slope) + M(1, 1) * slope; }
+                } else {
+                    if (gx < fabs(gy)) { slope = -nx / ny; fp = M(-1, 0) * (1 - slope) + M(-1, 1) * slope; fm = M(1, 0) * (1 - slope) + M(1, -1) * slope; }
+                    else { slope = -ny / nx; fp = M(0, 1) * (1 - slope) + M(-1, 1) * slope; fm = M(0, -1) * (1 - slope) + M(1, -1) * slope; }
+                }
+                if ((m > fm && m > fp) || (m > fm && m >= fp) || (m >= fm && m > fp)) {   // :481
+                    const double s = sqrt(1 + slope * slope);
+                    const double A = (fm + fp - 2 * m) / (2 * s * s), Bc = (fp - fm) / (2 * s);
+                    const double ss = -Bc / (2 * A);
+                    if (fabs(ss) <= sqrt(2.0)) {                                          // :496
+                        const double X = (double)gj + ss * nx, Y = (double)gi + ss * ny;  // :499-500
+                        ex = (X - 1) / 2; ey = (Y - 1) / 2;                               // :538, :542
+                        ok = X != 0.0 && ex > (double)border && ex < (double)(b.W - border) && ey > (double)border && ey < (double)(b.H - border);   // :534, :553-554
+                        // third-order orientation, cpu_toed.cpp:224-229
+                        const double fx = gx, fy = gy, fxx = o[18], fyy = o[19], fxy = o[20], fxxy = o[21], fxyy = o[22], fxxx = o[23], fyyy = o[24];
+                        double tx = fx * (2 * fxx * fxx + 2 * fxy * fxy) + fy * (2 * fxx * fxy + 2 * fyy * fxy) + 2 * fx * fy * fxxy + fy * fy * fxyy + fx * fx * fxxx;
+                        double ty = fx * (2 * fxx * fxy + 2 * fyy * fxy) + fy * (2 * fyy * fyy + 2 * fxy * fxy) + 2 * fx * fy * fxyy + fx * fx * fxxy + fy * fy * fyyy;
+                        const double tm = sqrt(tx * tx + ty * ty);
+                        tx /= tm; ty /= tm;
+                        eth = atan2(tx, -ty);
+                    }
+                }
+            }
+            const size_t oo = (size_t)img * b.E + e0 + lane;
+            b.ex[oo] = ok ? ex : CUDART_NAN; b.ey[oo] = ey; b.eth[oo] = eth;     // NaN x marks a prefilter survivor the FP64 tests reject
+            if (!ok) ++nrej;
+        }
+        __syncwarp();
+    }
+    nrej = __reduce_add_sync(0xffffffffu, nrej);
+    if (lane == 0 && nrej) atomicAdd(&b.nRej[img], nrej);
+}
+
+// Stable in-place compaction of an image's edge list after the FP64 tests (one CTA per image; nothing to do - and nothing
+// done - for the usual image without rejections).  Chunks are read whole before they are written and destinations never
+// lie beyond their sources, so the compaction is safe in place and keeps the row-major order of cpu_toed.cpp:530-575.
+__global__ void __launch_bounds__(1024) toed_prune_kernel(DevBatch b)
+{
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (b.nRej[img] == 0) return;
+    const int n = b.nE[img];
+    double *ex = b.ex + (size_t)img * b.E, *ey = b.ey + (size_t)img * b.E, *eth = b.eth + (size_t)img * b.E;
+    __shared__ int s_w[32];
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+        const int i = c0 + tid;
+        double x = 0, y = 0, t = 0;
+        if (i < n) { x = ex[i]; y = ey[i]; t = eth[i]; }
+        const bool keep = i < n && x == x;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_w[w] = __popc(m);
+        __syncthreads();
+        if (w == 0) {
+            const int v = s_w[lane];
+            int s = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += u; }
+            s_w[lane] = s - v;
+        }
+        __syncthreads();
+        const int base = s_base;
+        const int pos = base + s_w[w] + __popc(m & ((1u << lane) - 1));
+        if (keep) { ex[pos] = x; ey[pos] = y; eth[pos] = t; }
+        __syncthreads();
+        if (tid == 1023) s_base = base + s_w[31] + __popc(m);
+        __syncthreads();
+    }
+    if (tid == 0) b.nE[img] = s_base;
 }
 
 // Tensor map over the context's image array: dims (W, H, images) of u8, strides (pitch, imgStride) bytes, box 64 x 52 x 1.
@@ -398,13 +562,17 @@ void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_
 {
     cudaMemsetAsync(b.rowcnt, 0, sizeof(int) * b.rowStride * nImages, st);
     cudaMemsetAsync(b.nTot, 0, sizeof(int) * nImages, st);
+    cudaMemsetAsync(b.nRej, 0, sizeof(int) * nImages, st);
     dim3 gA(b.tilesX, b.tilesY, nImages);
     EBVO_KERNEL(prof, "toed_grad_nms", st, (toed_grad_nms_kernel<<<gA, TOED_THREADS, TOED_SMEM, st>>>(b, *reinterpret_cast<const CUtensorMap*>(b.tmap), p.toed_mag_thresh, p.toed_border)));
     EBVO_KERNEL(prof, "toed_scan", st, (toed_scan_kernel<<<nImages, 1024, 0, st>>>(b)));
     dim3 gE((b.H2 + 7) / 8, nImages);
     EBVO_KERNEL(prof, "toed_expand", st, (toed_expand_kernel<<<gE, 256, 0, st>>>(b)));
-    dim3 gC((b.E + 127) / 128, nImages);
-    EBVO_KERNEL(prof, "toed_orient", st, (toed_orient_kernel<<<gC, 128, 0, st>>>(b)));
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dim3 gC(std::max(1, std::min((b.E + 127) / 128, (sms * 12 + nImages - 1) / nImages)), nImages);
+    EBVO_KERNEL(prof, "toed_refine", st, (toed_refine_kernel<<<gC, 128, 0, st>>>(b, (double)p.toed_mag_thresh, p.toed_border)));
+    EBVO_KERNEL(prof, "toed_prune", st, (toed_prune_kernel<<<nImages, 1024, 0, st>>>(b)));
 }
 
 }  // namespace ebvo
