@@ -197,7 +197,7 @@ def run_reference(args, cal, rank):
                              "kind": "reference" if kind == "reference" else "port",
                              "sample": "1 frame per step: TOED = unmodified reference cpu_toed.cpp on both views; stereo S1-S13 (SIFT-off) = "
                                        "unmodified reference Stereo_Matches.cpp/utility.cpp/EdgeClusterer.cpp compiled in place "
-                                       "(oracle/_ref, OpenCV/Eigen primitives from oracle/ref_shim), OpenMP on all host cores"},
+                                       "(oracle/_ref, OpenCV/Eigen primitives from third_party_shim), OpenMP on all host cores"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

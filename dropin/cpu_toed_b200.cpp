@@ -10,6 +10,7 @@
 //
 // Build: add this file to the library instead of src/toed/cpu_toed.cpp and link libebvo_b200.so:
 //   g++ -std=c++17 -I<reference>/include -I<ebvo-b200>/include -c dropin/cpu_toed_b200.cpp
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <mutex>
@@ -18,20 +19,11 @@
 #include <opencv2/opencv.hpp>
 #include "toed/cpu_toed.hpp"   // the reference header (leaks img()/Ix()/... macros: keep locals clear of those names)
 #include "ebvo_b200.h"
+#include "ebvo_dropin_common.hpp"   // the process-wide context shared with the matcher drop-ins (no second set of device buffers)
 
-namespace {
-// The reference class has no room for a context handle (its private members are fixed by the header), so the
-// handles live in a side table keyed by the object address.
-std::mutex g_mu;
-std::map<const void*, ebvo_ctx*> g_ctx;
-
-ebvo_ctx* context_of(const void* self)
-{
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ctx.find(self);
-    return it == g_ctx.end() ? nullptr : it->second;
-}
-}  // namespace
+// edges per image the shared context is sized for: one per 8 input pixels (a dense synthetic scene yields one per 14), at
+// least 65 536 (KITTI / EuRoC / ETH3D shapes), at most 2 M (the 4K stress shape); beyond it ebvo_toed reports EBVO_ERR_CAPACITY
+static int edge_capacity(int H, int W) { return std::min(1 << 21, std::max(1 << 16, H * W / 8)); }
 
 ThirdOrderEdgeDetectionCPU::ThirdOrderEdgeDetectionCPU(int H, int W)
 {
@@ -51,27 +43,11 @@ ThirdOrderEdgeDetectionCPU::ThirdOrderEdgeDetectionCPU(int H, int W)
     img = Ix = Iy = I_grad_mag = I_orient = nullptr;
     subpix_pos_x_map = subpix_pos_y_map = subpix_grad_mag_map = nullptr;
     subpix_edge_pts_final = new double[(size_t)4 * 4 * H * W]();   // (x, y, theta, 0) rows of the LAST call's edges
-    ebvo_ctx* c = nullptr;
-    const int max_edges = H * W;   // an edge sample needs a local maximum: far below one per input pixel
-    int rc = ebvo_create(&c, 0, W, H, 1, max_edges < 1024 ? 1024 : max_edges, nullptr);
-    if (rc != EBVO_OK) {
-        std::printf("\033[1;31m[ERROR] ebvo_create failed (%d): %s\033[0m\n", rc, c ? ebvo_last_error(c) : "no CUDA device");
-        if (c) ebvo_destroy(c);
-        c = nullptr;
-    }
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_ctx[this] = c;
+    ebvo_dropin::Lease lease(W, H, edge_capacity(H, W));             // creates the shared context now, so that a missing GPU is reported here
 }
 
 ThirdOrderEdgeDetectionCPU::~ThirdOrderEdgeDetectionCPU()
 {
-    ebvo_ctx* c = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_ctx.find(this);
-        if (it != g_ctx.end()) { c = it->second; g_ctx.erase(it); }
-    }
-    if (c) ebvo_destroy(c);
     delete[] subpix_edge_pts_final;
 }
 
@@ -80,13 +56,14 @@ void ThirdOrderEdgeDetectionCPU::get_Third_Order_Edges(cv::Mat image)
     toed_edges.clear();
     Total_Num_Of_TOED = 0;
     edge_pt_list_idx = 0;
-    ebvo_ctx* c = context_of(this);
+    ebvo_dropin::Lease lease(img_width, img_height, edge_capacity(img_height, img_width));
+    ebvo_ctx* c = lease.ctx;
     if (!c) return;
     if (image.rows != img_height || image.cols != img_width) {
         std::printf("\033[1;31m[ERROR] image size differs from the detector's (H, W)\033[0m\n");
         return;
     }
-    const int cap = img_height * img_width;
+    const int cap = std::max(1 << 16, ebvo_dropin::shared().edges);      // the context's edge capacity (EBVO_ERR_CAPACITY beyond it)
     std::vector<ebvo_edge> out((size_t)cap);
     int n = 0, n_total = 0;
     const unsigned char* first = &image.at<unsigned char>(0, 0);
@@ -110,6 +87,12 @@ void ThirdOrderEdgeDetectionCPU::get_Third_Order_Edges(cv::Mat image)
     }
     edge_pt_list_idx = n_total;
     Total_Num_Of_TOED = n_total;   // unfiltered count, as cpu_toed.cpp:76,581
+    // the class's profiling members (seconds, cpu_toed.cpp:366-368, 516-518) from the kernels' CUDA-event times: the dense kernel
+    // fuses the convolution with the NMS tests, the sparse ones (ordering, FP64 sub-pixel fit) are what is left of the NMS stage
+    const char* conv[] = {"toed_grad_nms"};
+    const char* nms[] = {"toed_scan", "toed_expand", "toed_refine", "toed_prune"};
+    time_conv = ebvo_dropin::kernel_ms(c, conv, 1) * 1e-3;
+    time_nms = ebvo_dropin::kernel_ms(c, nms, 4) * 1e-3;
 }
 
 // The three stages are fused on the GPU; the reference's separate entry points stay callable.

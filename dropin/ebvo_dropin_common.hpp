@@ -1,24 +1,38 @@
-// Shared by the drop-in translation units: one process-wide ebvo context (one GPU), grown on demand.
+// Shared by the drop-in translation units: one process-wide ebvo context (one GPU), grown on demand, handed out under a lock.
 //
 // The reference classes have no room for a context handle (their members are fixed by the reference headers), and
 // Pipeline constructs exactly one of each (Pipeline.cpp:15-21), so a process-wide context created on first use
-// mirrors the reference's lifetime.  No CPU fallback: when the context cannot be created the caller reports the
-// error the reference way (a LOG_ERROR-style print) and returns an empty result.
+// mirrors the reference's lifetime.  The detector, the matcher and the quad tracker share it (a context holds the buffers
+// of all three; one per class instance would triple the device memory).  A caller holds a Lease for the duration of its
+// C-ABI calls: growing the context destroys the old one, which must not happen under another caller's feet.
+// No CPU fallback: when the context cannot be created the caller reports the error the reference way (a LOG_ERROR-style
+// print) and returns an empty result.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "ebvo_b200.h"
 
 namespace ebvo_dropin {
 
+// what get_Stereo_Edge_Pairs already computed for finalize_stereo_edge_mates (same call, same upload): right patches and
+// right descriptor pairs of the mates, valid while `frame` / `n` / the first and last mate still identify the same result
+struct FinalizeCache {
+    const void* frame = nullptr;
+    size_t n = 0;
+    double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    std::vector<float> r_plus, r_minus, r_desc;
+};
+
 struct Shared {
-    std::mutex mu;
+    std::recursive_mutex mu;
     ebvo_ctx* ctx = nullptr;
     int w = 0, h = 0, edges = 0;
+    FinalizeCache fin;
 };
 inline Shared& shared()
 {
@@ -34,28 +48,45 @@ inline bool sift_enabled()
     return !(e && e[0] == '0');
 }
 
-// Returns a context able to hold w x h images and `edges` edges per image (nullptr + message on failure).
-inline ebvo_ctx* context(int w, int h, int edges)
-{
-    Shared& s = shared();
-    std::lock_guard<std::mutex> lk(s.mu);
-    if (s.ctx && w <= s.w && h <= s.h && edges <= s.edges) return s.ctx;
-    if (s.ctx) { ebvo_destroy(s.ctx); s.ctx = nullptr; }
-    const int W = w > s.w ? w : s.w, H = h > s.h ? h : s.h;
-    int E = edges > s.edges ? edges : s.edges;
-    if (E < 1 << 16) E = 1 << 16;
-    ebvo_ctx* c = nullptr;
-    ebvo_params prm;
-    ebvo_params_default(&prm);
-    prm.sift_mode = sift_enabled() ? 1 : 0;
-    const int rc = ebvo_create(&c, 0, W, H, 1, E, &prm);
-    if (rc != EBVO_OK) {
-        std::printf("\033[1;31m[ERROR] ebvo_create failed (%d): %s\033[0m\n", rc, c ? ebvo_last_error(c) : "no CUDA device");
-        if (c) ebvo_destroy(c);
-        return nullptr;
+// A context able to hold w x h images and `edges` edges per image, locked for the lifetime of the object
+// (ctx == nullptr + message on failure).
+struct Lease {
+    std::unique_lock<std::recursive_mutex> lk;
+    ebvo_ctx* ctx = nullptr;
+    Lease(int w, int h, int edges) : lk(shared().mu)
+    {
+        Shared& s = shared();
+        if (s.ctx && w <= s.w && h <= s.h && edges <= s.edges) { ctx = s.ctx; return; }
+        if (s.ctx) { ebvo_destroy(s.ctx); s.ctx = nullptr; s.fin = FinalizeCache(); }
+        const int W = w > s.w ? w : s.w, H = h > s.h ? h : s.h;
+        int E = edges > s.edges ? edges : s.edges;
+        if (E < 1 << 16) E = 1 << 16;
+        ebvo_ctx* c = nullptr;
+        ebvo_params prm;
+        ebvo_params_default(&prm);
+        prm.sift_mode = sift_enabled() ? 1 : 0;
+        const int rc = ebvo_create(&c, 0, W, H, 1, E, &prm);
+        if (rc != EBVO_OK) {
+            std::printf("\033[1;31m[ERROR] ebvo_create failed (%d): %s\033[0m\n", rc, c ? ebvo_last_error(c) : "no CUDA device");
+            if (c) ebvo_destroy(c);
+            return;
+        }
+        ebvo_set_profiling(c, 1);      // per-kernel CUDA events: time_conv / time_nms and Timing_Statistics are filled from them
+        s.ctx = c; s.w = W; s.h = H; s.edges = E;
+        ctx = c;
     }
-    s.ctx = c; s.w = W; s.h = H; s.edges = E;
-    return c;
+};
+
+// milliseconds the named kernels took in the last profiled call (prefix match)
+inline double kernel_ms(ebvo_ctx* c, const char* const* prefixes, int np)
+{
+    const char** names = nullptr; const float* ms = nullptr; const int* launches = nullptr; int n = 0;
+    if (ebvo_get_kernel_times(c, &names, &ms, &launches, &n) != EBVO_OK) return 0.0;
+    double t = 0.0;
+    for (int k = 0; k < n; ++k)
+        for (int p = 0; p < np; ++p)
+            if (std::strncmp(names[k], prefixes[p], std::strlen(prefixes[p])) == 0) { t += ms[k]; break; }
+    return t;
 }
 
 // Tightly packed copy of an 8-bit single-channel image given (data, rows, cols, step in bytes).

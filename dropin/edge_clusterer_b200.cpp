@@ -35,7 +35,8 @@ void EdgeClusterer::performClustering()
     const int n = Num_Of_Epipolar_Corrected_H2_Edges;
     returned_clusters.clear(); clusters.clear(); Num_Of_Clusters = 0;
     if (n == 0) return;
-    ebvo_ctx* ctx = ebvo_dropin::context(64, 64, 1024);
+    ebvo_dropin::Lease lease(64, 64, 1024);
+    ebvo_ctx* ctx = lease.ctx;
     if (!ctx) return;
     const std::vector<Edge> shifted_edges = Epip_Correct_Edges;
     std::vector<ebvo_edge> in((size_t)n), centers((size_t)n);

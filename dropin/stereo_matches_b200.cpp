@@ -4,7 +4,7 @@
 // (reference src/Stereo_Matches.cpp:1360-1540 and :1578-1653), compiled against the reference's OWN headers
 // (include/Stereo_Matches.h, Dataset.h, Stereo_Iterator.h, toed/cpu_toed.hpp - unmodified), so the call sites in
 // Pipeline::get_Stereo_Edge_Correspondences (src/Pipeline.cpp:116-131) compile and behave unchanged.  The work is
-// done on the GPU through the C ABI (include/ebvo_b200.h: ebvo_stereo_match, ebvo_edge_patches).  No CPU fallback.
+// done on the GPU through the C ABI (include/ebvo_b200.h: ebvo_stereo_match_full - ONE call per frame).  No CPU fallback.
 //
 // How a maintainer links it (no reference source is edited):
 //   * add this file and libebvo_b200.so to the library;
@@ -83,14 +83,15 @@ std::pair<cv::Mat, cv::Mat> patch_pair(const float* plus49, const float* minus49
 
 Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr dataset, Stereo_Edge_Pairs& pairs, size_t frame_idx, Timing_Statistics& timing_statistics)
 {
-    (void)frame_idx; (void)timing_statistics;
+    (void)frame_idx;
     Frame_Evaluation_Metrics frame_metrics;
     const StereoFrame& f = *pairs.stereo_frame;
     const int W = f.left_image.cols, H = f.left_image.rows;
     const size_t nF = pairs.focused_edge_indices.size();
     const int nR = (int)f.right_edges.size();
     const int cap = (int)std::max<size_t>(std::max<size_t>(nF, (size_t)nR), 1);
-    ebvo_ctx* ctx = ebvo_dropin::context(W, H, cap);
+    ebvo_dropin::Lease lease(W, H, cap);
+    ebvo_ctx* ctx = lease.ctx;
 
     // what the reference's stages leave behind even when nothing survives
     auto fail_empty = [&]() {
@@ -101,11 +102,20 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     };
     if (!ctx) return fail_empty();
 
-    // inputs: raw images for the NCC stages (:562-563), undistorted ones for Gauss-Newton and finalisation (:1293, :1580)
-    const std::vector<unsigned char> Lraw = ebvo_dropin::packed_u8(f.left_image.data, H, W, f.left_image.step);
-    const std::vector<unsigned char> Rraw = ebvo_dropin::packed_u8(f.right_image.data, H, W, f.right_image.step);
-    const std::vector<unsigned char> Lund = ebvo_dropin::packed_u8(f.left_image_undistorted.data, H, W, f.left_image_undistorted.step);
-    const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(f.right_image_undistorted.data, H, W, f.right_image_undistorted.step);
+    // inputs: raw images for the NCC stages (:562-563), undistorted ones for Gauss-Newton and finalisation (:1293, :1580).
+    // The four cv::Mat are handed over as they are when they share one row step (the usual case: continuous matrices);
+    // otherwise tightly packed copies are made.
+    const cv::Mat* im[4] = {&f.left_image, &f.right_image, &f.left_image_undistorted, &f.right_image_undistorted};
+    const unsigned char* ptr[4];
+    std::vector<unsigned char> packed[4];
+    size_t step = f.left_image.step;
+    bool same = true;
+    for (int k = 0; k < 4; ++k) same = same && (size_t)im[k]->step == step && im[k]->cols == W && im[k]->rows == H;
+    for (int k = 0; k < 4; ++k) {
+        if (same) ptr[k] = im[k]->data;
+        else { packed[k] = ebvo_dropin::packed_u8(im[k]->data, H, W, im[k]->step); ptr[k] = packed[k].data(); }
+    }
+    if (!same) step = (size_t)W;
     std::vector<ebvo_edge> L(nF), R((size_t)nR);
     for (size_t i = 0; i < nF; ++i) {                      // the focused left edges, in Stereo_Edge_Pairs order (:192-198)
         const Edge& e = f.left_edges[pairs.focused_edge_indices[i]];
@@ -116,27 +126,42 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
         R[k] = ebvo_edge{e.location.x, e.location.y, e.orientation, k, e.frame_source};
     }
     const ebvo_calib calib = calib_of(*dataset);
-    std::vector<ebvo_mate> mates(std::max<size_t>(nF, 1));
+    // ONE call: matching, then - on the images already on the device - the left patches of the matched edges from the RAW left
+    // image (apply_NCC_Filtering, :570-576), their descriptor pairs (augment_Edge_Data, :655-689), and what
+    // finalize_stereo_edge_mates will ask for: the mates' patches from the UNDISTORTED right image (:1580-1582, :1622) and
+    // their descriptor pairs (:1627-1635)
+    const bool sift = ebvo_dropin::sift_enabled();
+    const size_t capM = std::max<size_t>(nF, 1);
+    std::vector<ebvo_mate> mates(capM);
+    std::vector<float> pp(capM * 49), pm(capM * 49), dl(sift ? capM * 256 : 0);
+    ebvo_dropin::FinalizeCache& fin = ebvo_dropin::shared().fin;
+    fin = ebvo_dropin::FinalizeCache();
+    fin.r_plus.resize(capM * 49); fin.r_minus.resize(capM * 49); fin.r_desc.resize(sift ? capM * 256 : 0);
     int n = 0;
-    int rc = ebvo_stereo_match(ctx, &calib, Lraw.data(), Rraw.data(), Lund.data(), Rund.data(), W, H, W, L.data(), (int)nF, R.data(), nR,
-                               nullptr, nullptr, mates.data(), (int)mates.size(), &n);
-    if (rc != EBVO_OK) { log_error("ebvo_stereo_match", ctx, rc); return fail_empty(); }
-
-    // left patches of the matched edges from the RAW left image (apply_NCC_Filtering, :570-576)
-    std::vector<ebvo_edge> Lm((size_t)n);
-    for (int k = 0; k < n; ++k) Lm[k] = L[mates[k].left_index];
-    std::vector<float> pp((size_t)n * 49), pm((size_t)n * 49);
+    int rc = ebvo_stereo_match_full(ctx, &calib, ptr[0], ptr[1], ptr[2], ptr[3], W, H, (int)step, L.data(), (int)nF, R.data(), nR,
+                                    mates.data(), (int)mates.size(), &n, pp.data(), pm.data(), fin.r_plus.data(), fin.r_minus.data(),
+                                    sift ? dl.data() : nullptr, sift ? fin.r_desc.data() : nullptr);
+    if (rc != EBVO_OK) { log_error("ebvo_stereo_match_full", ctx, rc); fin = ebvo_dropin::FinalizeCache(); return fail_empty(); }
     if (n > 0) {
-        rc = ebvo_edge_patches(ctx, Lraw.data(), W, H, W, Lm.data(), n, pp.data(), pm.data());
-        if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); return fail_empty(); }
+        fin.frame = pairs.stereo_frame; fin.n = (size_t)n;
+        fin.x0 = mates[0].rx; fin.y0 = mates[0].ry; fin.x1 = mates[n - 1].rx; fin.y1 = mates[n - 1].ry;
     }
-
-    // SIFT descriptors of the matched left edges from the undistorted left image (augment_Edge_Data, :655-689)
-    std::vector<float> dl;
-    if (ebvo_dropin::sift_enabled() && n > 0) {
-        dl.resize((size_t)n * 256);
-        rc = ebvo_sift_descriptors(ctx, Lund.data(), W, H, W, Lm.data(), n, dl.data());
-        if (rc != EBVO_OK) { log_error("ebvo_sift_descriptors", ctx, rc); return fail_empty(); }
+    {   // Timing_Statistics (Stereo_Matches.h:32-47; the reference's own assignments are commented out at :1376-1538): kernel
+        // milliseconds of this call.  The epipolar, disparity and orientation gates are ONE fused kernel: its time is under time_EP.
+        auto ms = [&](std::initializer_list<const char*> p) { return ebvo_dropin::kernel_ms(ctx, p.begin(), (int)p.size()); };
+        timing_statistics.time_EP = ms({"sobel", "bounds", "gate"});
+        timing_statistics.time_DP = 0.0; timing_statistics.time_OR = 0.0;
+        timing_statistics.time_SIFT = ms({"sift_"});
+        timing_statistics.time_NCC = ms({"patch", "ncc_bnb"});
+        timing_statistics.time_BNB_NCC = 0.0; timing_statistics.time_BNB_SIFT = 0.0;       // inside ncc_bnb
+        timing_statistics.time_Refinement = ms({"shift", "gn"});
+        timing_statistics.time_Clustering = ms({"cluster"});
+        timing_statistics.time_Post_NCC = ms({"ncc2_best"});
+        timing_statistics.time_Best = 0.0;                                                  // inside ncc2_best
+        timing_statistics.time_Finalize = ms({"compact"});
+        timing_statistics.total_time = timing_statistics.time_EP + timing_statistics.time_SIFT + timing_statistics.time_NCC +
+                                       timing_statistics.time_Refinement + timing_statistics.time_Clustering +
+                                       timing_statistics.time_Post_NCC + timing_statistics.time_Finalize;
     }
 
     // rebuild the per-left-edge containers for the survivors, in left-edge order (the order remove_empty_clusters keeps)
@@ -147,6 +172,8 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     std::vector<Eigen::Vector3d> g_left((size_t)n), g_right((size_t)n), lines((size_t)n);
     std::vector<std::pair<cv::Mat, cv::Mat>> desc((size_t)n), patches((size_t)n);
     std::vector<Stereo_Matching_Edge_Clusters> clusters((size_t)n);
+    // (the per-mate containers - cv::Mat pairs, EdgeCluster - are what the reference's data model costs on the host: built in parallel)
+#pragma omp parallel for schedule(static)
     for (int k = 0; k < n; ++k) {
         const int i = mates[k].left_index;                 // position in the focused list handed to the matcher
         focused[k] = pairs.focused_edge_indices[i];
@@ -157,7 +184,7 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
         const Eigen::Vector3d x(L[i].x, L[i].y, 1.0);     // CalculateEpipolarLine (:10-20)
         lines[k] = F21 * x;
         patches[k] = patch_pair(&pp[(size_t)k * 49], &pm[(size_t)k * 49]);
-        if (!dl.empty()) desc[k] = descriptor_pair(&dl[(size_t)k * 256]);
+        if (sift) desc[k] = descriptor_pair(&dl[(size_t)k * 256]);
         EdgeCluster ec;
         ec.center_edge = Edge(cv::Point2d(mates[k].rx, mates[k].ry), mates[k].rtheta, false, 0);   // :39 / EdgeClusterer.cpp:243
         ec.center_edge.index = -1;                         // uninitialised in the reference (cpu_toed.hpp:35)
@@ -193,7 +220,9 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
     final_stereo_edge_pairs.resize(n);
     if (n == 0) { std::cout << "Size of finalized stereo edge pairs = 0" << std::endl; return; }
 
-    // right patches of every mate from the UNDISTORTED right image (:1580-1582, :1622), one batched call
+    // right patches (UNDISTORTED right image, :1580-1582, :1622) and right descriptor pairs (:1627-1635) of every mate: the
+    // matching call computed them while the images were on the device; they are recomputed here only when this is not the
+    // result that call produced (another frame, or clusters edited in between)
     const cv::Mat& Rimg = pairs.stereo_frame->right_image_undistorted;
     const int W = Rimg.cols, H = Rimg.rows;
     std::vector<ebvo_edge> Rm(n);
@@ -201,19 +230,29 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         const Edge& e = pairs.matching_edge_clusters[i].edge_clusters[0].center_edge;
         Rm[i] = ebvo_edge{e.location.x, e.location.y, e.orientation, (int)i, 0};
     }
-    std::vector<float> pp(n * 49), pm(n * 49);
-    ebvo_ctx* ctx = ebvo_dropin::context(W, H, (int)n);
+    ebvo_dropin::Lease lease(W, H, (int)n);
+    ebvo_ctx* ctx = lease.ctx;
     if (!ctx) { final_stereo_edge_pairs.clear(); return; }
-    const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(Rimg.data, H, W, Rimg.step);
-    int rc = ebvo_edge_patches(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, pp.data(), pm.data());
-    if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); final_stereo_edge_pairs.clear(); return; }
-    std::vector<float> dr;                                 // right descriptors of the mates (:1627-1635)
-    if (ebvo_dropin::sift_enabled()) {
-        dr.resize(n * 256);
-        rc = ebvo_sift_descriptors(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, dr.data());
-        if (rc != EBVO_OK) { log_error("ebvo_sift_descriptors", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+    const bool sift = ebvo_dropin::sift_enabled();
+    ebvo_dropin::FinalizeCache& fin = ebvo_dropin::shared().fin;
+    const bool cached = fin.frame == pairs.stereo_frame && fin.n == n && fin.x0 == Rm[0].x && fin.y0 == Rm[0].y && fin.x1 == Rm[n - 1].x &&
+                        fin.y1 == Rm[n - 1].y && fin.r_plus.size() >= n * 49 && (!sift || fin.r_desc.size() >= n * 256);
+    std::vector<float> pp_own, pm_own, dr_own;
+    const float *pp = fin.r_plus.data(), *pm = fin.r_minus.data(), *dr = sift ? fin.r_desc.data() : nullptr;
+    if (!cached) {
+        pp_own.resize(n * 49); pm_own.resize(n * 49);
+        const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(Rimg.data, H, W, Rimg.step);
+        int rc = ebvo_edge_patches(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, pp_own.data(), pm_own.data());
+        if (rc != EBVO_OK) { log_error("ebvo_edge_patches", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+        if (sift) {
+            dr_own.resize(n * 256);
+            rc = ebvo_sift_descriptors(ctx, Rund.data(), W, H, W, Rm.data(), (int)n, dr_own.data());
+            if (rc != EBVO_OK) { log_error("ebvo_sift_descriptors", ctx, rc); final_stereo_edge_pairs.clear(); return; }
+        }
+        pp = pp_own.data(); pm = pm_own.data(); dr = sift ? dr_own.data() : nullptr;
     }
 
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; ++i) {
         final_stereo_edge_pair mate;
         mate.left_edge = pairs.get_focused_edge_by_Stereo_Edge_Pairs_index(i);
@@ -221,7 +260,7 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         mate.left_edge_patches = pairs.left_edge_patches[i];
         mate.right_edge_patches = patch_pair(&pp[i * 49], &pm[i * 49]);
         mate.left_edge_descriptors = pairs.left_edge_descriptors[i];
-        if (!dr.empty()) mate.right_edge_descriptors = descriptor_pair(&dr[i * 256]);
+        if (dr) mate.right_edge_descriptors = descriptor_pair(&dr[i * 256]);
         mate.Gamma_in_left_cam_coord = pairs.Gamma_in_left_cam_coord[i];
         mate.Gamma_in_right_cam_coord = pairs.Gamma_in_right_cam_coord[i];
         mate.gt_right_location = pairs.GT_locations_from_left_edges[i];

@@ -55,7 +55,8 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
     const int W = current_frame.left_image.cols, H = current_frame.left_image.rows;
     const int n_kf = (int)KF.size(), n_cf = (int)CF.size();
     if (quads.empty() || n_kf == 0) return frame_metrics;
-    ebvo_ctx* ctx = ebvo_dropin::context(W, H, 1);
+    ebvo_dropin::Lease lease(W, H, 1);
+    ebvo_ctx* ctx = lease.ctx;
     if (!ctx) return frame_metrics;
 
     std::vector<unsigned char> mask((size_t)n_kf, 0);

@@ -49,7 +49,8 @@ double ncc_of(const cv::Mat& a, const cv::Mat& b)
     }
     float pa[49], pb[49];
     for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) { pa[i * 7 + j] = a.at<float>(i, j); pb[i * 7 + j] = b.at<float>(i, j); }
-    ebvo_ctx* ctx = ebvo_dropin::context(64, 64, 1024);
+    ebvo_dropin::Lease lease(64, 64, 1024);
+    ebvo_ctx* ctx = lease.ctx;
     if (!ctx) return std::nan("");
     double out = std::nan("");
     const int rc = ebvo_ncc_patch_pair(ctx, pa, pb, 1, &out);
@@ -67,7 +68,8 @@ std::pair<cv::Mat, cv::Mat> Utility::get_edge_patches(const Edge edge, const cv:
         std::printf("\033[1;31m[ERROR] get_edge_patches: the image must hold 8-bit integer values\033[0m\n");
         return {plus, minus};
     }
-    ebvo_ctx* ctx = ebvo_dropin::context(img.cols, img.rows, 1024);
+    ebvo_dropin::Lease lease(img.cols, img.rows, 1024);
+    ebvo_ctx* ctx = lease.ctx;
     if (!ctx) return {plus, minus};
     const ebvo_edge e{edge.location.x, edge.location.y, edge.orientation, edge.index, edge.frame_source};
     float pp[49], pm[49];
@@ -89,7 +91,7 @@ MatlabNCCComputer::MatlabNCCComputer() : initialized(false) {}
 MatlabNCCComputer::~MatlabNCCComputer() {}
 bool MatlabNCCComputer::initialize()
 {
-    initialized = ebvo_dropin::context(64, 64, 1024) != nullptr;     // no MATLAB engine is started: the GPU computes the NCC
+    initialized = ebvo_dropin::Lease(64, 64, 1024).ctx != nullptr;     // no MATLAB engine is started: the GPU computes the NCC
     return initialized;
 }
 double MatlabNCCComputer::computeNCC(const cv::Mat& patch1, const cv::Mat& patch2)

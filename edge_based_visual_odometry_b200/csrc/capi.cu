@@ -155,17 +155,24 @@ int upload_image(ebvo_ctx* ctx, uint8_t* base, int slot, const uint8_t* src, int
     return EBVO_OK;
 }
 
-int check_err_flag(ebvo_ctx* ctx)
+// Capacity overflows are recorded per FRAME (DevBatch::errFlag[f]): a dense or repetitive frame that exhausts a fixed
+// capacity fails alone, the other frames of the batch keep their results.  Returns EBVO_ERR_CAPACITY when any frame of
+// [0, nFrames) overflowed; `failed` (optional, nFrames entries) receives the per-frame codes.
+int check_err_flag(ebvo_ctx* ctx, int nFrames = 1, std::vector<int>* failed = nullptr)
 {
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, ctx->b.errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    nFrames = std::max(1, std::min(nFrames, ctx->maxB));
+    std::vector<int> flags((size_t)nFrames, 0);
+    CK(cudaMemcpyAsync(flags.data(), ctx->b.errFlag, sizeof(int) * nFrames, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
-    if (flag) {
-        int zero = 0;
-        cudaMemcpyAsync(ctx->b.errFlag, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->st);
+    int first = -1, count = 0;
+    for (int f = 0; f < nFrames; ++f) if (flags[f]) { if (first < 0) first = f; ++count; }
+    if (failed) *failed = flags;
+    if (first >= 0) {
+        cudaMemsetAsync(ctx->b.errFlag, 0, sizeof(int) * nFrames, ctx->st);
         static const char* what[] = {"", "edge capacity (max_edges) exceeded", "candidate pool exhausted", "more than 128 NCC survivors for one left edge",
                                      "more than 128 candidates entering the clusterer for one left edge"};
-        ctx->err = std::string("capacity: ") + what[flag < 5 ? flag : 0];
+        const int flag = flags[first];
+        ctx->err = std::string("capacity: ") + what[flag > 0 && flag < 5 ? flag : 0] + " (frame " + std::to_string(first) + (count > 1 ? ", " + std::to_string(count) + " frames in all" : "") + ")";
         return EBVO_ERR_CAPACITY;
     }
     return EBVO_OK;
@@ -387,7 +394,7 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     CK(dalloc(ctx, &b.c_score, (size_t)b.P * B)); CK(dalloc(ctx, &b.c_conf, (size_t)b.P * B));
     CK(dalloc(ctx, &b.c_owner, (size_t)b.P * B));
     CK(dalloc(ctx, &b.mates, (size_t)b.E * B)); CK(dalloc(ctx, &b.nMates, (size_t)B)); CK(dalloc(ctx, &b.mateFlag, (size_t)b.E * B));
-    CK(dalloc(ctx, &b.errFlag, (size_t)4)); CK(dalloc(ctx, &b.counters, (size_t)8 * B));
+    CK(dalloc(ctx, &b.errFlag, (size_t)B + 4)); CK(dalloc(ctx, &b.counters, (size_t)8 * B));
     CK(dalloc(ctx, &ctx->d_out, (size_t)b.E * B));
     if (ctx->params.sift_mode == 1) {
         b.blurStride = align_up((size_t)max_w * max_h, 64);
@@ -395,7 +402,7 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
         CK(dalloc(ctx, &b.desc8, (size_t)b.E * 256 * nImg));
     }
     CK(dalloc(ctx, &b.dF, (size_t)16));
-    CK(cudaMemsetAsync(b.errFlag, 0, 16, ctx->st));
+    CK(cudaMemsetAsync(b.errFlag, 0, sizeof(int) * ((size_t)B + 4), ctx->st));
     CK(cudaMemsetAsync(b.nE, 0, sizeof(int) * nImg, ctx->st));
     CK(cudaMemsetAsync(b.nMates, 0, sizeof(int) * B, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -501,9 +508,9 @@ static int run_match_with_dumps(ebvo_ctx* ctx, const double* F21, bool sift, int
     return EBVO_OK;
 }
 
-int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
+static int stereo_match_core(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
                       const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL, const ebvo_edge* R, int nR,
-                      const float* descL, const float* descR, ebvo_mate* out, int cap, int* n_mates)
+                      const float* descL, const float* descR)
 {
     if (!ctx || !calib || !L_raw || !R_raw || (nL && !L) || (nR && !R) || nL < 0 || nR < 0) return EBVO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -546,7 +553,70 @@ int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_r
     CK(cudaGetLastError());
     if ((rc = check_err_flag(ctx))) return rc;
     ctx->prof.collect();
+    return EBVO_OK;
+}
+
+
+int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
+                      const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL, const ebvo_edge* R, int nR,
+                      const float* descL, const float* descR, ebvo_mate* out, int cap, int* n_mates)
+{
+    int rc = stereo_match_core(ctx, calib, L_raw, R_raw, L_und, R_und, w, h, stride, L, nL, R, nR, descL, descR);
+    if (rc) return rc;
     return download_mates(ctx, 1, out, cap, n_mates);
+}
+
+int ebvo_stereo_match_full(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
+                           const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL, const ebvo_edge* R, int nR,
+                           ebvo_mate* out, int cap, int* n_mates, float* l_plus49, float* l_minus49, float* r_plus49, float* r_minus49,
+                           float* l_desc256, float* r_desc256)
+{
+    int rc = stereo_match_core(ctx, calib, L_raw, R_raw, L_und, R_und, w, h, stride, L, nL, R, nR, nullptr, nullptr);
+    if (rc) return rc;
+    int n = 0;
+    if ((rc = download_mates(ctx, 1, out, cap, &n))) return rc;
+    if (n_mates) *n_mates = n;
+    n = std::min(n, cap);
+    if (n == 0) return EBVO_OK;
+    const bool wantDesc = l_desc256 || r_desc256;
+    if (wantDesc && ctx->params.sift_mode != 1) { ctx->err = "descriptors need a context created with sift_mode = 1"; return EBVO_ERR_INVALID; }
+    const DevBatch& b = ctx->b;
+    // scratch: six coordinate arrays, four patch arrays, two descriptor arrays of n entries (stream-ordered, pooled by the driver)
+    double* xy = nullptr; float* pt = nullptr; float* ds = nullptr;
+    CK(cudaMallocAsync(&xy, sizeof(double) * 6 * (size_t)n, ctx->st));
+    CK(cudaMallocAsync(&pt, sizeof(float) * 4 * 49 * (size_t)n, ctx->st));
+    if (wantDesc) CK(cudaMallocAsync(&ds, sizeof(float) * 2 * 256 * (size_t)n, ctx->st));
+    double *lx = xy, *ly = xy + n, *lt = xy + 2 * (size_t)n, *rx = xy + 3 * (size_t)n, *ry = xy + 4 * (size_t)n, *rt = xy + 5 * (size_t)n;
+    launch_mates_to_edges(ctx->d_out, n, lx, ly, lt, rx, ry, rt, ctx->st);
+    // left patches from the RAW left image (Stereo_Matches.cpp:570-576), right patches from the UNDISTORTED right image (:1580-1582, :1622)
+    launch_edge_patches(ctx->d_raw, w, h, b.pitch, lx, ly, lt, n, ctx->dp.shift_mag, pt, pt + 49 * (size_t)n, ctx->st);
+    launch_edge_patches(b.und + b.imgStride, w, h, b.pitch, rx, ry, rt, n, ctx->dp.shift_mag, pt + 98 * (size_t)n, pt + 147 * (size_t)n, ctx->st);
+    if (wantDesc) {
+        // left descriptor pairs: those of the matched left edges, already computed for the SIFT gate (:655-689)
+        launch_gather_desc(b.desc8, ctx->d_out, n, ds, ctx->st);
+        // right descriptor pairs at the mates (:1627-1635): the right view's edge slots are free now, so the mates take their place
+        CK(cudaMemcpyAsync(b.ex + b.E, rx, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.ey + b.E, ry, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.eth + b.E, rt, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(b.nE + 1, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+        DevBatch v = b;
+        v.ex += b.E; v.ey += b.E; v.eth += b.E; v.nE += 1; v.blur += b.blurStride; v.desc8 += (size_t)b.E * 256;
+        launch_sift_desc(v, 1, ctx->st, &ctx->prof);
+        launch_desc_to_float(v.desc8, n, ds + 256 * (size_t)n, ctx->st);
+    }
+    CK(cudaGetLastError());
+    const size_t pb = sizeof(float) * 49 * (size_t)n;
+    if (l_plus49) CK(cudaMemcpyAsync(l_plus49, pt, pb, cudaMemcpyDeviceToHost, ctx->st));
+    if (l_minus49) CK(cudaMemcpyAsync(l_minus49, pt + 49 * (size_t)n, pb, cudaMemcpyDeviceToHost, ctx->st));
+    if (r_plus49) CK(cudaMemcpyAsync(r_plus49, pt + 98 * (size_t)n, pb, cudaMemcpyDeviceToHost, ctx->st));
+    if (r_minus49) CK(cudaMemcpyAsync(r_minus49, pt + 147 * (size_t)n, pb, cudaMemcpyDeviceToHost, ctx->st));
+    if (l_desc256) CK(cudaMemcpyAsync(l_desc256, ds, sizeof(float) * 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    if (r_desc256) CK(cudaMemcpyAsync(r_desc256, ds + 256 * (size_t)n, sizeof(float) * 256 * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    cudaFreeAsync(xy, ctx->st); cudaFreeAsync(pt, ctx->st);
+    if (ds) cudaFreeAsync(ds, ctx->st);
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->prof.collect();
+    return EBVO_OK;
 }
 
 // The same device view restricted to frames [f0, f0 + n): every per-image / per-frame base pointer advanced, so that
@@ -569,7 +639,7 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     v.cstart += F0 * E; v.ccount += F0 * E; v.poolUsed += F0;
     v.c_ridx += F0 * P; v.c_x += F0 * P; v.c_y += F0 * P; v.c_th += F0 * P; v.c_score += F0 * P; v.c_conf += F0 * P; v.c_owner += F0 * P;
     v.mates += F0 * E; v.nMates += F0; v.mateFlag += F0 * E;
-    v.counters += F0 * 8;
+    v.counters += F0 * 8; v.errFlag += F0;
     if (v.blur) v.blur += i0 * b.blurStride;
     if (v.desc8) v.desc8 += i0 * E * 256;
     return v;
@@ -645,7 +715,7 @@ int ebvo_batch_sync(ebvo_ctx* ctx)
 {
     if (!ctx) return EBVO_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->st));
-    int rc = check_err_flag(ctx);
+    int rc = check_err_flag(ctx, ctx->curFrames);
     ctx->prof.collect();
     return rc;
 }
@@ -749,7 +819,13 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
     }
     if ((rc = download(nsb - 1))) return rc;
     CK(cudaStreamSynchronize(ctx->stOut));
-    if ((rc = check_err_flag(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->st)); CK(cudaStreamSynchronize(ctx->st2));
+    {   // a frame that exhausted a capacity fails ALONE: its count becomes -1, every other frame keeps its mates
+        std::vector<int> failed;
+        rc = check_err_flag(ctx, n_frames, &failed);
+        if (rc && n_mates) for (int f = 0; f < n_frames; ++f) if (failed[f]) n_mates[f] = -1;
+        if (rc) { ctx->prof.collect(); return rc; }
+    }
     ctx->prof.collect();
     return over;
 }

@@ -61,7 +61,7 @@ struct DevBatch {
     int* c_owner;                         // [frame][P] left-edge index of a live pool slot, -1 for dead slots
     ebvo_mate* mates; int* nMates;        // [frame][E], [frame]
     int* mateFlag;                        // [frame][E]
-    int* errFlag;                         // single int: capacity overflows
+    int* errFlag;                         // [frame] capacity overflows (0 = none): only the frame that overflowed is reported as failed
     unsigned long long* counters;         // [frame][8] work counters (s3 pairs, ncc pairs, gn pairs, gn iters, ncc2 pairs ...)
     const float* descL; const float* descR; // optional caller-supplied SIFT descriptors (frame 0 only), may be null
     float* blur; size_t blurStride;         // sift_mode 1: Gaussian-blurred float images [img][H*W] (descriptor image of cv::SIFT)
@@ -88,6 +88,10 @@ void launch_toed(const DevBatch& b, const DevParams& p, int nImages, cudaStream_
 void launch_match(const DevBatch& b, const DevParams& p, const double* F21 /*host 9*/, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
 void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, struct Prof* prof);
 void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);
+void launch_sift_desc(const DevBatch& b, int nImages, cudaStream_t st, struct Prof* prof);
+void launch_mates_to_edges(const ebvo_mate* m, int n, double* lx, double* ly, double* lt, double* rx, double* ry, double* rt, cudaStream_t st);
+void launch_gather_desc(const uint8_t* desc8, const ebvo_mate* m, int n, float* out, cudaStream_t st);
+void launch_desc_to_float(const uint8_t* desc8, int n, float* out, cudaStream_t st);
 void launch_undistort(const uint8_t* src, int srcPitch, uint8_t* dst, int dstPitch, int W, int H, const double K[9], const double dist[4], cudaStream_t st);   // undistort.cu   // blur + descriptors of every edge (sift.cu)
 void upload_toed_tables();
 void upload_sift_tables();

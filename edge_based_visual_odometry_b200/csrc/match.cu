@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams
         if (lane == 0 && n > 0) start = atomicAdd(&b.poolUsed[f], n);
         start = __shfl_sync(FULL, start, 0);
         if (n > 0 && start + n > b.P) {  // pool exhausted
-            if (lane == 0) atomicExch(b.errFlag, 2);
+            if (lane == 0) atomicExch(b.errFlag + f, 2);
             n = 0;
         }
         __syncwarp();
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams
             }
             ns += __popc(m);
         }
-        if (ns > MAXC) { if (lane == 0) atomicExch(b.errFlag, 3); ns = MAXC; }
+        if (ns > MAXC) { if (lane == 0) atomicExch(b.errFlag + f, 3); ns = MAXC; }
         __syncwarp();
         if (dumps) {
             for (int k = lane; k < ns; k += 32) { int r = s_ri[w][k]; dump_put(b.dump[DUMP_S6], st + k, r, exR[r], eyR[r], ethR[r], s_sc[w][k]); }
@@ -1675,7 +1675,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
         int n = ccount[i];
         const bool mid = n <= 48 && n <= p.clus_small;
         if (CAP < MAXC ? !mid : (mid || n <= small)) continue;      // the other launch's set (or already clustered by it)
-        if (n > CAP) { if (lane == 0) atomicExch(b.errFlag, 4); n = CAP; }
+        if (n > CAP) { if (lane == 0) atomicExch(b.errFlag + f, 4); n = CAP; }
         const int st = cstart[i];
         for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
         __syncwarp();
@@ -1995,6 +1995,33 @@ void launch_edge_patches(const uint8_t* d_img, int w, int h, int pitch, const do
                          double shift, float* plus, float* minus, cudaStream_t st)
 {
     if (n > 0) edge_patches_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_img, w, h, pitch, ex, ey, eth, n, shift, plus, minus);
+}
+
+// finalisation helpers of ebvo_stereo_match_full: coordinate arrays of the mates, descriptor gathers
+__global__ void mates_to_edges_kernel(const ebvo_mate* m, int n, double* lx, double* ly, double* lt, double* rx, double* ry, double* rt)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const ebvo_mate a = m[k];
+    lx[k] = a.lx; ly[k] = a.ly; lt[k] = a.ltheta; rx[k] = a.rx; ry[k] = a.ry; rt[k] = a.rtheta;
+}
+void launch_mates_to_edges(const ebvo_mate* m, int n, double* lx, double* ly, double* lt, double* rx, double* ry, double* rt, cudaStream_t st)
+{
+    if (n > 0) mates_to_edges_kernel<<<(n + 127) / 128, 128, 0, st>>>(m, n, lx, ly, lt, rx, ry, rt);
+}
+__global__ void gather_desc_kernel(const uint8_t* desc8, const ebvo_mate* m, int n, float* out)   // one CTA of 256 threads per mate
+{
+    const int k = blockIdx.x;
+    if (k >= n) return;
+    out[(size_t)k * 256 + threadIdx.x] = (float)desc8[(size_t)(m ? m[k].left_index : k) * 256 + threadIdx.x];
+}
+void launch_gather_desc(const uint8_t* desc8, const ebvo_mate* m, int n, float* out, cudaStream_t st)
+{
+    if (n > 0) gather_desc_kernel<<<n, 256, 0, st>>>(desc8, m, n, out);
+}
+void launch_desc_to_float(const uint8_t* desc8, int n, float* out, cudaStream_t st)
+{
+    if (n > 0) gather_desc_kernel<<<n, 256, 0, st>>>(desc8, nullptr, n, out);
 }
 
 __global__ void ncc_pairs_kernel(const float* p1, const float* p2, int n, double* out)

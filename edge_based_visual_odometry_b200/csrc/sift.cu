@@ -183,6 +183,15 @@ __global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
     }
 }
 
+void launch_sift_desc(const DevBatch& b, int nImages, cudaStream_t st, Prof* prof)   // descriptors only: the blurred images exist already
+{
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int gx = (sms * 16 + nImages - 1) / nImages;
+    if (gx < 1) gx = 1;
+    EBVO_KERNEL(prof, "sift_desc", st, (sift_desc_kernel<<<dim3(gx, nImages), 128, 0, st>>>(b)));
+}
+
 void launch_sift(const DevBatch& b, int nImages, cudaStream_t st, Prof* prof)
 {
     dim3 gB((b.W + 31) / 32, (b.H + 31) / 32, nImages);

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(1024) toed_scan_kernel(DevBatch b)
     if (tid == 1023) {
         int total = excl;
         rowoff[b.H2] = total;
-        if (total > b.E) { atomicExch(b.errFlag, 1); total = b.E; }
+        if (total > b.E) { atomicExch(b.errFlag + (img >> 1), 1); total = b.E; }
         b.nE[img] = total;
     }
 }

@@ -162,6 +162,18 @@ int ebvo_stereo_match(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_r
                       const ebvo_edge* R, int nR, const float* descL, const float* descR, ebvo_mate* out, int cap,
                       int* n_mates);
 
+/* ebvo_stereo_match followed, in the SAME call and on the images already on the device, by everything the reference's
+ * get_Stereo_Edge_Pairs leaves behind per surviving left edge and finalize_stereo_edge_mates adds per mate
+ * (Stereo_Matches.cpp:570-576, 655-689, 1578-1653): the "+"/"-" 7x7 patches of the matched left edge from the RAW left image
+ * (l_plus49 / l_minus49, 49 floats per mate), the mate's patches from the UNDISTORTED right image (r_plus49 / r_minus49) and -
+ * for a context created with sift_mode = 1 - the two 128-entry descriptors of the left edge and of the mate (l_desc256 /
+ * r_desc256, 256 floats per mate).  Any of the six outputs may be NULL; they hold `cap` entries.  One upload of the four
+ * images and one synchronisation per frame instead of the five calls the members would otherwise make. */
+int ebvo_stereo_match_full(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_raw, const uint8_t* R_raw, const uint8_t* L_und,
+                           const uint8_t* R_und, int w, int h, int stride, const ebvo_edge* L, int nL, const ebvo_edge* R, int nR,
+                           ebvo_mate* out, int cap, int* n_mates, float* l_plus49, float* l_minus49, float* r_plus49, float* r_minus49,
+                           float* l_desc256, float* r_desc256);
+
 /* Pipeline::prepare_Stereo_Images edge part + get_Stereo_Edge_Correspondences (src/Pipeline.cpp:93-131):
  * TOED on both views + matching, edges stay on the device.  Optional edge outputs may be NULL. */
 int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_img, const uint8_t* R_img, int w, int h,
@@ -170,7 +182,10 @@ int ebvo_stereo_frame(ebvo_ctx* ctx, const ebvo_calib* calib, const uint8_t* L_i
 
 /* Batch of independent stereo frames (the StereoIterator::getNext loop of cmd/main_VO.cpp:99-113 with
  * frames already in memory).  L_imgs/R_imgs: n_frames host pointers.  out: n_frames*cap mates;
- * n_mates: n_frames counts.  Host buffers in, host buffers out (copies are part of the call). */
+ * n_mates: n_frames counts.  Host buffers in, host buffers out (copies are part of the call).
+ * Capacities (max_edges per image, the candidate pool of 8 x max_edges per frame, 128 NCC survivors / clusterer inputs per left
+ * edge) are checked PER FRAME: a frame that exhausts one is reported with n_mates[f] = -1 and the call returns
+ * EBVO_ERR_CAPACITY (ebvo_last_error names the first such frame), while every other frame of the batch keeps its mates. */
 int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
                       const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, int cap, int* n_mates);
 

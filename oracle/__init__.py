@@ -67,7 +67,7 @@ _SREF = None
 
 
 def stereo_ref_lib():
-    """oracle/_ref/libstereo_ref.so: the UNMODIFIED reference stereo sources compiled in place against oracle/ref_shim."""
+    """oracle/_ref/libstereo_ref.so: the UNMODIFIED reference stereo sources compiled in place against third_party_shim."""
     global _SREF
     if _SREF is None:
         build()

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): drives the UNMODIFIED reference stereo sources
 //   /root/reference/src/Stereo_Matches.cpp, src/utility.cpp, src/EdgeClusterer.cpp
-// compiled in place against oracle/ref_shim (mini OpenCV / Eigen / yaml-cpp stand-ins) -> oracle/_ref/libstereo_ref.so.
+// compiled in place against third_party_shim (mini OpenCV / Eigen / yaml-cpp stand-ins) -> oracle/_ref/libstereo_ref.so.
 // Purpose: pin oracle/stereo_oracle.cpp (the restatement) against the reference's own control flow and arithmetic,
 // stage by stage (tests/test_oracle_stereo.py, golden fixture tests/golden/stereo_ref_small.npz).
 //

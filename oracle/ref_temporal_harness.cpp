@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): drives the UNMODIFIED reference quad-tracking source
 //   /root/reference/src/Temporal_Matches.cpp (+ src/utility.cpp, src/EdgeClusterer.cpp)
-// compiled in place against oracle/ref_shim -> oracle/_ref/libtemporal_ref.so.
+// compiled in place against third_party_shim -> oracle/_ref/libtemporal_ref.so.
 // Purpose: pin oracle/temporal_oracle.inl (the restatement) against the reference's own control flow and arithmetic,
 // stage by stage (tests/test_oracle_temporal.py, golden fixture tests/golden/temporal_ref_small.npz).
 //

@@ -6,7 +6,7 @@
 #include <cstring>
 #include <memory>
 #include <omp.h>
-#include <opencv2/opencv.hpp>          // the shim in oracle/ref_shim
+#include <opencv2/opencv.hpp>          // the shim in third_party_shim
 #include "toed/cpu_toed.hpp"           // the reference header, from /root/reference/include
 
 extern "C" {

@@ -6,7 +6,7 @@
  *
  * PARITY PINNING: pinned against the reference's OWN stereo sources.  /root/reference/src/Stereo_Matches.cpp,
  * src/utility.cpp and src/EdgeClusterer.cpp are compiled in place, unmodified, into oracle/_ref/libstereo_ref.so
- * (oracle/Makefile) against stand-in headers for the absent third-party libraries (oracle/ref_shim: a minimal
+ * (oracle/Makefile) against stand-in headers for the absent third-party libraries (third_party_shim: a minimal
  * cv::Mat/MatExpr/Sobel/mean/sum/dot, fixed-size Eigen matrices, a yaml-cpp stub) and driven stage by stage by
  * oracle/ref_stereo_harness.cpp in the order of get_Stereo_Edge_Pairs.  On the KITTI-shape pair (32.6 k edges per
  * view) every stage's candidate lists, the Gauss-Newton iterates, the cluster centres and the 27 095 final mates of

@@ -7,7 +7,7 @@
 * stereo_small.npz     : a 320x200 KITTI-calibrated synthetic pair, its reference TOED edges (both views) and
                          the oracle's stage counts + final mates (regression pin of the restatement itself).
 * stereo_ref_small.npz : the same pair through the REFERENCE'S OWN stereo code (oracle/_ref/libstereo_ref.so =
-                         Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in place against oracle/ref_shim,
+                         Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in place against third_party_shim,
                          driven by oracle/ref_stereo_harness.cpp): per-stage candidate lists and final mates.
 """
 import os, sys

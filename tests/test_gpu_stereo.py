@@ -304,6 +304,35 @@ def test_pipelined_batch_call_equals_the_resident_batch_path():
         assert np.array_equal(out[f, :n[f]], out[f % 5, :n[f % 5]])
 
 
+def test_capacity_overflow_fails_only_its_own_frame():
+    """A frame that exhausts a fixed capacity (here max_edges) is reported alone (n_mates = -1, EBVO_ERR_CAPACITY); the other
+    frames of the batch keep exactly the mates they get when run on their own."""
+    cal = synth.kitti_calib(320, 200)
+    sparse = [synth.stereo_pair(cal, s, density=0.3) for s in (1, 2)]
+    dense = synth.stereo_pair(cal, 3, density=4.0)
+    frames = [sparse[0], dense, sparse[1]]
+    ctx = _lib.Context(0, 320, 200, max_batch=3, max_edges=3072)
+    alone = []
+    for L, R in frames:
+        try:
+            alone.append(ctx.stereo_frame(_calib(cal), L, R)[0])
+        except _lib.EbvoError as e:
+            assert e.code == -4
+            alone.append(None)
+    assert alone[0] is not None and alone[2] is not None and alone[1] is None, [None if a is None else len(a) for a in alone]
+    out = np.zeros((3, 4000), _lib.MATE_DTYPE)
+    n = np.zeros(3, np.int32)
+    with pytest.raises(_lib.EbvoError) as e:
+        ctx.stereo_batch(_calib(cal), [f[0] for f in frames], [f[1] for f in frames], 4000, out, n)
+    assert e.value.code == -4 and "frame 1" in str(e.value)
+    assert n[1] == -1 and n[0] == len(alone[0]) and n[2] == len(alone[2])
+    assert np.array_equal(out[0, :n[0]], alone[0]) and np.array_equal(out[2, :n[2]], alone[2])
+    # the context stays usable
+    again, n2 = ctx.stereo_batch(_calib(cal), [sparse[0][0]], [sparse[0][1]], 4000)
+    ctx.close()
+    assert n2[0] == n[0] and np.array_equal(again[0, :n2[0]], alone[0])
+
+
 def test_multi_context_batch_entry_point():
     """ebvo_stereo_batch_multi splits a batch into contiguous blocks over several contexts (normally one per GPU; here
     as many devices as the box has, and two contexts on device 0 when there is only one) with one host thread each:

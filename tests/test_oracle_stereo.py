@@ -140,7 +140,7 @@ def test_full_stereo_invariants(golden_stereo):
 
 
 # ---- pin against the reference's own stereo code (Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in
-# ---- place against oracle/ref_shim; golden fixture generated by tests/golden/make_golden.py) --------------------------
+# ---- place against third_party_shim; golden fixture generated by tests/golden/make_golden.py) --------------------------
 import os
 
 GOLDEN_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stereo_ref_small.npz")
