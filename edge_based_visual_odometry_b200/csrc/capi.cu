@@ -367,7 +367,7 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     DevBatch& b = ctx->b;
     memset(&b, 0, sizeof b);
     const int B = max_batch, nImg = 2 * B;
-    b.E = ctx->E; b.P = ctx->P; b.NB = ctx->E / 32;
+    b.E = ctx->E; b.P = ctx->P; b.NB = (ctx->E + 7) / 8;   // index blocks of 8 right edges (match.cu: EB)
     const int tilesX = (max_w + TW - 1) / TW, tilesY = (max_h + TH - 1) / TH;
     b.imgStride = align_up((size_t)align_up(max_w, 16) * max_h, 256);
     b.maskStride = (size_t)(2 * tilesX) * (2 * TH * tilesY);
@@ -401,7 +401,9 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
         CK(dalloc(ctx, &b.blur, b.blurStride * nImg));
         CK(dalloc(ctx, &b.desc8, (size_t)b.E * 256 * nImg));
     }
-    CK(dalloc(ctx, &b.dF, (size_t)16));
+    b.YT = max_h + 3;
+    CK(dalloc(ctx, &b.wcur, (size_t)4 * B));
+    CK(dalloc(ctx, &b.ytab, (size_t)2 * b.YT * B));
     CK(cudaMemsetAsync(b.errFlag, 0, sizeof(int) * ((size_t)B + 4), ctx->st));
     CK(cudaMemsetAsync(b.nE, 0, sizeof(int) * nImg, ctx->st));
     CK(cudaMemsetAsync(b.nMates, 0, sizeof(int) * B, ctx->st));
@@ -484,7 +486,7 @@ static int run_match_with_dumps(ebvo_ctx* ctx, const double* F21, bool sift, int
     if ((rc = gate_stage(ctx, EBVO_STAGE_EPI, 0, F21, nL, rx, ry, rth))) return rc;
     if ((rc = gate_stage(ctx, EBVO_STAGE_DISP, 1, F21, nL, rx, ry, rth))) return rc;
     if ((rc = gate_stage(ctx, EBVO_STAGE_ORIENT, 2, F21, nL, rx, ry, rth))) return rc;
-    match_gate(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
+    match_gate(ctx->b, ctx->dp, F21, 1, ctx->st, &ctx->prof);
     if (sift) {
         if (ctx->b.siftDev) launch_sift(ctx->b, 2, ctx->st, &ctx->prof);
         match_sift(ctx->b, ctx->dp, 1, ctx->st, &ctx->prof);
@@ -634,9 +636,9 @@ static DevBatch frame_view(const DevBatch& b, int f0, int n)
     if (v.pk16) v.pk16 += F0 * b.gStride;
     if (v.pk) v.pk += F0 * b.gStride;
     v.npatch += i0 * E * NPF; v.pflag += i0 * E;
-    v.blk += F0 * b.NB; v.pmax += F0 * b.NB; v.smin += F0 * b.NB;
+    v.blk += F0 * b.NB; v.pmax += F0 * b.NB; v.smin += F0 * b.NB; v.ytab += F0 * 2 * b.YT;
     v.lines += F0 * E * 8;
-    v.cstart += F0 * E; v.ccount += F0 * E; v.poolUsed += F0;
+    v.cstart += F0 * E; v.ccount += F0 * E; v.poolUsed += F0; v.wcur += F0 * 4;
     v.c_ridx += F0 * P; v.c_x += F0 * P; v.c_y += F0 * P; v.c_th += F0 * P; v.c_score += F0 * P; v.c_conf += F0 * P; v.c_owner += F0 * P;
     v.mates += F0 * E; v.nMates += F0; v.mateFlag += F0 * E;
     v.counters += F0 * 8; v.errFlag += F0;

@@ -57,6 +57,7 @@ struct DevBatch {
     double* lines;                        // [frame][E][8]: a, b, c, dirx, diry, sin(thL), cos(thL), pad
     int *cstart, *ccount;                 // [frame][E]
     int* poolUsed;                        // [frame]
+    int* wcur;                            // [frame][4] work cursors of the list-driven clusterer launches (zeroed per run)
     int* c_ridx; double *c_x, *c_y, *c_th, *c_score, *c_conf;  // [frame][P]
     int* c_owner;                         // [frame][P] left-edge index of a live pool slot, -1 for dead slots
     ebvo_mate* mates; int* nMates;        // [frame][E], [frame]
@@ -67,7 +68,7 @@ struct DevBatch {
     float* blur; size_t blurStride;         // sift_mode 1: Gaussian-blurred float images [img][H*W] (descriptor image of cv::SIFT)
     uint8_t* desc8;                         // sift_mode 1: descriptors computed on the device [img][E][2][128]
     int siftDev;                            // != 0: use desc8 (all frames) instead of descL/descR
-    double* dF;                           // device copy of F21 (9 doubles, row-major)
+    int* ytab; int YT;                    // [frame][2][YT] first index block per integer image row (bounds_kernel -> gate_kernel), YT = H + 3
     int dumps;                            // != 0: fill dump[] for frame 0
     DumpBuf dump[DUMP_COUNT];
 };
@@ -109,7 +110,7 @@ void launch_compact(const DevBatch& b, int nFrames, ebvo_mate* d_out, int stride
 void launch_pack(const ebvo_mate* src, int srcStride, const int* nMates, int nFrames, ebvo_mate* dst, long long cap, int* offsets, cudaStream_t st, struct Prof* prof);
 // individual matching stages (used by the stage-dump path, which snapshots between them)
 void match_prologue(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, struct Prof* prof);
-void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
+void match_gate(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, struct Prof* prof);
 void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);
 void match_ncc(const DevBatch& b, const DevParams& p, int nFrames, bool sift, cudaStream_t st, struct Prof* prof);
 void match_gn(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, struct Prof* prof);

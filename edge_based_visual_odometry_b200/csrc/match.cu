@@ -27,6 +27,7 @@ constexpr int MAXC = 128;     // max candidates per left edge held in shared mem
 constexpr int WPB = 4;        // warps per block in the warp-per-item kernels
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int GEO = 8;        // doubles per left edge in DevBatch::lines: a, b, c, dirx, diry, sin(thL), cos(thL), pad
+constexpr int EB = 8;         // right edges per index block (bounds_kernel / gate_kernel): DevBatch::NB = E / EB
 
 // 64-bit shuffles without the `asm volatile` register moves of the CUDA header's double overloads (those cost two MOVs per
 // shuffle that ptxas may not remove: 6 % of the Gauss-Newton kernel's instructions); pure data movement, same values.
@@ -110,34 +111,37 @@ __global__ void sobel_kernel(DevBatch b)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Bounding intervals of 32-edge blocks of the right edge list + monotone envelopes for binary search.
-// The TOED list is in row-major interp order, so blocks are thin horizontal bands; any order is still correct.
+// Bounding intervals of EB-edge blocks of the right edge list + monotone envelopes for the search.
+// The TOED list is in row-major interp order, so blocks are short runs along image rows; any order is still correct.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) bounds_kernel(DevBatch b)
 {
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = 2 * f + 1;
     const int nR = b.nE[img];
-    const int nblk = (nR + 31) >> 5;
+    const int nblk = (nR + EB - 1) / EB;
     const double* ex = b.ex + (size_t)img * b.E;
     const double* ey = b.ey + (size_t)img * b.E;
     float4* blk = b.blk + (size_t)f * b.NB;
     float* pmax = b.pmax + (size_t)f * b.NB;
     float* smin = b.smin + (size_t)f * b.NB;
-    for (int k = warp; k < nblk; k += 32) {
-        int e = k * 32 + lane;
+    // four blocks of EB = 8 consecutive edges per warp pass: the TOED list is in row-major interp order, so a block is a short
+    // run along one image row (x span ~ 100 px); 32-edge blocks span a third of the row and made the x window nearly useless
+    for (int k4 = warp * 4; k4 < nblk; k4 += 128) {
+        const int k = k4 + (lane >> 3);
+        const int e = k * EB + (lane & 7);
         float ylo = CUDART_INF_F, yhi = -CUDART_INF_F, xlo = CUDART_INF_F, xhi = -CUDART_INF_F;
-        if (e < nR) {
+        if (k < nblk && e < nR) {
             double x = ex[e], y = ey[e];
             ylo = __double2float_rd(y); yhi = __double2float_ru(y);
             xlo = __double2float_rd(x); xhi = __double2float_ru(x);
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
+        for (int o = 4; o; o >>= 1) {
             ylo = fminf(ylo, __shfl_xor_sync(FULL, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(FULL, yhi, o));
             xlo = fminf(xlo, __shfl_xor_sync(FULL, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(FULL, xhi, o));
         }
-        if (lane == 0) blk[k] = make_float4(ylo, yhi, xlo, xhi);
+        if ((lane & 7) == 0 && k < nblk) blk[k] = make_float4(ylo, yhi, xlo, xhi);
     }
     __syncthreads();
     // prefix max of yhi, suffix min of ylo (serial per chunk + block scan; nblk <= NB)
@@ -165,11 +169,30 @@ __global__ void __launch_bounds__(1024) bounds_kernel(DevBatch b)
         int j = nblk - 1 - (tid * per + k);
         if (j >= 0) { runmn = fminf(runmn, blk[j].x); smin[j] = runmn; }
     }
+    __syncthreads();
+    // per-row lookup tables on the two monotone envelopes (binary search per integer y; the gate reads one entry each)
+    int* yt = b.ytab + (size_t)f * 2 * b.YT;
+    for (int k = tid; k < b.YT; k += 1024) {
+        const float key = (float)k;
+        int lo = 0, hi = nblk;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pmax[mid] >= key) hi = mid; else lo = mid + 1; }
+        yt[k] = lo;
+        lo = 0; hi = nblk;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (smin[mid] > key) hi = mid; else lo = mid + 1; }
+        yt[b.YT + k] = lo;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Gates.  mode 0: S1 only; 1: S1+S2; 2: S1+S2+S3 (production).  One warp per left edge.
 // ------------------------------------------------------------------------------------------------------
+struct Fmat { double v[9]; };     // F21, row-major: a kernel parameter (constant bank), not a device buffer shared between streams
+static Fmat fmat_of(const double* F21)
+{
+    Fmat F;
+    for (int k = 0; k < 9; ++k) F.v[k] = F21[k];
+    return F;
+}
 struct GateCtx {
     double a, b, c, nrm, xL, yL, thL;
     double ylo, yhi, xlo, xhi;
@@ -201,10 +224,11 @@ __device__ __forceinline__ bool gate_test(const GateCtx& g, const DevParams& p, 
     return ok;
 }
 
-__device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const DevParams& p, const double* F, int f, int i, int mode)
+__device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const DevParams& p, const Fmat& Fm, int f, int i, int mode)
 {
     const int imgL = 2 * f;
     g.xL = b.ex[(size_t)imgL * b.E + i]; g.yL = b.ey[(size_t)imgL * b.E + i]; g.thL = b.eth[(size_t)imgL * b.E + i];
+    const double* F = Fm.v;
     g.a = F[0] * g.xL + F[1] * g.yL + F[2] * 1.0;   // Stereo_Matches.cpp:15-16
     g.b = F[3] * g.xL + F[4] * g.yL + F[5] * 1.0;
     g.c = F[6] * g.xL + F[7] * g.yL + F[8] * 1.0;
@@ -222,32 +246,12 @@ __device__ __forceinline__ void gate_setup(GateCtx& g, const DevBatch& b, const 
         g.ylo = fmax(g.ylo, fmin(y1, y2) - m);
         g.yhi = fmin(g.yhi, fmax(y1, y2) + m);
     }
-    const int nR = b.nE[2 * f + 1];
-    const int nblk = (nR + 31) >> 5;
-    const float* pmax = b.pmax + (size_t)f * b.NB;
-    const float* smin = b.smin + (size_t)f * b.NB;
-    const float ylo = (float)g.ylo - 1e-3f, yhi = (float)g.yhi + 1e-3f;
-    // warp-cooperative 32-ary searches on the monotone envelopes (2 rounds of one coalesced load for ~1000 blocks instead
-    // of 2 x 10 dependent loads of a binary search replicated across the lanes)
-    const int lane = threadIdx.x & 31;
-    auto first_true = [&](const float* a, float key, bool strict) {
-        int lo = 0, end = nblk, ans = nblk;
-        while (lo < end) {
-            const int stride = (end - lo + 31) >> 5;
-            const int idx = lo + lane * stride;
-            const bool valid = idx < end;
-            const bool t = valid && (strict ? a[idx] > key : a[idx] >= key);
-            const unsigned m = __ballot_sync(FULL, t), mv = __ballot_sync(FULL, valid);
-            if (!m) { lo = lo + (__popc(mv) - 1) * stride + 1; continue; }      // every probe false: go on after the last one
-            const int L = __ffs(m) - 1;
-            ans = lo + L * stride; end = ans;
-            if (L == 0) break;
-            lo = lo + (L - 1) * stride + 1;
-        }
-        return ans;
-    };
-    g.blo = first_true(pmax, ylo, false);   // first block with pmax >= ylo
-    g.bhi = first_true(smin, yhi, true);    // first block with smin > yhi (exclusive end)
+    // block range from the per-row tables bounds_kernel built (one load each instead of two multi-round searches on the
+    // envelopes): ytab[0][k] = first block with pmax >= k, ytab[1][k] = first block with smin > k; floor / ceil keep it conservative
+    const int* yt = b.ytab + (size_t)f * 2 * b.YT;
+    const int klo = min(max((int)floorf((float)g.ylo - 1e-3f), 0), b.YT - 1), khi = min(max((int)ceilf((float)g.yhi + 1e-3f), 0), b.YT - 1);
+    g.blo = yt[klo];
+    g.bhi = yt[b.YT + khi];
 }
 
 // scan: calls emit(rank, ridx) in ascending ridx order for passing right edges; returns the count
@@ -262,37 +266,31 @@ __device__ __forceinline__ int gate_scan(const GateCtx& g, const DevBatch& b, co
     const float4* blk = b.blk + (size_t)f * b.NB;
     const float ylo = (float)g.ylo - 1e-3f, yhi = (float)g.yhi + 1e-3f, xlo = (float)g.xlo - 1e-3f, xhi = (float)g.xhi + 1e-3f;
     int count = 0;
-    // the bounds of 32 blocks are tested at once (one coalesced load instead of a chain of dependent ones), then the
-    // surviving blocks are scanned two at a time so that their edge loads are in flight together
+    // the bounds of 32 blocks (256 right edges) are tested at once, then the surviving blocks are scanned four at a time: lane
+    // l tests edge l & 7 of the (l >> 3)-th surviving block, so ascending lanes are ascending right-edge indices
     for (int k0 = g.blo; k0 < g.bhi; k0 += 32) {
         const int kk = k0 + lane;
         bool hit = false;
         if (kk < g.bhi) { const float4 bb = blk[kk]; hit = !(bb.y < ylo || bb.x > yhi || bb.w < xlo || bb.z > xhi); }
         unsigned bm = __ballot_sync(FULL, hit);
         while (bm) {
-            const int ka = k0 + __ffs(bm) - 1;
-            bm &= bm - 1;
-            int kb = -1;
-            if (bm) { kb = k0 + __ffs(bm) - 1; bm &= bm - 1; }
-            const int ea = ka * 32 + lane, eb = kb * 32 + lane;
-            const bool ina = ea < nR, inb = kb >= 0 && eb < nR;
-            double xa = 0, ya = 0, ta = 0, xb = 0, yb = 0, tb = 0;
-            if (ina) { xa = ex[ea]; ya = ey[ea]; ta = eth[ea]; }
-            if (inb) { xb = ex[eb]; yb = ey[eb]; tb = eth[eb]; }
-            const bool oka = ina && gate_test(g, p, mode, xa, ya, ta);
-            unsigned m = __ballot_sync(FULL, oka);
-            if (oka) emit(count + __popc(m & ((1u << lane) - 1)), ea);
-            count += __popc(m);
-            const bool okb = inb && gate_test(g, p, mode, xb, yb, tb);
-            m = __ballot_sync(FULL, okb);
-            if (okb) emit(count + __popc(m & ((1u << lane) - 1)), eb);
+            const unsigned pos = __fns(bm, 0, (lane >> 3) + 1);             // position of this lane group's block, 0xffffffff if none
+#pragma unroll
+            for (int r = 0; r < 4; ++r) bm &= bm - 1;                       // (bm & (bm - 1) of 0 stays 0)
+            const int e = (k0 + (int)pos) * EB + (lane & 7);
+            const bool in = pos != 0xffffffffu && e < nR;
+            double xa = 0, ya = 0, ta = 0;
+            if (in) { xa = ex[e]; ya = ey[e]; ta = eth[e]; }
+            const bool ok = in && gate_test(g, p, mode, xa, ya, ta);
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (ok) emit(count + __popc(m & ((1u << lane) - 1)), e);
             count += __popc(m);
         }
     }
     return count;
 }
 
-__global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams p, const double* __restrict__ F)
+__global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams p, const Fmat F)
 {
     __shared__ int s_buf[WPB][64];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -335,7 +333,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams
 }
 
 // debug variants for the stage dumps (frame 0): count, then fill at host-scanned offsets
-__global__ void __launch_bounds__(32 * WPB) gate_count_kernel(DevBatch b, DevParams p, const double* __restrict__ F, int mode, int* counts)
+__global__ void __launch_bounds__(32 * WPB) gate_count_kernel(DevBatch b, DevParams p, const Fmat F, int mode, int* counts)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nL = b.nE[0];
@@ -346,7 +344,7 @@ __global__ void __launch_bounds__(32 * WPB) gate_count_kernel(DevBatch b, DevPar
         if (lane == 0) counts[i] = n;
     }
 }
-__global__ void __launch_bounds__(32 * WPB) gate_fill_kernel(DevBatch b, DevParams p, const double* __restrict__ F, int mode, const int* offsets, int* ridx)
+__global__ void __launch_bounds__(32 * WPB) gate_fill_kernel(DevBatch b, DevParams p, const Fmat F, int mode, const int* offsets, int* ridx)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nL = b.nE[0];
@@ -619,7 +617,7 @@ __device__ __forceinline__ void load_patch_row(const float* __restrict__ np_, co
     P.p1 = q < 5 ? __ldg(o + 8 + q) : z; P.m1 = q < 5 ? __ldg(o + 21 + q) : z;
     P.flags = pf[e];
 }
-__global__ void __launch_bounds__(32 * WPB) ncc_bnb_kernel(DevBatch b, DevParams p, int use_sift)
+__global__ void __launch_bounds__(32 * WPB, 6) ncc_bnb_kernel(DevBatch b, DevParams p, int use_sift)
 {
     __shared__ double s_sc[WPB][MAXC];
     __shared__ double s_cf[WPB][MAXC];
@@ -1469,15 +1467,16 @@ __device__ int warp_cluster(const double* sx, const double* sy, const double* st
                 if (adm) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        unsigned long long wbits = adm[2 * i + h];
+                        unsigned long long wbits = adm[2 * i + h], live = wbits;
                         while (wbits) {
-                            const int j = __ffsll((long long)wbits) - 1 + 64 * h;
+                            const int bit = __ffsll((long long)wbits) - 1, j = bit + 64 * h;
                             wbits &= wbits - 1;
-                            if (lab[j] == li) continue;
+                            if (lab[j] == li) { live &= ~(1ull << bit); continue; }      // same cluster now, and for good: never looked at again
                             const double dx = xi - sx[j], dy = yi - sy[j];
                             const double d2 = dx * dx + dy * dy;
                             if (d2 < best) { best = d2; bj = j; }
                         }
+                        adm[2 * i + h] = live;
                     }
                 } else {
                     for (int j = 0; j < n; ++j) {
@@ -1652,8 +1651,10 @@ __global__ void __launch_bounds__(32 * WPB, 8) cluster8_kernel(DevBatch b, DevPa
 }
 
 // The warp-per-set launches work through the list cluster8_kernel left behind.  CAP = shared-memory capacity per warp.
-// <48> (3.4 KB per warp, 8 CTAs per SM) takes the sets with n <= min(48, clus_small); <MAXC> takes the others (it
-// recognises the sets the first launch has already replaced by their clusters: their count is small now).
+// <48> (4.6 KB per warp) takes the sets with n <= min(48, clus_small) and passes the others on in a second list (indices in the
+// mates staging area, count in nMates[f]: both free until ncc2_best / compact); <MAXC> takes that list.  Both decide pair
+// admissibility once (bit masks) and drop a neighbour from a point's mask for good once the two share a cluster: a rescan
+// costs the number of neighbours still in OTHER clusters instead of n.
 template <int CAP, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, DevParams p)
 {
@@ -1661,26 +1662,35 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
     __shared__ double s_ox[WPB][CAP], s_oy[WPB][CAP], s_ot[WPB][CAP];
     __shared__ int s_lab[WPB][CAP], s_csz[WPB][CAP];
     __shared__ double s_dk[WPB][CAP], s_gk[WPB][CAP];
-    __shared__ unsigned long long s_adm[CAP == MAXC ? WPB : 1][CAP == MAXC ? 2 * MAXC : 1];
+    __shared__ unsigned long long s_adm[WPB][2 * CAP];
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
     double *c_x = b.c_x + (size_t)f * b.P, *c_y = b.c_y + (size_t)f * b.P, *c_th = b.c_th + (size_t)f * b.P;
     const bool dumps = b.dumps && f == 0;
-    const int* big = b.mateFlag + (size_t)f * b.E;
-    const int nwork = (int)b.counters[(size_t)f * 8 + 6];
-    const int small = min(8, p.clus_small);
-    for (int wi = blockIdx.x * WPB + w; wi < nwork; wi += gridDim.x * WPB) {
-        const int i = big[wi];
+    const int* listA = b.mateFlag + (size_t)f * b.E;
+    int* listB = reinterpret_cast<int*>(b.mates + (size_t)f * b.E);
+    const int* work = CAP < MAXC ? listA : listB;
+    const int nwork = CAP < MAXC ? (int)b.counters[(size_t)f * 8 + 6] : b.nMates[f];
+    // sets are handed out one at a time from a per-frame cursor: their cost grows faster than n^2, so a static split leaves the
+    // kernel waiting for the warp that drew the largest ones
+    int* cursor = b.wcur + (size_t)f * 4 + (CAP < MAXC ? 0 : 1);
+    for (;;) {
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(cursor, 1);
+        wi = __shfl_sync(FULL, wi, 0);
+        if (wi >= nwork) break;
+        const int i = work[wi];
         int n = ccount[i];
-        const bool mid = n <= 48 && n <= p.clus_small;
-        if (CAP < MAXC ? !mid : (mid || n <= small)) continue;      // the other launch's set (or already clustered by it)
+        if (CAP < MAXC && (n > CAP || n > p.clus_small)) {          // left for the MAXC launch
+            if (lane == 0) listB[atomicAdd(&b.nMates[f], 1)] = i;
+            continue;
+        }
         if (n > CAP) { if (lane == 0) atomicExch(b.errFlag + f, 4); n = CAP; }
         const int st = cstart[i];
         for (int k = lane; k < n; k += 32) { s_x[w][k] = c_x[st + k]; s_y[w][k] = c_y[st + k]; s_t[w][k] = c_th[st + k]; }   // after the second shift
         __syncwarp();
-        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_csz[w], s_dk[w], s_gk[w], s_ox[w], s_oy[w], s_ot[w],
-                                     CAP == MAXC ? s_adm[CAP == MAXC ? w : 0] : nullptr);
+        const int ncl = warp_cluster(s_x[w], s_y[w], s_t[w], n, true, p, lane, s_lab[w], s_csz[w], s_dk[w], s_gk[w], s_ox[w], s_oy[w], s_ot[w], s_adm[w]);
         __syncwarp();
         for (int k = lane; k < ncl; k += 32) {
             c_x[st + k] = s_ox[w][k]; c_y[st + k] = s_oy[w][k]; c_th[st + k] = s_ot[w][k];
@@ -1694,7 +1704,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
 // S11 NCC of every cluster centre against the left patches (raw images, :1500) + S12 arg-max (first maximum wins, :941-951).
 // A quarter-warp per LEFT EDGE, four left edges per warp in lock step (a left edge has one or two cluster centres, so a
 // full warp per edge idles on memory latency and a quarter-warp per centre of one edge finds nothing to do).
-__global__ void __launch_bounds__(32 * WPB, 4) ncc2_best_kernel(DevBatch b, DevParams p)
+__global__ void __launch_bounds__(32 * WPB, 5) ncc2_best_kernel(DevBatch b, DevParams p)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int g = lane >> 3, q = lane & 7, base = lane & ~7;
@@ -1860,24 +1870,20 @@ void launch_sobel(const DevBatch& b, int nFrames, cudaStream_t st, Prof* prof)
     EBVO_KERNEL(prof, "sobel", st, (sobel_kernel<<<g, t, 0, st>>>(b)));
 }
 
-static const double* upload_F(const DevBatch& b, const double* F21, cudaStream_t st)
-{
-    cudaMemcpyAsync(b.dF, F21, 9 * sizeof(double), cudaMemcpyHostToDevice, st);
-    return b.dF;
-}
 
 void match_prologue(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, Prof* prof)
 {
     (void)p;
-    upload_F(b, F21, st);
     cudaMemsetAsync(b.poolUsed, 0, sizeof(int) * nFrames, st);
     cudaMemsetAsync(b.counters, 0, sizeof(unsigned long long) * 8 * nFrames, st);
+    cudaMemsetAsync(b.nMates, 0, sizeof(int) * nFrames, st);      // doubles as the count of the clusterer's second work list until compact writes it
+    cudaMemsetAsync(b.wcur, 0, sizeof(int) * 4 * nFrames, st);
     launch_sobel(b, nFrames, st, prof);
     EBVO_KERNEL(prof, "bounds", st, (bounds_kernel<<<nFrames, 1024, 0, st>>>(b)));
 }
-void match_gate(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
+void match_gate(const DevBatch& b, const DevParams& p, const double* F21, int nFrames, cudaStream_t st, Prof* prof)
 {
-    EBVO_KERNEL(prof, "gate", st, (gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, b.dF)));
+    EBVO_KERNEL(prof, "gate", st, (gate_kernel<<<warp_grid(nFrames), 32 * WPB, 0, st>>>(b, p, fmat_of(F21))));
 }
 void match_sift(const DevBatch& b, const DevParams& p, int nFrames, cudaStream_t st, Prof* prof)
 {
@@ -1920,7 +1926,7 @@ void launch_match(const DevBatch& b, const DevParams& p, const double* F21, int 
 {
     match_prologue(b, p, F21, nFrames, st, prof);
     if (sift && b.siftDev) launch_sift(b, 2 * nFrames, st, prof);
-    match_gate(b, p, nFrames, st, prof);
+    match_gate(b, p, F21, nFrames, st, prof);
     if (sift) match_sift(b, p, nFrames, st, prof);
     match_ncc(b, p, nFrames, sift, st, prof);
     match_gn(b, p, nFrames, st, prof);
@@ -1963,13 +1969,11 @@ void launch_pack(const ebvo_mate* src, int srcStride, const int* nMates, int nFr
 
 void launch_gate_count(const DevBatch& b, const DevParams& p, const double* F21, int mode, int* d_counts, cudaStream_t st)
 {
-    const double* dF = upload_F(b, F21, st);
-    gate_count_kernel<<<592, 32 * WPB, 0, st>>>(b, p, dF, mode, d_counts);
+    gate_count_kernel<<<592, 32 * WPB, 0, st>>>(b, p, fmat_of(F21), mode, d_counts);
 }
 void launch_gate_fill(const DevBatch& b, const DevParams& p, const double* F21, int mode, const int* d_offsets, int* d_ridx, cudaStream_t st)
 {
-    const double* dF = upload_F(b, F21, st);
-    gate_fill_kernel<<<592, 32 * WPB, 0, st>>>(b, p, dF, mode, d_offsets, d_ridx);
+    gate_fill_kernel<<<592, 32 * WPB, 0, st>>>(b, p, fmat_of(F21), mode, d_offsets, d_ridx);
 }
 void launch_snapshot(const DevBatch& b, int src, const int* d_offsets, int* ridx, double* x, double* y, double* th, double* score, cudaStream_t st)
 {
