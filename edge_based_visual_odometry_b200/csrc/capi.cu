@@ -92,7 +92,7 @@ namespace {
             char buf[512];                                                                         \
             snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
             ctx->err = buf;                                                                        \
-            return EBVO_ERR_CUDA;                                                                  \
+            return e__ == cudaErrorMemoryAllocation ? EBVO_ERR_NOMEM : EBVO_ERR_CUDA;              \
         }                                                                                          \
     } while (0)
 
@@ -355,15 +355,27 @@ int ebvo_create(ebvo_ctx** out, int device, int max_w, int max_h, int max_batch,
     *out = ctx;   // returned even on failure so that ebvo_last_error() can be read; caller destroys it
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    {   // the stream-ordered scratch of the quad-tracking and finalisation calls (cudaMallocAsync) stays in the device's pool between
+        // calls instead of going back to the driver at every synchronisation: after the first call the "allocations" are pointer bumps
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     {   // the quad-tracking call takes its scratch from the stream-ordered allocator: keep freed blocks in the pool between calls
         cudaMemPool_t mp; unsigned long long keep = ~0ull;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     CK(cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+    // per-device set-up (constant tables, opt-in shared memory, the TMA driver entry point): a device or driver that cannot grant
+    // them is reported HERE, not as a launch failure in some later call
+    cudaGetLastError();
     init_toed_device();
     init_match_device();
     if (ctx->params.sift_mode == 1) upload_sift_tables();
+    CK(cudaGetLastError());
     DevBatch& b = ctx->b;
     memset(&b, 0, sizeof b);
     const int B = max_batch, nImg = 2 * B;
@@ -802,10 +814,15 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         }
         return EBVO_OK;
     };
+    // an error return must not leave copies or kernels of this call in flight on any of the four streams
+    auto bail = [&](int r) {
+        cudaStreamSynchronize(ctx->stIn); cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st2); cudaStreamSynchronize(ctx->stOut);
+        return r;
+    };
     // the copy-in stream must not overwrite images a previous call's kernels may still read: calls are synchronous at return
-    if ((rc = upload(0))) return rc;
+    if ((rc = upload(0))) return bail(rc);
     for (int k = 0; k < nsb; ++k) {
-        if (k + 1 < nsb && (rc = upload(k + 1))) return rc;
+        if (k + 1 < nsb && (rc = upload(k + 1))) return bail(rc);
         const int f0 = k * SB, n = std::min(n_frames, f0 + SB) - f0;
         const DevBatch v = frame_view(b, f0, n);
         // sub-batches alternate between two compute streams: the tail of one sub-batch's kernels (a persistent kernel waits for
@@ -817,9 +834,9 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         launch_compact(v, n, ctx->d_out + (size_t)f0 * b.E, b.E, cs, &ctx->prof);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->evDone[k], cs));
-        if (k >= 1 && (rc = download(k - 1))) return rc;
+        if (k >= 1 && (rc = download(k - 1))) return bail(rc);
     }
-    if ((rc = download(nsb - 1))) return rc;
+    if ((rc = download(nsb - 1))) return bail(rc);
     CK(cudaStreamSynchronize(ctx->stOut));
     CK(cudaStreamSynchronize(ctx->st)); CK(cudaStreamSynchronize(ctx->st2));
     {   // a frame that exhausted a capacity fails ALONE: its count becomes -1, every other frame keeps its mates

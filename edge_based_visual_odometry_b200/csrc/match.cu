@@ -1849,11 +1849,15 @@ __global__ void snapshot_kernel(DevBatch b, int src, const int* offsets, int* ri
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
-static int g_sms = 0;     // SM count (every GPU of a box is the same model)
+static int g_sms = 0;     // SM count (every GPU of a box is the same model); set by init_match_device, i.e. before any launch
 
 void init_match_device()   // per-device function attributes, called by ebvo_create after cudaSetDevice
 {
     cudaFuncSetAttribute(gn_lerp64_kernel<GNL_PX, GNL_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 0) g_sms = sms;
 }
 
 static dim3 warp_grid(int nFrames)

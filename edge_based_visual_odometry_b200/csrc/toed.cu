@@ -17,6 +17,7 @@
 #include "ebvo_internal.cuh"
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <cuda.h>
 #include <math_constants.h>
 
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) toed_expand_kernel(DevBatch b)
 // those samples only, everything that reaches the edge list in FP64 and in the reference's own formulas: the gradient
 // (fx, fy) at the sample and its 8 neighbours (cpu_toed.cpp:200-222), the octant interpolation and parabola fit
 // (:418-510), the seven third-order responses and the orientation (:224-229).  The edge list then carries the
-// reference's FP64 values (measured |dx|, |dy| < 1e-11 px, |dtheta| < 1e-11 rad against the oracle instead of 5e-5 px /
+// reference's FP64 values (measured |dx|, |dy| < 1e-11 px, |dtheta| < 1e-11 rad against the FP64 CPU restatement instead of 5e-5 px /
 // 3e-5 rad for the FP32 values), so the matcher downstream sees the same input as the CPU path and the 0.1 % budget for
 // near-threshold flips is not spent on detector noise.  Separable form per edge: lane = image row (21 rows x 21
 // columns cover the 3 x 3 samples' 19 x 19 supports): 1-D row sums for the three sample columns (G, Gx; the 17-tap and
@@ -535,12 +536,13 @@ int make_toed_tensor_map(void* out128, const uint8_t* base, int W, int H, int pi
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
-    if (!encode) {
+    static std::once_flag once;      // contexts may be created from several host threads (one per GPU)
+    std::call_once(once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
-        encode = (EncodeFn)fn;
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn) encode = (EncodeFn)fn;
+    });
+    if (!encode) return -1;
     const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nImages};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)imgStride};
     const cuuint32_t box[3] = {(cuuint32_t)TMA_BOX_W, (cuuint32_t)IN_H, 1}, estr[3] = {1, 1, 1};

@@ -40,7 +40,18 @@ for name, (W, H) in (("eth3d_cables_2-shape 742x464", (742, 464)), ("kitti-shape
         ctx.temporal_quads(kf_imgs, cf_imgs, m0, m1)
     kt = {k: v[0] / args.steps for k, v in ctx.kernel_times().items() if k.startswith("tq_")}
     ctx.set_profiling(False)
-    line = dict(metric="quad-tracking frame pairs/s (keyframe -> current frame, grid + orientation + NCC + BNB + 2-D GN + clustering)",
+    # roofline of the dominant kernel (tq_gn, 2-D Gauss-Newton on both views, Temporal_Matches.cpp:735-851): per iteration 98 samples x
+    # 60 FP64 flop (coordinates, three four-corner blends rounded to float, residual, Huber weight, the five sums of the 2 x 2 normal
+    # equations) = 5.9 kflop, against the MEASURED DFMA throughput (profiles/r02_fma_peaks.json)
+    try:
+        fp64_peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_fma_peaks.json")))["fp64_fma_tflops"]
+    except Exception:
+        fp64_peak = None
+    gn_key = next((k for k in kt if k.startswith("tq_gn")), None)
+    ach = 5880.0 * cnt["gn_iterations"] / (kt[gn_key] * 1e-3) / 1e12 if gn_key and kt[gn_key] > 0 else None
+    roof = dict(kernel=gn_key, bound="fp64", algorithmic_flop_per_iteration=5880.0, iterations=cnt["gn_iterations"], achieved=ach, peak=fp64_peak, unit="TFLOP/s",
+                frac=(ach / fp64_peak) if (ach and fp64_peak) else None, avg_launch_ms=kt.get(gn_key), share_of_kernel_time=(kt[gn_key] / sum(kt.values())) if gn_key else None)
+    line = dict(roofline=roof, metric="quad-tracking frame pairs/s (keyframe -> current frame, grid + orientation + NCC + BNB + 2-D GN + clustering)",
                 workload=name, value=1.0 / t_e2e, unit="pairs/s", ms_per_pair=1e3 * t_e2e, timing="host clock around ebvo_temporal_quads, host buffers in and out",
                 kf_mates=int(len(m0)), cf_mates=int(len(m1)), quads=int(len(q)), counters=cnt,
                 kernels_ms={k: round(v, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])}, kernel_ms_total=round(sum(kt.values()), 4))

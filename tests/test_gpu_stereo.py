@@ -259,6 +259,32 @@ def test_4k_stress_shape_properties():
     assert np.array_equal(m1["lx"], Le["x"][m1["left_index"]])
 
 
+def test_4k_sparse_scene_stage_lists_exact_against_the_oracle():
+    """BASELINE config 5 at a density where the brute-force oracle still finishes (0.05: ~68 k edges per 3840x2160 view, about
+    20 s of CPU): the gate index (8-edge blocks, per-row tables), the pool capacities and every later stage at 4K geometry -
+    sloped-free rectified lines, 3840 px rows, block / table sizes 7x the KITTI ones - compared list by list, end to end
+    (device TOED -> device matcher): NO left edge may differ at any stage."""
+    cal = synth.kitti4k_calib()
+    L, R = synth.stereo_pair(cal, 7, density=0.05)
+    eL, _ = oracle.toed(L)
+    eR, _ = oracle.toed(R)
+    F21, _ = oracle.fundamental(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    res = oracle.stereo(L, R, eL, eR, F21)
+    ctx = _lib.Context(0, cal.width, cal.height, max_batch=1, max_edges=1 << 17)
+    gL, _ = ctx.toed(L)
+    gR, _ = ctx.toed(R)
+    assert len(gL) == len(eL) and len(gR) == len(eR) and len(eL) > 50000
+    assert np.hypot(gL["x"] - eL[:, 0], gL["y"] - eL[:, 1]).max() < 1e-9
+    ctx.set_stage_dumps(True)
+    m = ctx.stereo_match(_calib(cal), L, R, gL, gR)
+    frac_bad = _check_stages(ctx, res)
+    ctx.close()
+    assert frac_bad == 0
+    assert np.array_equal(m["left_index"], res.mate_left) and len(m) > 40000
+    assert np.hypot(res.mate_right[:, 0] - m["rx"], res.mate_right[:, 1] - m["ry"]).max() < 1e-3
+    assert np.abs(res.mate_right[:, 2] - m["rtheta"]).max() < 1e-4 and np.abs(res.mate_score - m["score"]).max() < 1e-5
+
+
 def test_against_reference_stereo_golden(gpu_ctx, golden_stereo):
     """CUDA path against output of the reference's OWN stereo code (tests/golden/stereo_ref_small.npz, produced by
     Stereo_Matches.cpp + utility.cpp + EdgeClusterer.cpp compiled in place; see tests/golden/make_golden.py)."""
