@@ -366,13 +366,19 @@ __global__ void __launch_bounds__(32 * WPB) gate_fill_kernel(DevBatch b, DevPara
 __device__ __forceinline__ float bilinear_u8(const uint8_t* __restrict__ I, int pitch, int W, int H, double px, double py)
 {
     if (!(px == px) || !(py == py)) return CUDART_NAN_F;
-    const double fx = floor(px), fy = floor(py);
-    if (fx < 0.0 || fy < 0.0 || fx == px || fy == py) return CUDART_NAN_F;
-    if (fx + 1.0 >= (double)W || fy + 1.0 >= (double)H) return CUDART_NAN_F;
-    const int ix = (int)fx, iy = (int)fy;
+    // floor and the integer cell without conversion instructions (the conversion unit - 16 lanes per SM and clock - is what bound
+    // the patch kernels: floor, double -> int and four u8 -> double per sample): a round-down add of 1.5 * 2^52 leaves floor(p) in
+    // the low word and, minus the constant, as a double (exact for |p| < 2^31; an infinite p fails the fx == px test below)
+    const double MAGIC = 6755399441055744.0;
+    const double tx = __dadd_rd(px, MAGIC), ty = __dadd_rd(py, MAGIC);
+    const double fx = tx - MAGIC, fy = ty - MAGIC;
+    const int ix = __double2loint(tx), iy = __double2loint(ty);
+    if (ix < 0 || iy < 0 || fx == px || fy == py) return CUDART_NAN_F;
+    if (ix + 1 >= W || iy + 1 >= H) return CUDART_NAN_F;
     const double wx2 = px - fx, wx1 = (fx + 1.0) - px, wy2 = py - fy, wy1 = (fy + 1.0) - py;   // denominators are exactly 1
     const uint8_t* r0 = I + (size_t)iy * pitch + ix;
-    const double v12 = (double)__ldg(r0), v22 = (double)__ldg(r0 + 1), v11 = (double)__ldg(r0 + pitch), v21 = (double)__ldg(r0 + pitch + 1);
+    auto u8d = [](uint8_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; };   // exact u8 -> double
+    const double v12 = u8d(__ldg(r0)), v22 = u8d(__ldg(r0 + 1)), v11 = u8d(__ldg(r0 + pitch)), v21 = u8d(__ldg(r0 + pitch + 1));
     const double f1 = wx1 * v11 + wx2 * v21;   // row ceil(y)
     const double f2 = wx1 * v12 + wx2 * v22;   // row floor(y)
     return (float)(wy2 * f1 + wy1 * f2);
