@@ -212,6 +212,9 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic frames per GPU (default: the batch size, i.e. every frame of the "
                     "batch is its own scene; smaller values are cycled to fill the batch)")
     ap.add_argument("--strong-frames", type=int, default=1000, help="frames of the ONE batch that the strong-scaling leg splits over the ranks (0 = skip)")
+    ap.add_argument("--strong-gather", default="host", choices=["host", "nccl"],
+                    help="final gather of the strong-scaling leg: host = every rank copies its records device -> host over its own PCIe link into one "
+                         "shared page-locked buffer (sharding.HostGather); nccl = device-to-device sends to rank 0, then one D2H (sharding.gather_packed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="kitti", choices=["kitti", "euroc", "4k"],
                     help="kitti = the BASELINE.json metric (default); euroc / 4k = BASELINE configs[1] / configs[4] shapes (extra measurements)")
@@ -346,11 +349,16 @@ def main():
         lo, hi = sharding.shard_range(FS, world, rank)
         nloc = hi - lo
         dev = torch.device("cuda", local_rank)
-        per_frame = float(nM.mean()) * 1.25 + 1024
+        pf = torch.tensor([float(nM.mean()) * 1.25 + 1024], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pf, op=dist.ReduceOp.MAX)      # one capacity for every rank
+        per_frame = float(pf.item())
         cap_rec = int(max(nloc, 1) * per_frame)
         packed = torch.empty((cap_rec, 64), dtype=torch.uint8, device=dev)
         offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        h_res = torch.empty((int(FS * per_frame), 64), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        use_host = world > 1 and args.strong_gather == "host"
+        h_res = torch.empty((int(FS * per_frame), 64), dtype=torch.uint8).pin_memory() if (rank == 0 and not use_host) else None
+        hg = sharding.HostGather(int(FS * per_frame) * 64, dist, tag="bench") if use_host else None
 
         def strong_pass():
             pos, counts = 0, []
@@ -362,15 +370,20 @@ def main():
             ct = (torch.cat(counts) if counts else torch.zeros(0, dtype=torch.int32)).to(dev)
             torch.cuda.synchronize()
             tg = time.perf_counter()
-            if world > 1:
-                allp, allc = sharding.gather_packed(packed[:pos], ct, FS, dist)
-            else:
-                allp, allc = packed[:pos], ct
             nrec = 0
-            if rank == 0:
-                nrec = int(allp.shape[0])
-                h_res[:nrec].copy_(allp, non_blocking=True)
-                allc.cpu()
+            if use_host:
+                allp, allc = hg.gather(packed[:pos], ct, FS)
+                if rank == 0:
+                    nrec = int(allp.shape[0])
+            else:
+                if world > 1:
+                    allp, allc = sharding.gather_packed(packed[:pos], ct, FS, dist)
+                else:
+                    allp, allc = packed[:pos], ct
+                if rank == 0:
+                    nrec = int(allp.shape[0])
+                    h_res[:nrec].copy_(allp, non_blocking=True)
+                    allc.cpu()
             torch.cuda.synchronize()
             return time.perf_counter() - tg, nrec
 
@@ -382,7 +395,9 @@ def main():
             gs, nrec = strong_pass()
             g_s += gs
         barrier()
-        strong = [(time.perf_counter() - t0) / reps, g_s / reps, nrec]
+        strong = [(time.perf_counter() - t0) / reps, g_s / reps, nrec, "host" if use_host else ("nccl" if world > 1 else "single device: one D2H")]
+        if hg is not None:
+            hg.close()
         del packed, h_res
 
     t = torch.tensor([ms_total, e2e_s * 1e3, (strong[0] if strong else 0.0) * 1e3], dtype=torch.float64, device="cuda")
@@ -484,8 +499,11 @@ def main():
             line["strong_scaling"] = {
                 "workload": "configs[2]: ONE %d-frame KITTI-shape batch split into contiguous blocks of ceil(F/N) frames per rank "
                             "(sharding.shard_range; %d distinct scenes per rank cycled), host images in (ebvo_stereo_batch, pipelined H2D), results packed "
-                            "on the device (ebvo_batch_pack), gathered to rank 0 at their exact size (counts all_gather + NCCL send/recv, "
-                            "sharding.gather_packed) and copied to pinned host memory - all inside the timed region" % (FS, len(base)),
+                            "on the device (ebvo_batch_pack) and gathered at their exact size into ONE host buffer of rank 0's process - %s - "
+                            "all inside the timed region" % (FS, len(base), {"host": "every rank copies its records device -> host over its own PCIe link into its "
+                            "slice of a shared page-locked buffer (sharding.HostGather; counts all_gather + barrier are the only exchange)",
+                            "nccl": "counts all_gather + NCCL send/recv to rank 0's GPU (sharding.gather_packed), then one D2H"}.get(strong[3], strong[3])),
+                "gather": strong[3],
                 "frames": FS, "n_gpus": world, "frames_per_gpu": -(-FS // world), "value": FS / (strong_ms / 1e3), "unit": "frames/s",
                 "ms": strong_ms, "gather_ms_rank0": strong[1] * 1e3, "gather_share": strong[1] * 1e3 / strong_ms if strong_ms else None,
                 "mate_records_gathered": strong[2], "bytes_gathered": strong[2] * 64,

@@ -53,6 +53,77 @@ def gather_packed(packed, counts, n_frames: int, dist, dst: int = 0):
     return out, allc[:n_frames]
 
 
+class HostGather:
+    """The final gather when the consumer is ONE host process (MotionTracker's sequential pose estimation stays on the host,
+    BASELINE.json north star): every rank copies its own mate records device -> host over ITS OWN PCIe link straight into
+    its slice of one shared, page-locked host buffer (POSIX shared memory mapped by all ranks of the box and registered with
+    CUDA), so the transfer runs on all links at once instead of funnelling 1.7 GB through rank 0's GPU and link; the only
+    exchange between the ranks is the per-frame counts (one small all_gather) and a barrier.  Collective constructor."""
+
+    def __init__(self, nbytes: int, dist, tag: str = "0", register: bool = True):
+        import mmap
+        import os
+        import torch
+        self.dist, self.nbytes = dist, int(nbytes)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.path = f"/dev/shm/ebvo_gather_{os.getuid()}_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        if self.rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        dist.barrier()
+        self.nbytes = os.path.getsize(self.path)          # rank 0's size is the buffer's size for every rank
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), self.nbytes)
+        self.buf = torch.frombuffer(self._mm, dtype=torch.uint8)
+        self._registered = False
+        if register and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), self.nbytes, 0)
+            self._registered = int(rc) == 0
+        dist.barrier()
+
+    def gather(self, packed, counts, n_frames: int, dst: int = 0):
+        """packed: [n_local, 64] uint8 (device or CPU), counts: int32 [f_local] on the same device.  Returns (records
+        [n_total, 64] - a view of the shared host buffer -, counts[n_frames]) on `dst`, (None, None) elsewhere."""
+        import torch
+        dist, world, rank = self.dist, self.world, self.rank
+        per = (n_frames + world - 1) // world
+        dev = packed.device
+        pad = torch.zeros(per, dtype=torch.int32, device=dev)
+        pad[:counts.numel()] = counts
+        allc = torch.empty(world * per, dtype=torch.int32, device=dev)
+        dist.all_gather(list(allc.view(world, per).unbind(0)), pad)
+        allc_h = allc.cpu()
+        per_rank = allc_h.view(world, per).sum(dim=1).tolist()
+        n, off = per_rank[rank], sum(per_rank[:rank])
+        if (off + n) * 64 > self.nbytes:
+            raise RuntimeError("HostGather buffer too small")
+        if n:
+            self.buf[off * 64:(off + n) * 64].view(n, 64).copy_(packed[:n], non_blocking=self._registered)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        dist.barrier()
+        if rank != dst:
+            return None, None
+        total = sum(per_rank)
+        return self.buf[:total * 64].view(total, 64), allc_h[:n_frames]
+
+    def close(self):
+        import os
+        import torch
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.buf.data_ptr())
+            self._registered = False
+        self.dist.barrier()
+        self.buf = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        self._f.close()
+        if self.rank == 0 and os.path.exists(self.path):
+            os.unlink(self.path)
+
+
 def gather_mates(local_mates, local_counts, n_frames: int, dist=None, device=None):
     """Padded convenience form for host arrays: local_mates [f_local, cap] (MATE_DTYPE), local_counts [f_local] int32.
     Returns (mates[n_frames, cap], counts[n_frames]) on rank 0 and (None, None) elsewhere; the exchange itself is

@@ -58,6 +58,13 @@ def _worker(rank, world, port, F, q):
     tot = ctx.batch_pack(packed.data_ptr(), packed.shape[0], offs.data_ptr())
     assert tot == int(nm.sum()) and offs.cpu().numpy()[-1] == tot
     allp, allc = sharding.gather_packed(packed[:tot], torch.from_numpy(nm.copy()).to(dev), F, dist)
+    # the same gather into one shared page-locked host buffer, every rank over its own PCIe link (sharding.HostGather)
+    hg = sharding.HostGather(64 * 200000, dist, tag="t")
+    hp, hc = hg.gather(packed[:tot], torch.from_numpy(nm.copy()).to(dev), F)
+    if rank == 0:
+        assert hg._registered and np.array_equal(hp.numpy(), allp.cpu().numpy()) and np.array_equal(hc.numpy(), allc.cpu().numpy())
+    del hp
+    hg.close()
     if rank == 0:
         one = _lib.Context(0, 480, 200, max_batch=F, max_edges=16384)
         ref, nref = one.stereo_batch(_calib(cal), Ls, Rs, cap=12000)

@@ -64,6 +64,45 @@ def _worker_packed(rank, world, port, F, q):
     dist.destroy_process_group()
 
 
+def _worker_host(rank, world, port, F, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(F, world, rank)
+    counts = np.array([(3 * f) % 7 for f in range(lo, hi)], np.int32)
+    rec = np.zeros(int(counts.sum()), _lib.MATE_DTYPE)
+    pos = 0
+    for k, f in enumerate(range(lo, hi)):
+        rec["left_index"][pos:pos + counts[k]] = 1000 * f + np.arange(counts[k])
+        pos += counts[k]
+    hg = sharding.HostGather(64 * 64, dist, tag="t", register=False)
+    for _ in range(2):          # reusable
+        allp, allc = hg.gather(torch.from_numpy(rec.view(np.uint8).reshape(-1, 64).copy()), torch.from_numpy(counts), F)
+    if rank == 0:
+        want_c = np.array([(3 * f) % 7 for f in range(F)], np.int32)
+        got = allp.numpy().copy().reshape(-1).view(_lib.MATE_DTYPE)["left_index"]
+        want = np.concatenate([1000 * f + np.arange(want_c[f]) for f in range(F)])
+        q.put(bool(np.array_equal(allc.numpy(), want_c) and np.array_equal(got, want)))
+    del allp
+    hg.close()
+    dist.destroy_process_group()
+
+
+def test_host_gather_shared_memory_world2_gloo():
+    """sharding.HostGather: every rank writes its records into its slice of one shared host buffer (on a GPU box: its own
+    device -> host copy over its own PCIe link); rank 0 reads all of them in global frame order."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_host, args=(r, 2, port, 7, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
 def test_gather_packed_world2_gloo_exact_sizes():
     """The exchange of a sharded batch: counts, then every rank's records at their exact size, global frame order kept
     (7 frames over 2 ranks: blocks of 4 and 3; frame 0 and frame 7k have no mates)."""
