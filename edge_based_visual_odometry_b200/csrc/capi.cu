@@ -671,14 +671,17 @@ static int run_frames(ebvo_ctx* ctx, const ebvo_calib* calib, int nFrames, int d
         }
     };
     if (nFrames >= 32 && !ctx->prof.enabled) {
-        // big batches: two slices on two compute streams forked from / joined into the context stream, so that the tail of
-        // every kernel (last wave, slowest warp of a persistent kernel) is filled by the other slice's work (+3.6 % at 160
-        // frames).  With per-kernel profiling enabled the batch stays on one stream so that kernel durations are exclusive.
+        // big batches: slices alternating between two compute streams forked from / joined into the context stream, so that the
+        // tail of every kernel (last wave, slowest warp of a persistent kernel) is filled by the other stream's work.  With
+        // per-kernel profiling enabled the batch stays on one stream so that kernel durations are exclusive.
+        static const int NS_ENV = getenv("EBVO_SLICES") ? std::max(2, atoi(getenv("EBVO_SLICES"))) : 0;
+        const int ns = std::min(NS_ENV ? NS_ENV : 2, nFrames / 8);
         CK(cudaEventRecord(ctx->evFork, ctx->st));
         CK(cudaStreamWaitEvent(ctx->st2, ctx->evFork, 0));
-        const int h = (nFrames + 1) / 2;
-        run(frame_view(ctx->b, 0, h), 0, h, ctx->st);
-        run(frame_view(ctx->b, h, nFrames - h), h, nFrames - h, ctx->st2);
+        for (int k = 0; k < ns; ++k) {
+            const int f0 = (int)((long long)nFrames * k / ns), f1 = (int)((long long)nFrames * (k + 1) / ns);
+            run(frame_view(ctx->b, f0, f1 - f0), f0, f1 - f0, (k & 1) ? ctx->st2 : ctx->st);
+        }
         CK(cudaEventRecord(ctx->evJoin, ctx->st2));
         CK(cudaStreamWaitEvent(ctx->st, ctx->evJoin, 0));
     } else run(ctx->b, 0, nFrames, ctx->st);
@@ -776,9 +779,11 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
     ctx->prof.reset();
     int rc = configure(ctx, w, h, n_frames);
     if (rc) return rc;
+    // (SB = 16: swept 8 .. 80 at 160 frames, profiles/r02_sub_batch_sweep.txt; EBVO_SUB_BATCH overrides it)
     // Software pipeline over sub-batches of SB frames: the images of sub-batch k+1 are copied in and the mates of
     // sub-batch k-1 copied out while the kernels of sub-batch k run (three streams, events in between).
-    const int SB = 32, nsb = (n_frames + SB - 1) / SB;
+    static const int SB_ENV = getenv("EBVO_SUB_BATCH") ? std::max(1, atoi(getenv("EBVO_SUB_BATCH"))) : 0;
+    const int SB = SB_ENV ? SB_ENV : 16, nsb = (n_frames + SB - 1) / SB;
     if (!ctx->stIn) {
         CK(cudaStreamCreateWithFlags(&ctx->stIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->stOut, cudaStreamNonBlocking));
     }

@@ -994,7 +994,10 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 #define GNL_PXV 256
 #endif
 constexpr int GNL_PX = GNL_PXV;
-constexpr int GN_CHUNK = 8;        // pool slots fetched per atomic
+#ifndef GN_CHUNKV
+#define GN_CHUNKV 32
+#endif
+constexpr int GN_CHUNK = GN_CHUNKV;        // pool slots fetched per atomic (at most 32: one lane per slot)
 #ifndef GN_RV
 #define GN_RV 5
 #endif
@@ -1047,6 +1050,17 @@ template <int GT64_MAXPX, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, DevParams p, int Rmax, int nFrames)
 {
     __shared__ uint2 s_tile[WPB][2][GT64_MAXPX];
+    // the per-left-edge sample geometry and centred left samples live in shared memory (lane-contiguous, conflict-free reads): the 24
+    // registers they would hold are worth more to the scheduler's interleaving of the three sample chains (-2.6 %; a fifth CTA per
+    // SM bought with them instead is not: 20 warps run no faster than 16)
+    __shared__ double s_state[WPB][12][32];
+    double (*SS)[32] = s_state[threadIdx.x >> 5];
+#define RX(m) SS[m][lane]
+#define RY(m) SS[3 + (m)][lane]
+#define LC(m) SS[6 + (m)][lane]
+#define RX48 SS[9][lane]
+#define RY48 SS[10][lane]
+#define LC48 SS[11][lane]
     uint2* tF = s_tile[threadIdx.x >> 5][(threadIdx.x & 31) >> 4];
     const int lane = threadIdx.x & 31;
     const int hw = lane >> 4, hl = lane & 15;
@@ -1075,15 +1089,20 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
             q0 = __shfl_sync(FULL, q0, 0);
             if (q0 >= used) break;
             const int q1 = min(q0 + GN_CHUNK, used);
+            // the chunk's slots are fetched by the first GN_CHUNK lanes at once and handed out by shuffles: no global-memory
+            // round trip between two candidates
+            int own_l = -1;
+            double x_l = 0, y_l = 0;
+            if (lane < GN_CHUNK && q0 + lane < q1) { own_l = c_owner[q0 + lane]; x_l = c_x[q0 + lane]; y_l = c_y[q0 + lane]; }
             int owner = -1;
             double dirx = 0, diry = 0, cx = 0, cy = 0, hext = 0;
             int Rint = 0;
             bool tileValid = false;
-            double rx[3], ry[3], Lc[3], rx48 = 0, ry48 = 0, Lc48 = 0;
             int TWp = 0, THp = 0, npx = 0, ox = 0, oy = 0;
             float invTW = 0.f;
             for (int q = q0; q < q1; ++q) {
-                const int i = c_owner[q];
+                const int i = __shfl_sync(FULL, own_l, q - q0);
+                const double xr = shfl_idx_d(x_l, q - q0), yr = shfl_idx_d(y_l, q - q0);
                 if (i < 0) continue;          // dead slot (dropped by NCC / best-nearly-best)
                 if (i != owner) {
                     owner = i;
@@ -1095,21 +1114,23 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     const double side = 7 / 2.0 + 1.0;                               // :1171
                     cx = hw ? st_ * side : -st_ * side;                              // +-n*side, n = (-t.y, t.x) (:1169-1170)
                     cy = hw ? -ct_ * side : ct_ * side;
-                    double sumL = 0;
+                    double sumL = 0, lcv[3];
 #pragma unroll
                     for (int m = 0; m < 3; ++m) {
                         const int t = hl + 16 * m;
                         const int ii = t / 7 - 3, jj = t % 7 - 3;
-                        rx[m] = ct_ * ii - st_ * jj; ry[m] = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
-                        Lc[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx[m], (yL + cy) + ry[m]); sumL += Lc[m];
+                        const double rxm = ct_ * ii - st_ * jj, rym = st_ * ii + ct_ * jj;    // rotated cell (utility.h:154)
+                        RX(m) = rxm; RY(m) = rym;
+                        lcv[m] = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rxm, (yL + cy) + rym); sumL += lcv[m];
                     }
-                    rx48 = ct_ * 3 - st_ * 3; ry48 = st_ * 3 + ct_ * 3;              // cell (3, 3), t = 48
-                    Lc48 = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx48, (yL + cy) + ry48);
-                    sumL = half_sum(sumL) + Lc48;
+                    const double rx48v = ct_ * 3 - st_ * 3, ry48v = st_ * 3 + ct_ * 3;              // cell (3, 3), t = 48
+                    RX48 = rx48v; RY48 = ry48v;
+                    const double lc48v = sample_u8_exact(IL, b.pitch, W, H, (xL + cx) + rx48v, (yL + cy) + ry48v);
+                    sumL = half_sum(sumL) + lc48v;
                     const double mL = sumL / 49.0;
 #pragma unroll
-                    for (int m = 0; m < 3; ++m) Lc[m] -= mL;
-                    Lc48 -= mL;
+                    for (int m = 0; m < 3; ++m) LC(m) = lcv[m] - mL;
+                    LC48 = lc48v - mL;
                     // tile: every sample of this patch stays within (centre +- (R|dir| + hext)) while |alpha - alpha0| <= R
                     hext = 3.0 * (fabs(ct_) + fabs(st_)) + 1e-6;
                     int R = Rmax;
@@ -1127,7 +1148,6 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     tileValid = false;           // the tile shape belongs to the left edge
                 }
                 {
-                const double xr = c_x[q], yr = c_y[q];
                 const double xc = xr + cx, yc = yr + cy;      // patch centre at alpha = 0 (:1203-1204)
                 double alpha = 0.0, score = 0.0, conf = 0.0, alpha0 = CUDART_NAN;
                 double Rv = (double)Rint - 1e-6;
@@ -1161,7 +1181,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     double sR = 0;
 #pragma unroll
                     for (int m = 0; m < 3; ++m) {
-                        const double x = xs + rx[m], y = ys + ry[m];
+                        const double x = xs + RX(m), y = ys + RY(m);
                         const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
@@ -1183,7 +1203,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
                     double vi48, vg48;
                     {
-                        const double x = xs + rx48, y = ys + ry48;
+                        const double x = xs + RX48, y = ys + RY48;
                         const double tx = __dadd_rd(x, MAGIC), ty = __dadd_rd(y, MAGIC);
                         const double a = x - (tx - MAGIC), bb = y - (ty - MAGIC);
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
@@ -1205,7 +1225,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     double Hh = 0, bb_ = 0, cost = 0;
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
-                        const double r = (m < 3 ? Lc[m] : Lc48) - ((m < 3 ? vi[m] : vi48) - mR);
+                        const double r = (m < 3 ? LC(m < 3 ? m : 0) : LC48) - ((m < 3 ? vi[m] : vi48) - mR);
                         const double gg = m < 3 ? vg[m] : vg48;
                         const double ar = fabs(r);
                         double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
@@ -1240,6 +1260,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
         }
     }
 }
+#undef RX
+#undef RY
+#undef LC
+#undef RX48
+#undef RY48
+#undef LC48
 
 __global__ void __launch_bounds__(32 * WPB, 5) gn64_kernel(DevBatch b, DevParams p)
 {
