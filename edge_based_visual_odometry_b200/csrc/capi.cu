@@ -172,7 +172,7 @@ int check_err_flag(ebvo_ctx* ctx, int nFrames = 1, std::vector<int>* failed = nu
         static const char* what[] = {"", "edge capacity (max_edges) exceeded", "candidate pool exhausted", "more than 128 NCC survivors for one left edge",
                                      "more than 128 candidates entering the clusterer for one left edge"};
         const int flag = flags[first];
-        ctx->err = std::string("capacity: ") + what[flag > 0 && flag < 5 ? flag : 0] + " (frame " + std::to_string(first) + (count > 1 ? ", " + std::to_string(count) + " frames in all" : "") + ")";
+        ctx->err = std::string(flag == 99 ? "internal bounds assertion (EBVO_CHECKED build)" : "capacity: ") + what[flag > 0 && flag < 5 ? flag : 0] + " (frame " + std::to_string(first) + (count > 1 ? ", " + std::to_string(count) + " frames in all" : "") + ")";
         return EBVO_ERR_CAPACITY;
     }
     return EBVO_OK;

@@ -173,6 +173,15 @@ struct Prof {
     void reset();
 };
 
+// Checked build (-DEBVO_CHECKED, scripts/checked_run.sh): compute-sanitizer is closed on the GPU pool, so the kernels carry their own
+// bounds assertions on every shared-memory tile / list / pool index; a violation sets the frame's error flag to 99 and the call fails
+// with EBVO_ERR_CAPACITY "internal bounds assertion".  Compiled out of the product build.
+#ifdef EBVO_CHECKED
+#define EBVO_ASSERT(errp, cond) do { if (!(cond)) atomicExch((errp), 99); } while (0)
+#else
+#define EBVO_ASSERT(errp, cond) do { } while (0)
+#endif
+
 #define EBVO_KERNEL(prof, name, st, ...)            \
     do {                                            \
         if (prof) ++(prof)->launchCount;            \

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams
             l[0] = g.a; l[1] = g.b; l[2] = g.c; l[3] = dirx; l[4] = diry; l[5] = sn; l[6] = cs; l[7] = 0.0;
         }
         int* buf = s_buf[w];
-        int n = gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { if (rank < 64) buf[rank] = e; });
+        int n = gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { EBVO_ASSERT(b.errFlag + f, e >= 0 && e < b.nE[2 * f + 1]); if (rank < 64) buf[rank] = e; });
         int start = 0;
         if (lane == 0 && n > 0) start = atomicAdd(&b.poolUsed[f], n);
         start = __shfl_sync(FULL, start, 0);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) gate_kernel(DevBatch b, DevParams
         __syncwarp();
         if (n > 0) {
             if (n <= 64) { for (int k = lane; k < n; k += 32) c_ridx[start + k] = buf[k]; }
-            else gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { c_ridx[start + rank] = e; });
+            else gate_scan(g, b, p, f, 2, lane, [&](int rank, int e) { EBVO_ASSERT(b.errFlag + f, start + rank < b.P); c_ridx[start + rank] = e; });
         }
         if (lane == 0) { cstart[i] = start; ccount[i] = n; }
         pairs += n;
@@ -658,6 +658,7 @@ __global__ void __launch_bounds__(32 * WPB, 6) ncc_bnb_kernel(DevBatch b, DevPar
         const bool lP = L.flags & 1, lM = L.flags & 2;
         int ns = 0;
         int rn = g < n ? c_ridx[st + g] : -1;
+        EBVO_ASSERT(b.errFlag + f, st >= 0 && st + n <= b.P && rn < b.nE[imgR]);
         N = L;
         if (rn >= 0) load_patch_row(npR, pfR, rn, q, N);
         for (int j0 = 0; j0 < n; j0 += 4) {
@@ -757,6 +758,9 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate_kernel(DevBatch b, DevPara
             }
             __syncwarp();
         }
+        // the slots the gate dropped stay allocated in the pool: mark them dead, or the slot-driven kernels (shift, Gauss-Newton) would
+        // work on whatever owner index an earlier call left there
+        for (int k = ns + lane; k < n; k += 32) b.c_owner[(size_t)f * b.P + st + k] = -1;
         if (lane == 0) ccount[i] = ns;
     }
 }
@@ -795,6 +799,9 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate8_kernel(DevBatch b, DevPar
             }
             __syncwarp();
         }
+        // the slots the gate dropped stay allocated in the pool: mark them dead, or the slot-driven kernels (shift, Gauss-Newton) would
+        // work on whatever owner index an earlier call left there
+        for (int k = ns + lane; k < n; k += 32) b.c_owner[(size_t)f * b.P + st + k] = -1;
         if (lane == 0) ccount[i] = ns;
     }
 }
@@ -1104,6 +1111,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                 const int i = __shfl_sync(FULL, own_l, q - q0);
                 const double xr = shfl_idx_d(x_l, q - q0), yr = shfl_idx_d(y_l, q - q0);
                 if (i < 0) continue;          // dead slot (dropped by NCC / best-nearly-best)
+                EBVO_ASSERT(b.errFlag + f, i < b.nE[imgL] && q < b.P);
                 if (i != owner) {
                     owner = i;
                     // ---- per left edge: geometry, centred left samples, tile shape ----
@@ -1187,6 +1195,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                         const int o = yi * TWp + xi;
+                        EBVO_ASSERT(b.errFlag + f, o >= 0 && o + TWp + 1 < npx && npx <= GT64_MAXPX);
                         const uint2 p00 = tF[o], p10 = tF[o + 1], p01 = tF[o + TWp], p11 = tF[o + TWp + 1];
                         const unsigned d0x = hsub2_u32(p10.x, p00.x), d0y = hsub2_u32(p10.y, p00.y);
                         const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
@@ -1209,6 +1218,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const int xi = (int)min((unsigned)(__double2loint(tx) - ox), (unsigned)(TWp - 2));
                         const int yi = (int)min((unsigned)(__double2loint(ty) - oy), (unsigned)(THp - 2));
                         const int o = (yi + cRow) * TWp + xi;
+                        EBVO_ASSERT(b.errFlag + f, o >= 0 && o + 1 < npx);
                         const uint2 p0 = tF[o], p1 = tF[o + 1];
                         const unsigned s0 = cCh == 0 ? p0.x : (cCh == 1 ? p0.y : p0.y >> 16);
                         const unsigned s1 = cCh == 0 ? p1.x : (cCh == 1 ? p1.y : p1.y >> 16);
@@ -1609,6 +1619,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) cluster8_kernel(DevBatch b, DevPa
         if (n > small) { if (gl == 0) big[(int)atomicAdd(nbig, 1ull)] = i; n = 0; }      // left for the warp-per-set launches
         else if (n == 0 && i < nL && dumps && gl == 0) b.dump[DUMP_S10].n[i] = 0;
         const int st = n ? cstart[i] : 0;
+        EBVO_ASSERT(b.errFlag + f, n >= 0 && n <= 8 && st >= 0 && st + n <= b.P);
         const bool valid = gl < n;
         double xi = 0, yi = 0, ti = 0;
         if (valid) { xi = c_x[st + gl]; yi = c_y[st + gl]; ti = c_th[st + gl]; }        // after the second shift
@@ -1633,6 +1644,7 @@ __global__ void __launch_bounds__(32 * WPB, 8) cluster8_kernel(DevBatch b, DevPa
             const unsigned mg = (m >> (8 * g)) & 0xffu;
             const int src = mg ? __ffs(mg) - 1 : 0;
             const int pj = __shfl_sync(FULL, bj, 8 * g + src);
+            EBVO_ASSERT(b.errFlag + f, !mg || (pj >= 0 && pj < n && src < n));
             int lnew = 0, lold = -1, merged = 0;
             if (mg) { lnew = LAB[src]; lold = LAB[pj]; merged = CSZ[lnew] + CSZ[lold]; }
             __syncwarp();
@@ -1713,6 +1725,7 @@ __global__ void __launch_bounds__(32 * WPB, MINB) cluster_kernel(DevBatch b, Dev
         wi = __shfl_sync(FULL, wi, 0);
         if (wi >= nwork) break;
         const int i = work[wi];
+        EBVO_ASSERT(b.errFlag + f, i >= 0 && i < b.nE[2 * f]);
         int n = ccount[i];
         if (CAP < MAXC && (n > CAP || n > p.clus_small)) {          // left for the MAXC launch
             if (lane == 0) listB[atomicAdd(&b.nMates[f], 1)] = i;

@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(128) toed_refine_kernel(DevBatch b, double mag
                 const int yv = ap ? 2 : (bp ? 1 : 0);
                 const int slot = xk >= 2 ? 10 + xk : 4 * (dj + 1) + xk + ((bp == 0 && ap) ? 2 : 0);   // 19-tap version for sub-grid (1,0)
                 const int r0 = cid - rbase;                                                           // row of tap p = 0
+                EBVO_ASSERT(b.errFlag + (img >> 1), r0 - 9 >= 0 && r0 + 9 <= 20 && slot >= 0 && slot < 14 && cbase - (cbase & ~3) + 20 < 28);
                 double acc = 0;
 #pragma unroll
                 for (int p = -9; p <= 9; ++p) acc = fma(s_rc[w][r0 - p][slot], s_T[yv][yk][p + 9], acc);
