@@ -1185,7 +1185,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         }
                         __syncwarp();
                     }
-                    double vi[3], vg[3];
+                    double vi[3], vg[3];       // (kept in registers: staging them in shared memory as well costs 4 %)
+#define VI(m) vi[m]
+#define VG(m) vg[m]
                     double sR = 0;
 #pragma unroll
                     for (int m = 0; m < 3; ++m) {
@@ -1201,13 +1203,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         const unsigned d1x = hsub2_u32(p11.x, p01.x), d1y = hsub2_u32(p11.y, p01.y);
                         // FP64 interpolation rounded to float = util_bilinear_Sample_F (utility.h:159-172) per channel
                         double top = fma(a, h2d(d0x), h2d(p00.x)), bot = fma(a, h2d(d1x), h2d(p01.x));
-                        vi[m] = round_to_float(fma(bb, bot - top, top));
+                        const double vim = round_to_float(fma(bb, bot - top, top));
+                        VI(m) = vim;
                         top = fma(a, h2d(d0y), h2d(p00.y)); bot = fma(a, h2d(d1y), h2d(p01.y));
                         const double gx = round_to_float(fma(bb, bot - top, top));
                         top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
                         const double gy = round_to_float(fma(bb, bot - top, top));
-                        vg[m] = -gx * dirx + gy * diry;                                   // :1240
-                        sR += vi[m];
+                        VG(m) = -gx * dirx + gy * diry;                                   // :1240
+                        sR += vim;
                     }
                     // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
                     double vi48, vg48;
@@ -1235,8 +1238,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     double Hh = 0, bb_ = 0, cost = 0;
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
-                        const double r = (m < 3 ? LC(m < 3 ? m : 0) : LC48) - ((m < 3 ? vi[m] : vi48) - mR);
-                        const double gg = m < 3 ? vg[m] : vg48;
+                        const double r = (m < 3 ? LC(m < 3 ? m : 0) : LC48) - ((m < 3 ? VI(m < 3 ? m : 0) : vi48) - mR);
+                        const double gg = m < 3 ? VG(m < 3 ? m : 0) : vg48;
                         const double ar = fabs(r);
                         double wgt = (ar <= huber) ? 1.0 : huber * rcp_fast(ar);
                         if (m == 3 && hl != 0) wgt = 0.0;                                 // sample 48 counts once per patch
@@ -1270,6 +1273,8 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
         }
     }
 }
+#undef VI
+#undef VG
 #undef RX
 #undef RY
 #undef LC
