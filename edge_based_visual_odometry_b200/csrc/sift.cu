@@ -16,7 +16,7 @@
 //     "o0 += n" wrap leaves a negative orientation index; the vote then lands 1..4 slots BEFORE the cell's first
 //     bin in the flat histogram (the previous cell's upper slots), exactly as OpenCV's pointer arithmetic does;
 //     votes that fall outside the array are dropped.
-// Votes are accumulated as 64-bit fixed point with shared-memory atomics, so the result does not depend on the order
+// Votes are accumulated in fixed point with shared-memory integer atomics, so the result does not depend on the order
 // of the lanes (deterministic run to run).
 #include "ebvo_internal.cuh"
 #include <cfloat>
@@ -98,87 +98,118 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 constexpr int SD = 4, SN = 8;                                  // SIFT_DESCR_WIDTH, SIFT_DESCR_HIST_BINS
 constexpr int SHIST = (SD + 2) * (SD + 2) * (SN + 2);          // 360
-constexpr float FIX = 4294967296.f;                            // 2^32 fixed-point scale of the votes
+constexpr float VFIX = 262144.f;                               // 2^18 fixed-point scale of the votes (a bin collects < 2^13: no overflow in 32 bits)
 
-// One warp per keypoint; keypoint 2e + s of an image = edge e, side s (0: p + 8 (sin, -cos), 1: p - 8 (sin, -cos)).
+// One warp per EDGE = two keypoints (side 0: p + 8 (sin, -cos), side 1: p - 8 (sin, -cos)) that share orientation, hence
+// the rotated sampling pattern: which of the 11 x 11 samples fall inside the descriptor window, their bin coordinates and
+// Gaussian weights are computed once and used for both sides.  The samples inside the window (46 % of the 121) are
+// compacted first, so two passes of 32 lanes replace four; votes are 32-bit fixed-point shared-memory atomics (native
+// ATOMS.ADD), so the histogram does not depend on the order of the lanes.
 __global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
 {
-    __shared__ unsigned long long s_h[4][SHIST];
+    __shared__ __align__(16) uint32_t s_h[4][2][SHIST];
+    __shared__ uint8_t s_list[4][128];
     const int img = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = b.nE[img];
     const float* I = b.blur + (size_t)img * b.blurStride;
     const int rows = b.H, cols = b.W;
-    unsigned long long* h = s_h[w];
-    for (int kp = blockIdx.x * 4 + w; kp < 2 * n; kp += gridDim.x * 4) {
-        const int e = kp >> 1, side = kp & 1;
+    const float bins_per_rad = SN / 360.f, exp_scale = -1.f / (SD * SD * 0.5f), hist_width = 3.f * 0.5f;
+    for (int e = blockIdx.x * 4 + w; e < n; e += gridDim.x * 4) {
         const size_t eo = (size_t)img * b.E + e;
         const double x = b.ex[eo], y = b.ey[eo], th = b.eth[eo];
         double sn, cs;
         sincos(th, &sn, &cs);
         // utility.cpp:128-139 and the cv::KeyPoint(Point2d, 1, 180 / M_PI * theta) constructor (narrowing to float)
-        const float px = (float)(side ? x + 8.0 * (-sn) : x + 8.0 * sn), py = (float)(side ? y + 8.0 * cs : y + 8.0 * (-cs));
+        const float pxs[2] = {(float)(x + 8.0 * sn), (float)(x + 8.0 * (-sn))}, pys[2] = {(float)(y + 8.0 * (-cs)), (float)(y + 8.0 * cs)};
         const float angle = (float)(180 / 3.14159265358979323846 * th);
-        for (int k = lane; k < SHIST; k += 32) h[k] = 0ull;
-        __syncwarp();
-        const int ptx = __float2int_rn(px), pty = __float2int_rn(py);       // cvRound
+        {
+            uint4* hz = reinterpret_cast<uint4*>(&s_h[w][0][0]);
+            for (int k = lane; k < 2 * SHIST / 4; k += 32) hz[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
         float ori = 360.f - angle;
         if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
         float cos_t = cosf(ori * (float)(3.14159265358979323846 / 180)), sin_t = sinf(ori * (float)(3.14159265358979323846 / 180));
-        const float bins_per_rad = SN / 360.f, exp_scale = -1.f / (SD * SD * 0.5f), hist_width = 3.f * 0.5f;
         cos_t /= hist_width; sin_t /= hist_width;
-        for (int k = lane; k < 121; k += 32) {
+        // samples inside the descriptor window, in sample order
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = lane + 32 * t;
             const int i = k / 11 - 5, j = k % 11 - 5;
             const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
-            float rbin = r_rot + SD / 2 - 0.5f, cbin = c_rot + SD / 2 - 0.5f;
-            const int r = pty + i, c = ptx + j;
-            if (rbin > -1 && rbin < SD && cbin > -1 && cbin < SD && r > 0 && r < rows - 1 && c > 0 && c < cols - 1) {
-                const float dx = I[(size_t)r * cols + c + 1] - I[(size_t)r * cols + c - 1];
-                const float dy = I[(size_t)(r - 1) * cols + c] - I[(size_t)(r + 1) * cols + c];
+            const float rbin = r_rot + SD / 2 - 0.5f, cbin = c_rot + SD / 2 - 0.5f;
+            const bool in = k < 121 && rbin > -1 && rbin < SD && cbin > -1 && cbin < SD;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) s_list[w][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)k;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        for (int p0 = 0; p0 < cnt; p0 += 32) {
+            if (p0 + lane < cnt) {
+                const int k = s_list[w][p0 + lane];
+                const int i = k / 11 - 5, j = k % 11 - 5;
+                const float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
+                float rbin = r_rot + SD / 2 - 0.5f, cbin = c_rot + SD / 2 - 0.5f;
                 const float wgt = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-                float obin = (fast_atan2_deg(dy, dx) - ori) * bins_per_rad;
-                const float mag = sqrtf(dx * dx + dy * dy) * wgt;
                 const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin);
-                int o0 = (int)floorf(obin);
-                rbin -= r0; cbin -= c0; obin -= o0;
-                if (o0 < 0) o0 += SN;
-                if (o0 >= SN) o0 -= SN;
-                const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-                const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-                const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
-                const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
-                const int idx = ((r0 + 1) * (SD + 2) + c0 + 1) * (SN + 2) + o0;
-                auto vote = [&](int o, float v) { if (o >= 0 && o < SHIST && v > 0.f) atomicAdd(&h[o], (unsigned long long)(v * FIX)); };
-                vote(idx, v000); vote(idx + 1, v001);
-                vote(idx + (SN + 2), v010); vote(idx + (SN + 3), v011);
-                vote(idx + (SD + 2) * (SN + 2), v100); vote(idx + (SD + 2) * (SN + 2) + 1, v101);
-                vote(idx + (SD + 3) * (SN + 2), v110); vote(idx + (SD + 3) * (SN + 2) + 1, v111);
+                rbin -= r0; cbin -= c0;
+                const int idx0 = ((r0 + 1) * (SD + 2) + c0 + 1) * (SN + 2);
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const int r = __float2int_rn(pys[side]) + i, c = __float2int_rn(pxs[side]) + j;       // cvRound
+                    if (r > 0 && r < rows - 1 && c > 0 && c < cols - 1) {
+                        const float dx = I[(size_t)r * cols + c + 1] - I[(size_t)r * cols + c - 1];
+                        const float dy = I[(size_t)(r - 1) * cols + c] - I[(size_t)(r + 1) * cols + c];
+                        float obin = (fast_atan2_deg(dy, dx) - ori) * bins_per_rad;
+                        const float mag = sqrtf(dx * dx + dy * dy) * wgt;
+                        int o0 = (int)floorf(obin);
+                        obin -= o0;
+                        if (o0 < 0) o0 += SN;
+                        if (o0 >= SN) o0 -= SN;
+                        const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                        const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                        const float v111 = v_rc11 * obin, v110 = v_rc11 - v111, v101 = v_rc10 * obin, v100 = v_rc10 - v101;
+                        const float v011 = v_rc01 * obin, v010 = v_rc01 - v011, v001 = v_rc00 * obin, v000 = v_rc00 - v001;
+                        const int idx = idx0 + o0;
+                        uint32_t* h = s_h[w][side];
+                        auto vote = [&](int o, float v) { if (o >= 0 && o < SHIST && v > 0.f) atomicAdd(&h[o], __float2uint_rn(v * VFIX)); };
+                        vote(idx, v000); vote(idx + 1, v001);
+                        vote(idx + (SN + 2), v010); vote(idx + (SN + 3), v011);
+                        vote(idx + (SD + 2) * (SN + 2), v100); vote(idx + (SD + 2) * (SN + 2) + 1, v101);
+                        vote(idx + (SD + 3) * (SN + 2), v110); vote(idx + (SD + 3) * (SN + 2) + 1, v111);
+                    }
+                }
             }
         }
         __syncwarp();
         // circular fold + copy: lane owns descriptor entries q = lane + 32 t (cell q / 8, orientation q % 8)
-        float val[4];
-        float nrm2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int q = lane + 32 * t, cell = q >> 3, o = q & 7;
-            const int idx = ((cell / SD + 1) * (SD + 2) + (cell % SD + 1)) * (SN + 2);
-            unsigned long long s = h[idx + o];
-            if (o < 2) s += h[idx + SN + o];
-            val[t] = (float)((double)s * (1.0 / 4294967296.0));
-            nrm2 += val[t] * val[t];
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t* h = s_h[w][side];
+            float val[4];
+            float nrm2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int q = lane + 32 * t, cell = q >> 3, o = q & 7;
+                const int idx = ((cell / SD + 1) * (SD + 2) + (cell % SD + 1)) * (SN + 2);
+                unsigned long long sacc = h[idx + o];
+                if (o < 2) sacc += h[idx + SN + o];
+                val[t] = (float)((double)sacc * (1.0 / 262144.0));
+                nrm2 += val[t] * val[t];
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+            const float thr = sqrtf(nrm2) * 0.2f;                                   // SIFT_DESCR_MAG_THR
+            float n2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { val[t] = fminf(val[t], thr); n2 += val[t] * val[t]; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            const float scale = 512.f / fmaxf(sqrtf(n2), FLT_EPSILON);              // SIFT_INT_DESCR_FCTR
+            uint8_t* d = b.desc8 + (eo * 2 + side) * 128;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) d[lane + 32 * t] = (uint8_t)min(max(__float2int_rn(val[t] * scale), 0), 255);   // saturate_cast<uchar>
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
-        const float thr = sqrtf(nrm2) * 0.2f;                                   // SIFT_DESCR_MAG_THR
-        float n2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) { val[t] = fminf(val[t], thr); n2 += val[t] * val[t]; }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-        const float scale = 512.f / fmaxf(sqrtf(n2), FLT_EPSILON);              // SIFT_INT_DESCR_FCTR
-        uint8_t* d = b.desc8 + (eo * 2 + side) * 128;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) d[lane + 32 * t] = (uint8_t)min(max(__float2int_rn(val[t] * scale), 0), 255);   // saturate_cast<uchar>
         __syncwarp();
     }
 }

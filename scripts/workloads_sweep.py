@@ -25,5 +25,5 @@ md = [f"# Round {tag[1:].lstrip('0')}: the other BASELINE.json configurations (o
       "| workload | frames/step | edges/image | mates/frame | frames/s (resident) | frames/s (e2e) | toed | gn |", "|---|---|---|---|---|---|---|---|"]
 for d in lines:
     c, ps = d["config"], d["roofline"]["per_stage"]
-    md.append(f"| {c['workload'][:60]} | {c['frames_per_gpu_per_step']} | {c['edges_per_image']:.0f} | {c['mates_per_frame']:.0f} | {d['value']:.1f} | {d['e2e']['value']:.1f} | {ps['toed']['frac']:.2f} | {ps['gauss_newton']['frac']:.2f} |")
+    md.append(f"| {c['workload'][:110]} | {c['frames_per_gpu_per_step']} | {c['edges_per_image']:.0f} | {c['mates_per_frame']:.0f} | {d['value']:.1f} | {d['e2e']['value']:.1f} | {ps['toed']['frac']:.2f} | {ps['gauss_newton']['frac']:.2f} |")
 open(os.path.join(dst, f"{tag}_workloads.md"), "w").write("\n".join(md) + "\n")
