@@ -767,10 +767,15 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate_kernel(DevBatch b, DevPara
 }
 
 // The same gate on descriptors computed on the device (sift.cu; every frame): 8-bit entries, so the four squared
-// distances are exact integer sums (cv::norm accumulates the float entries in double: the same value).
+// distances are exact integer sums (cv::norm accumulates the float entries in double: the same value), and the smallest
+// of the four distances is the root of the smallest squared one.  One warp per left edge, one quarter-warp per candidate
+// (four candidates per step): a lane holds 16 bytes of each of the two left and the two right descriptors, byte
+// differences and their squares are SIMD-in-a-word instructions (vabsdiffu4, dp4a).
 __global__ void __launch_bounds__(32 * WPB) sift_gate8_kernel(DevBatch b, DevParams p)
 {
     const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = lane >> 3, gl = lane & 7;
+    const unsigned gmask = 0xffu << (8 * g);
     const int nL = b.nE[2 * f];
     const int* cstart = b.cstart + (size_t)f * b.E;
     int* ccount = b.ccount + (size_t)f * b.E;
@@ -778,26 +783,39 @@ __global__ void __launch_bounds__(32 * WPB) sift_gate8_kernel(DevBatch b, DevPar
     double* c_conf = b.c_conf + (size_t)f * b.P;
     const uint8_t* dL = b.desc8 + (size_t)(2 * f) * b.E * 256;
     const uint8_t* dR = b.desc8 + (size_t)(2 * f + 1) * b.E * 256;
+    auto ssd = [](const uint4& u, const uint4& v) {
+        unsigned d, acc;
+        d = __vabsdiffu4(u.x, v.x); acc = __dp4a(d, d, 0u);
+        d = __vabsdiffu4(u.y, v.y); acc = __dp4a(d, d, acc);
+        d = __vabsdiffu4(u.z, v.z); acc = __dp4a(d, d, acc);
+        d = __vabsdiffu4(u.w, v.w); return __dp4a(d, d, acc);
+    };
     for (int i = blockIdx.x * WPB + w; i < nL; i += gridDim.x * WPB) {
         const int n = ccount[i];
         if (n == 0) continue;
         const int st = cstart[i];
-        const uchar4 a1 = reinterpret_cast<const uchar4*>(dL + (size_t)i * 256)[lane], a2 = reinterpret_cast<const uchar4*>(dL + (size_t)i * 256 + 128)[lane];
+        const uint4 a1 = reinterpret_cast<const uint4*>(dL + (size_t)i * 256)[gl], a2 = reinterpret_cast<const uint4*>(dL + (size_t)i * 256 + 128)[gl];
         int ns = 0;
-        for (int j = 0; j < n; ++j) {
-            const int r = c_ridx[st + j];
-            const uchar4 b1 = reinterpret_cast<const uchar4*>(dR + (size_t)r * 256)[lane], b2 = reinterpret_cast<const uchar4*>(dR + (size_t)r * 256 + 128)[lane];
-            auto d2 = [](uchar4 u, uchar4 v) {
-                const int x = (int)u.x - (int)v.x, y = (int)u.y - (int)v.y, z = (int)u.z - (int)v.z, q = (int)u.w - (int)v.w;
-                return x * x + y * y + z * z + q * q;
-            };
-            const int d11 = __reduce_add_sync(FULL, d2(a1, b1)), d21 = __reduce_add_sync(FULL, d2(a2, b1));
-            const int d12 = __reduce_add_sync(FULL, d2(a1, b2)), d22 = __reduce_add_sync(FULL, d2(a2, b2));
-            const double d = fmin(fmin(sqrt((double)d11), sqrt((double)d21)), fmin(sqrt((double)d12), sqrt((double)d22)));   // :736-740
-            if (d < p.sift_thresh) {
-                if (lane == 0) { c_ridx[st + ns] = r; c_conf[st + ns] = d; }
-                ++ns;
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            const int j = j0 + g;
+            const bool live = j < n;
+            const int r = live ? c_ridx[st + j] : 0;
+            unsigned dmin = 0xffffffffu;
+            if (live) {
+                const uint4 b1 = reinterpret_cast<const uint4*>(dR + (size_t)r * 256)[gl], b2 = reinterpret_cast<const uint4*>(dR + (size_t)r * 256 + 128)[gl];
+                const unsigned d11 = __reduce_add_sync(gmask, ssd(a1, b1)), d21 = __reduce_add_sync(gmask, ssd(a2, b1));
+                const unsigned d12 = __reduce_add_sync(gmask, ssd(a1, b2)), d22 = __reduce_add_sync(gmask, ssd(a2, b2));
+                dmin = min(min(d11, d21), min(d12, d22));                         // :736-740
             }
+            const double d = sqrt((double)dmin);
+            const bool pass = live && d < p.sift_thresh;
+            const unsigned pm = __ballot_sync(FULL, pass && gl == 0);             // bit 8 g = candidate j0 + g passes
+            __syncwarp();                                                         // every candidate of this step is read before a slot is rewritten
+            if (pass && gl == 0) {
+                const int pos = st + ns + __popc(pm & ((1u << lane) - 1u));
+                c_ridx[pos] = r; c_conf[pos] = d;
+            }
+            ns += __popc(pm);
             __syncwarp();
         }
         // the slots the gate dropped stay allocated in the pool: mark them dead, or the slot-driven kernels (shift, Gauss-Newton) would
