@@ -126,23 +126,37 @@ __global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
         if (f > x) { f -= 1.f; --n; }
         return f;
     };
-    for (int e = blockIdx.x * 4 + w; e < n; e += gridDim.x * 4) {
-        const size_t eo = (size_t)img * b.E + e;
-        const double x = b.ex[eo], y = b.ey[eo], th = b.eth[eo];
-        double sn, cs;
-        sincos(th, &sn, &cs);
-        // utility.cpp:128-139 and the cv::KeyPoint(Point2d, 1, 180 / M_PI * theta) constructor (narrowing to float)
-        const float pxs[2] = {(float)(x + 8.0 * sn), (float)(x + 8.0 * (-sn))}, pys[2] = {(float)(y + 8.0 * (-cs)), (float)(y + 8.0 * cs)};
-        const int ptx[2] = {__float2int_rn(pxs[0]), __float2int_rn(pxs[1])}, pty[2] = {__float2int_rn(pys[0]), __float2int_rn(pys[1])};   // cvRound
-        const float angle = (float)(180 / 3.14159265358979323846 * th);
+    // The scalar set-up of an edge (FP64 sincos for the keypoint offsets, the FP32 rotation) is done for SCH edges at once,
+    // one edge per lane, and handed to the warp by shuffles: replicated over 32 lanes it was a fifth of the kernel.
+    constexpr int SCH = 16;
+    for (int e0 = (blockIdx.x * 4 + w) * SCH; e0 < n; e0 += gridDim.x * 4 * SCH) {
+      const int cntE = min(SCH, n - e0);
+      int l_ptx0 = 0, l_ptx1 = 0, l_pty0 = 0, l_pty1 = 0;
+      float l_ori = 0.f, l_cos = 0.f, l_sin = 0.f;
+      if (lane < cntE) {
+          const size_t eo = (size_t)img * b.E + e0 + lane;
+          const double x = b.ex[eo], y = b.ey[eo], th = b.eth[eo];
+          double sn, cs;
+          sincos(th, &sn, &cs);
+          // utility.cpp:128-139 and the cv::KeyPoint(Point2d, 1, 180 / M_PI * theta) constructor (narrowing to float); cvRound
+          l_ptx0 = __float2int_rn((float)(x + 8.0 * sn)); l_ptx1 = __float2int_rn((float)(x + 8.0 * (-sn)));
+          l_pty0 = __float2int_rn((float)(y + 8.0 * (-cs))); l_pty1 = __float2int_rn((float)(y + 8.0 * cs));
+          const float angle = (float)(180 / 3.14159265358979323846 * th);
+          float ori = 360.f - angle;
+          if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
+          l_ori = ori;
+          l_cos = cosf(ori * (float)(3.14159265358979323846 / 180)) / hist_width;
+          l_sin = sinf(ori * (float)(3.14159265358979323846 / 180)) / hist_width;
+      }
+      for (int q = 0; q < cntE; ++q) {
+        const size_t eo = (size_t)img * b.E + e0 + q;
+        const int ptx[2] = {__shfl_sync(0xffffffffu, l_ptx0, q), __shfl_sync(0xffffffffu, l_ptx1, q)};
+        const int pty[2] = {__shfl_sync(0xffffffffu, l_pty0, q), __shfl_sync(0xffffffffu, l_pty1, q)};
+        const float ori = __shfl_sync(0xffffffffu, l_ori, q), cos_t = __shfl_sync(0xffffffffu, l_cos, q), sin_t = __shfl_sync(0xffffffffu, l_sin, q);
         {
             uint4* hz = reinterpret_cast<uint4*>(&s_h[w][0][0]);
             for (int k = lane; k < 2 * SHIST / 4; k += 32) hz[k] = make_uint4(0u, 0u, 0u, 0u);
         }
-        float ori = 360.f - angle;
-        if (fabsf(ori - 360.f) < FLT_EPSILON) ori = 0.f;
-        float cos_t = cosf(ori * (float)(3.14159265358979323846 / 180)), sin_t = sinf(ori * (float)(3.14159265358979323846 / 180));
-        cos_t /= hist_width; sin_t /= hist_width;
         // samples inside the descriptor window, in sample order
         int cnt = 0;
 #pragma unroll
@@ -234,6 +248,7 @@ __global__ void __launch_bounds__(128) sift_desc_kernel(DevBatch b)
             reinterpret_cast<uint32_t*>(b.desc8 + (eo * 2 + side) * 128)[lane] = pk;
         }
         __syncwarp();
+      }
     }
 }
 
