@@ -8,6 +8,7 @@
 // No CPU fallback: when the context cannot be created the caller reports the error the reference way (a LOG_ERROR-style
 // print) and returns an empty result.
 #pragma once
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,13 +20,35 @@
 
 namespace ebvo_dropin {
 
+// Grow-only host buffer for per-frame results, page-locked through the library (ebvo_host_alloc) so that the device -> host
+// copies of a frame's mates, patches and descriptors are direct DMA transfers; plain memory when that allocation fails.
+// Kept for the life of the process like the context (a fresh 90 MB of zero-filled vectors per frame cost 8 ms).
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    void* ensure(size_t bytes)
+    {
+        if (bytes <= cap) return p;
+        if (p) { if (pinned) ebvo_host_free(p); else std::free(p); }
+        const size_t want = bytes + bytes / 4;
+        p = ebvo_host_alloc(want);
+        pinned = p != nullptr;
+        if (!p) p = std::malloc(want);
+        cap = p ? want : 0;
+        return p;
+    }
+    float* floats(size_t n) { return static_cast<float*>(ensure(n * sizeof(float))); }
+};
+
 // what get_Stereo_Edge_Pairs already computed for finalize_stereo_edge_mates (same call, same upload): right patches and
-// right descriptor pairs of the mates, valid while `frame` / `n` / the first and last mate still identify the same result
+// right descriptor pairs of the mates (in Shared::r_plus / r_minus / r_desc), valid while `frame` / `n` / the first and
+// last mate still identify the same result
 struct FinalizeCache {
     const void* frame = nullptr;
     size_t n = 0;
     double x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    std::vector<float> r_plus, r_minus, r_desc;
+    bool has_desc = false;
 };
 
 struct Shared {
@@ -33,6 +56,7 @@ struct Shared {
     ebvo_ctx* ctx = nullptr;
     int w = 0, h = 0, edges = 0;
     FinalizeCache fin;
+    HostBuf mates, l_plus, l_minus, l_desc, r_plus, r_minus, r_desc;
 };
 inline Shared& shared()
 {
@@ -88,6 +112,21 @@ inline double kernel_ms(ebvo_ctx* c, const char* const* prefixes, int np)
             if (std::strncmp(names[k], prefixes[p], std::strlen(prefixes[p])) == 0) { t += ms[k]; break; }
     return t;
 }
+
+// EBVO_DROPIN_TRACE=1: wall-clock milliseconds of the drop-in's own sections on stderr (where a member's time goes)
+struct Trace {
+    bool on;
+    const char* who;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char* w) : on(std::getenv("EBVO_DROPIN_TRACE") != nullptr), who(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ebvo trace] %s: %s %.3f ms\n", who, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // Tightly packed copy of an 8-bit single-channel image given (data, rows, cols, step in bytes).
 inline std::vector<unsigned char> packed_u8(const unsigned char* data, int rows, int cols, size_t step)

@@ -90,8 +90,10 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     const size_t nF = pairs.focused_edge_indices.size();
     const int nR = (int)f.right_edges.size();
     const int cap = (int)std::max<size_t>(std::max<size_t>(nF, (size_t)nR), 1);
+    ebvo_dropin::Trace tr("get_Stereo_Edge_Pairs");
     ebvo_dropin::Lease lease(W, H, cap);
     ebvo_ctx* ctx = lease.ctx;
+    tr.mark("lease");
 
     // what the reference's stages leave behind even when nothing survives
     auto fail_empty = [&]() {
@@ -132,18 +134,21 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     // their descriptor pairs (:1627-1635)
     const bool sift = ebvo_dropin::sift_enabled();
     const size_t capM = std::max<size_t>(nF, 1);
-    std::vector<ebvo_mate> mates(capM);
-    std::vector<float> pp(capM * 49), pm(capM * 49), dl(sift ? capM * 256 : 0);
-    ebvo_dropin::FinalizeCache& fin = ebvo_dropin::shared().fin;
+    ebvo_dropin::Shared& S = ebvo_dropin::shared();
+    ebvo_dropin::FinalizeCache& fin = S.fin;
     fin = ebvo_dropin::FinalizeCache();
-    fin.r_plus.resize(capM * 49); fin.r_minus.resize(capM * 49); fin.r_desc.resize(sift ? capM * 256 : 0);
+    ebvo_mate* mates = static_cast<ebvo_mate*>(S.mates.ensure(capM * sizeof(ebvo_mate)));
+    float *pp = S.l_plus.floats(capM * 49), *pm = S.l_minus.floats(capM * 49), *dl = sift ? S.l_desc.floats(capM * 256) : nullptr;
+    float *rp = S.r_plus.floats(capM * 49), *rm = S.r_minus.floats(capM * 49), *rd = sift ? S.r_desc.floats(capM * 256) : nullptr;
+    if (!mates || !pp || !pm || !rp || !rm || (sift && (!dl || !rd))) { std::printf("\033[1;31m[ERROR] out of host memory for the result buffers\033[0m\n"); return fail_empty(); }
     int n = 0;
+    tr.mark("inputs + host buffers");
     int rc = ebvo_stereo_match_full(ctx, &calib, ptr[0], ptr[1], ptr[2], ptr[3], W, H, (int)step, L.data(), (int)nF, R.data(), nR,
-                                    mates.data(), (int)mates.size(), &n, pp.data(), pm.data(), fin.r_plus.data(), fin.r_minus.data(),
-                                    sift ? dl.data() : nullptr, sift ? fin.r_desc.data() : nullptr);
+                                    mates, (int)capM, &n, pp, pm, rp, rm, dl, rd);
+    tr.mark("ebvo_stereo_match_full");
     if (rc != EBVO_OK) { log_error("ebvo_stereo_match_full", ctx, rc); fin = ebvo_dropin::FinalizeCache(); return fail_empty(); }
     if (n > 0) {
-        fin.frame = pairs.stereo_frame; fin.n = (size_t)n;
+        fin.frame = pairs.stereo_frame; fin.n = (size_t)n; fin.has_desc = sift;
         fin.x0 = mates[0].rx; fin.y0 = mates[0].ry; fin.x1 = mates[n - 1].rx; fin.y1 = mates[n - 1].ry;
     }
     {   // Timing_Statistics (Stereo_Matches.h:32-47; the reference's own assignments are commented out at :1376-1538): kernel
@@ -204,6 +209,7 @@ Frame_Evaluation_Metrics Stereo_Matches::get_Stereo_Edge_Pairs(Dataset::Ptr data
     pairs.epip_line_coeffs_of_left_edges.swap(lines);
     pairs.left_edge_patches.swap(patches);
     pairs.matching_edge_clusters.swap(clusters);
+    tr.mark("containers");
     return frame_metrics;
 }
 
@@ -216,8 +222,10 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         std::printf("\033[1;31m[ERROR] Vector sizes are not consistent in finalize_stereo_edge_mates\033[0m\n");
         return;
     }
+    ebvo_dropin::Trace tr("finalize_stereo_edge_mates");
     final_stereo_edge_pairs.clear();
     final_stereo_edge_pairs.resize(n);
+    tr.mark("resize");
     if (n == 0) { std::cout << "Size of finalized stereo edge pairs = 0" << std::endl; return; }
 
     // right patches (UNDISTORTED right image, :1580-1582, :1622) and right descriptor pairs (:1627-1635) of every mate: the
@@ -234,11 +242,12 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
     ebvo_ctx* ctx = lease.ctx;
     if (!ctx) { final_stereo_edge_pairs.clear(); return; }
     const bool sift = ebvo_dropin::sift_enabled();
-    ebvo_dropin::FinalizeCache& fin = ebvo_dropin::shared().fin;
+    ebvo_dropin::Shared& S = ebvo_dropin::shared();
+    const ebvo_dropin::FinalizeCache& fin = S.fin;
     const bool cached = fin.frame == pairs.stereo_frame && fin.n == n && fin.x0 == Rm[0].x && fin.y0 == Rm[0].y && fin.x1 == Rm[n - 1].x &&
-                        fin.y1 == Rm[n - 1].y && fin.r_plus.size() >= n * 49 && (!sift || fin.r_desc.size() >= n * 256);
+                        fin.y1 == Rm[n - 1].y && S.r_plus.cap >= n * 49 * sizeof(float) && (!sift || (fin.has_desc && S.r_desc.cap >= n * 256 * sizeof(float)));
     std::vector<float> pp_own, pm_own, dr_own;
-    const float *pp = fin.r_plus.data(), *pm = fin.r_minus.data(), *dr = sift ? fin.r_desc.data() : nullptr;
+    const float *pp = static_cast<const float*>(S.r_plus.p), *pm = static_cast<const float*>(S.r_minus.p), *dr = sift ? static_cast<const float*>(S.r_desc.p) : nullptr;
     if (!cached) {
         pp_own.resize(n * 49); pm_own.resize(n * 49);
         const std::vector<unsigned char> Rund = ebvo_dropin::packed_u8(Rimg.data, H, W, Rimg.step);
@@ -252,6 +261,7 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         pp = pp_own.data(); pm = pm_own.data(); dr = sift ? dr_own.data() : nullptr;
     }
 
+    tr.mark("right patches + descriptors");
 #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; ++i) {
         final_stereo_edge_pair mate;
@@ -267,5 +277,6 @@ void Stereo_Matches::finalize_stereo_edge_mates(Stereo_Edge_Pairs& pairs, std::v
         mate.b_is_TP = cv::norm(mate.right_edge.location - pairs.GT_locations_from_left_edges[i]) <= DIST_TO_GT_THRESH;   // :1645
         final_stereo_edge_pairs[i] = mate;
     }
+    tr.mark("final_stereo_edge_pair objects");
     std::cout << "Size of finalized stereo edge pairs = " << final_stereo_edge_pairs.size() << std::endl;
 }

@@ -20,7 +20,7 @@ EXPORTS = [
     "ebvo_stereo_match", "ebvo_stereo_match_full", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_batch_pack", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
     "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_launch_count", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
-    "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream",
+    "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream", "ebvo_host_alloc", "ebvo_host_free",
     "ebvo_temporal_quads", "ebvo_temporal_quads_stage", "ebvo_temporal_counters",
 ]
 

@@ -1197,4 +1197,12 @@ int ebvo_get_kernel_times(ebvo_ctx* ctx, const char*** names, const float** ms, 
 }
 void* ebvo_stream(ebvo_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
 
+void* ebvo_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void ebvo_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 }  // extern "C"

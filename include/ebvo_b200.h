@@ -13,6 +13,7 @@
 #ifndef EBVO_B200_H
 #define EBVO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -272,6 +273,12 @@ int ebvo_get_kernel_times(ebvo_ctx* ctx, const char*** names, const float** ms, 
 long long ebvo_launch_count(ebvo_ctx* ctx);
 /* The CUDA stream (cudaStream_t) the context launches on, for external event timing. */
 void* ebvo_stream(ebvo_ctx* ctx);
+/* Page-locked host memory for the buffers a caller hands to the entry points above (images in, mates / patches /
+ * descriptors out): copies to and from such buffers are direct DMA transfers instead of staged ones.  Plain memory works
+ * everywhere; this is an optimisation the C++ drop-ins use for their per-frame result buffers (the reference has no
+ * counterpart: its results never leave host memory).  ebvo_host_alloc returns NULL when the allocation fails. */
+void* ebvo_host_alloc(size_t bytes);
+void ebvo_host_free(void* p);
 
 #ifdef __cplusplus
 }
