@@ -212,9 +212,11 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic frames per GPU (default: the batch size, i.e. every frame of the "
                     "batch is its own scene; smaller values are cycled to fill the batch)")
     ap.add_argument("--strong-frames", type=int, default=1000, help="frames of the ONE batch that the strong-scaling leg splits over the ranks (0 = skip)")
-    ap.add_argument("--strong-gather", default="host", choices=["host", "nccl"],
-                    help="final gather of the strong-scaling leg: host = every rank copies its records device -> host over its own PCIe link into one "
-                         "shared page-locked buffer (sharding.HostGather); nccl = device-to-device sends to rank 0, then one D2H (sharding.gather_packed)")
+    ap.add_argument("--strong-gather", default="stream", choices=["stream", "host", "nccl"],
+                    help="final gather of the strong-scaling leg: stream = every rank's ebvo_stereo_batch_packed copies each finished sub-batch's records "
+                         "over its own PCIe link into its slice of one shared page-locked host buffer while its next sub-batches compute "
+                         "(sharding.HostGather.region / finish); host = the same buffer, but one copy per rank after its last kernel; "
+                         "nccl = device-to-device sends to rank 0, then one D2H (sharding.gather_packed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="kitti", choices=["kitti", "euroc", "4k"],
                     help="kitti = the BASELINE.json metric (default); euroc / 4k = BASELINE configs[1] / configs[4] shapes (extra measurements)")
@@ -356,11 +358,33 @@ def main():
         cap_rec = int(max(nloc, 1) * per_frame)
         packed = torch.empty((cap_rec, 64), dtype=torch.uint8, device=dev)
         offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        use_host = world > 1 and args.strong_gather == "host"
-        h_res = torch.empty((int(FS * per_frame), 64), dtype=torch.uint8).pin_memory() if (rank == 0 and not use_host) else None
-        hg = sharding.HostGather(int(FS * per_frame) * 64, dist, tag="bench") if use_host else None
+        mode = args.strong_gather
+        use_host = world > 1 and mode == "host"
+        use_stream = mode == "stream"
+        pf_rec = int(per_frame)
+        h_res = torch.empty((int(FS * per_frame), 64), dtype=torch.uint8).pin_memory() if (rank == 0 and not use_host and not (use_stream and world > 1)) else None
+        hg = sharding.HostGather(world * (-(-FS // world)) * pf_rec * 64, dist, tag="bench") if (world > 1 and (use_host or use_stream)) else None
 
         def strong_pass():
+            if use_stream:
+                # every sub-batch's records go to host memory (this rank's slice of the shared buffer) while the next ones compute
+                if hg is not None:
+                    addr, cap, _ = hg.region(FS, pf_rec)
+                else:
+                    addr, cap = h_res.data_ptr(), h_res.shape[0]
+                pos, counts = 0, []
+                for s0 in range(0, nloc, B):
+                    n = min(B, nloc - s0)
+                    nm, wrote = ctx.stereo_batch_packed(calib, nL_imgs[:n], nR_imgs[:n], addr + pos * 64, cap - pos)
+                    pos += wrote
+                    counts.append(nm.copy())
+                tg = time.perf_counter()
+                nrec = pos
+                if hg is not None:
+                    segs, allc = hg.finish(np.concatenate(counts) if counts else np.zeros(0, np.int32), FS, pf_rec, device=dev)
+                    if rank == 0:
+                        nrec = int(sum(int(sg.shape[0]) for sg in segs))
+                return time.perf_counter() - tg, nrec
             pos, counts = 0, []
             for s0 in range(0, nloc, B):          # this rank's block, in sub-batches of the context's capacity
                 n = min(B, nloc - s0)
@@ -395,7 +419,8 @@ def main():
             gs, nrec = strong_pass()
             g_s += gs
         barrier()
-        strong = [(time.perf_counter() - t0) / reps, g_s / reps, nrec, "host" if use_host else ("nccl" if world > 1 else "single device: one D2H")]
+        strong = [(time.perf_counter() - t0) / reps, g_s / reps, nrec,
+                  "stream" if use_stream else ("host" if use_host else ("nccl" if world > 1 else "single device: one D2H"))]
         if hg is not None:
             hg.close()
         del packed, h_res
@@ -498,11 +523,14 @@ def main():
             FS = args.strong_frames
             line["strong_scaling"] = {
                 "workload": "configs[2]: ONE %d-frame KITTI-shape batch split into contiguous blocks of ceil(F/N) frames per rank "
-                            "(sharding.shard_range; %d distinct scenes per rank cycled), host images in (ebvo_stereo_batch, pipelined H2D), results packed "
-                            "on the device (ebvo_batch_pack) and gathered at their exact size into ONE host buffer of rank 0's process - %s - "
-                            "all inside the timed region" % (FS, len(base), {"host": "every rank copies its records device -> host over its own PCIe link into its "
+                            "(sharding.shard_range; %d distinct scenes per rank cycled), host images in (pipelined H2D), every mate record gathered "
+                            "into host memory of rank 0's process - %s - all inside the timed region" % (FS, len(base), {
+                            "stream": "ebvo_stereo_batch_packed: each rank copies every finished sub-batch's records over its own PCIe link into its slice of "
+                            "one shared page-locked buffer (sharding.HostGather.region) while its next sub-batches compute; after the last copy only the "
+                            "per-frame counts are exchanged (one all_gather + barrier: gather_ms_rank0)",
+                            "host": "results packed on the device (ebvo_batch_pack), then every rank copies its records device -> host over its own PCIe link into its "
                             "slice of a shared page-locked buffer (sharding.HostGather; counts all_gather + barrier are the only exchange)",
-                            "nccl": "counts all_gather + NCCL send/recv to rank 0's GPU (sharding.gather_packed), then one D2H"}.get(strong[3], strong[3])),
+                            "nccl": "results packed on the device (ebvo_batch_pack), counts all_gather + NCCL send/recv to rank 0's GPU (sharding.gather_packed), then one D2H"}.get(strong[3], strong[3])),
                 "gather": strong[3],
                 "frames": FS, "n_gpus": world, "frames_per_gpu": -(-FS // world), "value": FS / (strong_ms / 1e3), "unit": "frames/s",
                 "ms": strong_ms, "gather_ms_rank0": strong[1] * 1e3, "gather_share": strong[1] * 1e3 / strong_ms if strong_ms else None,

@@ -17,7 +17,7 @@ STAGES = ["epi", "disp", "orient", "sift", "ncc", "bnb_ncc", "bnb_sift", "shift"
 
 EXPORTS = [
     "ebvo_params_default", "ebvo_create", "ebvo_destroy", "ebvo_last_error", "ebvo_fundamental", "ebvo_toed",
-    "ebvo_stereo_match", "ebvo_stereo_match_full", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
+    "ebvo_stereo_match", "ebvo_stereo_match_full", "ebvo_stereo_frame", "ebvo_stereo_batch", "ebvo_stereo_batch_packed", "ebvo_stereo_batch_multi", "ebvo_batch_upload", "ebvo_batch_run",
     "ebvo_batch_sync", "ebvo_batch_download", "ebvo_batch_counts", "ebvo_batch_pack", "ebvo_edge_patches", "ebvo_ncc_patch_pair",
     "ebvo_cluster", "ebvo_sobel", "ebvo_sift_descriptors", "ebvo_undistort", "ebvo_launch_count", "ebvo_set_stage_dumps", "ebvo_stage_size", "ebvo_stage_fetch",
     "ebvo_set_profiling", "ebvo_get_kernel_times", "ebvo_stream", "ebvo_host_alloc", "ebvo_host_free",
@@ -94,6 +94,10 @@ def load():
         L = C.CDLL(LIB_PATH)
         L.ebvo_last_error.restype = C.c_char_p
         L.ebvo_last_error.argtypes = [C.c_void_p]
+        L.ebvo_host_alloc.restype = C.c_void_p
+        L.ebvo_host_alloc.argtypes = [C.c_size_t]
+        L.ebvo_host_free.restype = None
+        L.ebvo_host_free.argtypes = [C.c_void_p]
         L.ebvo_stream.restype = C.c_void_p
         L.ebvo_stream.argtypes = [C.c_void_p]
         L.ebvo_destroy.argtypes = [C.c_void_p]
@@ -259,6 +263,19 @@ class Context:
                                           L_imgs[0].strides[0], None, 0x7fffffff, _p(n_mates)))
         self._nframes = F
         return n_mates
+
+    def stereo_batch_packed(self, calib, L_imgs, R_imgs, out_ptr: int, cap_records: int, n_mates=None):
+        """ebvo_stereo_batch_packed: host images in, the batch's mates back to back at the HOST address out_ptr (streamed out
+        sub-batch by sub-batch while the rest computes).  Returns (n_mates, records written)."""
+        F = len(L_imgs)
+        h, w = L_imgs[0].shape
+        if n_mates is None:
+            n_mates = np.zeros(F, np.int32)
+        tot = C.c_longlong()
+        self._ck(self.L.ebvo_stereo_batch_packed(self.h, C.byref(calib), F, self._ptr_array(L_imgs), self._ptr_array(R_imgs), w, h,
+                                                 L_imgs[0].strides[0], C.c_void_p(out_ptr), C.c_longlong(cap_records), _p(n_mates), C.byref(tot)))
+        self._nframes = F
+        return n_mates, tot.value
 
     def batch_pack(self, dst_ptr: int, cap_records: int, offsets_ptr: int) -> int:
         """Pack the last batch's mates (device-resident) back to back into a caller-owned DEVICE buffer; returns the record count."""

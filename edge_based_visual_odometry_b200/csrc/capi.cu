@@ -771,8 +771,10 @@ int ebvo_batch_counts(ebvo_ctx* ctx, int* nL, int* nR, int* n_mates, long long* 
     return EBVO_OK;
 }
 
-int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
-                      int h, int stride, ebvo_mate* out, int cap, int* n_mates)
+// dense = false: frame f's mates at out + f * cap (ebvo_stereo_batch); dense = true: frame f's mates follow frame f - 1's, at most
+// cap_records in all (ebvo_stereo_batch_packed)
+static int stereo_batch_impl(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
+                             int h, int stride, ebvo_mate* out, int cap, int* n_mates, bool dense, long long cap_records, long long* total)
 {
     if (!ctx || !calib || !L_imgs || !R_imgs) return EBVO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -806,16 +808,20 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         return EBVO_OK;
     };
     int over = EBVO_OK;
+    long long written = 0;
     auto download = [&](int k) -> int {
         const int f0 = k * SB, f1 = std::min(n_frames, f0 + SB);
         CK(cudaStreamWaitEvent(ctx->stOut, ctx->evDone[k], 0));
         CK(cudaMemcpyAsync(ctx->h_counts.data() + f0, b.nMates + f0, sizeof(int) * (f1 - f0), cudaMemcpyDeviceToHost, ctx->stOut));
         CK(cudaStreamSynchronize(ctx->stOut));
         for (int f = f0; f < f1; ++f) {
-            const int n = ctx->h_counts[f], m = std::min(n, cap);
+            const int n = ctx->h_counts[f];
+            const int m = dense ? (int)std::max<long long>(0, std::min<long long>(n, cap_records - written)) : std::min(n, cap);
             if (n_mates) n_mates[f] = n;
-            if (n > cap) { ctx->err = "output mate buffer too small"; over = EBVO_ERR_CAPACITY; }
-            if (out && m) CK(cudaMemcpyAsync(out + (size_t)f * cap, ctx->d_out + (size_t)f * b.E, sizeof(ebvo_mate) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stOut));
+            if (n > m) { ctx->err = "output mate buffer too small"; over = EBVO_ERR_CAPACITY; }
+            ebvo_mate* dst = dense ? out + written : out + (size_t)f * cap;
+            if (out && m) CK(cudaMemcpyAsync(dst, ctx->d_out + (size_t)f * b.E, sizeof(ebvo_mate) * (size_t)m, cudaMemcpyDeviceToHost, ctx->stOut));
+            written += m;
         }
         return EBVO_OK;
     };
@@ -851,7 +857,21 @@ int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, cons
         if (rc) { ctx->prof.collect(); return rc; }
     }
     ctx->prof.collect();
+    if (total) *total = written;
     return over;
+}
+
+int ebvo_stereo_batch(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
+                      int h, int stride, ebvo_mate* out, int cap, int* n_mates)
+{
+    return stereo_batch_impl(ctx, calib, n_frames, L_imgs, R_imgs, w, h, stride, out, cap, n_mates, false, 0, nullptr);
+}
+
+int ebvo_stereo_batch_packed(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs, const uint8_t* const* R_imgs, int w,
+                             int h, int stride, ebvo_mate* out, long long cap_records, int* n_mates, long long* total)
+{
+    if (!out || cap_records < 0) return EBVO_ERR_INVALID;
+    return stereo_batch_impl(ctx, calib, n_frames, L_imgs, R_imgs, w, h, stride, out, 0, n_mates, true, cap_records, total);
 }
 
 int ebvo_stereo_batch_multi(ebvo_ctx* const* ctxs, int n_ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,

@@ -107,6 +107,38 @@ class HostGather:
         total = sum(per_rank)
         return self.buf[:total * 64].view(total, 64), allc_h[:n_frames]
 
+    def region(self, n_frames: int, per_frame_records: int):
+        """This rank's slice of the shared buffer for a STREAMED gather: (host address, capacity in records, record offset).
+        A rank hands the address to ebvo_stereo_batch_packed, which copies every finished sub-batch's mates there while the
+        next sub-batches compute; finish() then only exchanges the per-frame counts."""
+        per = (n_frames + self.world - 1) // self.world
+        cap = per * int(per_frame_records)
+        if (self.world * cap) * 64 > self.nbytes:
+            raise RuntimeError("HostGather buffer too small")
+        off = self.rank * cap
+        return self.buf.data_ptr() + off * 64, cap, off
+
+    def finish(self, counts, n_frames: int, per_frame_records: int, device=None, dst: int = 0):
+        """After every rank's ebvo_stereo_batch_packed into region(): counts = this rank's per-frame mate counts (int32 numpy
+        or tensor).  Returns ([records of rank 0's frames, records of rank 1's frames, ...] - views of the shared buffer -,
+        counts[n_frames]) on `dst`, (None, None) elsewhere."""
+        import torch
+        dist, world = self.dist, self.world
+        per = (n_frames + world - 1) // world
+        cap = per * int(per_frame_records)
+        counts = torch.as_tensor(counts, dtype=torch.int32)
+        pad = torch.zeros(per, dtype=torch.int32, device=device)
+        pad[:counts.numel()] = counts.to(pad.device)
+        allc = torch.empty(world * per, dtype=torch.int32, device=device)
+        dist.all_gather(list(allc.view(world, per).unbind(0)), pad)
+        dist.barrier()                                     # every rank's copies have landed (its call returned before its all_gather)
+        if self.rank != dst:
+            return None, None
+        allc_h = allc.cpu()
+        per_rank = allc_h.view(world, per).sum(dim=1).tolist()
+        segs = [self.buf[r * cap * 64:(r * cap + n) * 64].view(n, 64) for r, n in enumerate(per_rank)]
+        return segs, allc_h[:n_frames]
+
     def close(self):
         import os
         import torch

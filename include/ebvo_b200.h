@@ -218,6 +218,14 @@ int ebvo_temporal_quads_stage(ebvo_ctx* ctx, const uint8_t* kf_Lraw, const uint8
  * 3 grid candidates, 4 orientation survivors (8 values). */
 int ebvo_temporal_counters(ebvo_ctx* ctx, long long* out8);
 
+/* ebvo_stereo_batch with the mates of the whole batch back to back: frame f's records follow frame f - 1's in `out`
+ * (n_mates[f] of them; *total = records written, at most cap_records, EBVO_ERR_CAPACITY beyond).  Every sub-batch's records
+ * are copied out while the next sub-batches compute, so when `out` is page-locked memory shared by the processes of a box
+ * (one slice per GPU: edge_based_visual_odometry_b200/sharding.py HostGather) the call IS the final result gather of a
+ * batch sharded over the GPUs, overlapped with the computation (Pipeline.cpp:109-131 per frame; BASELINE configs[2]). */
+int ebvo_stereo_batch_packed(ebvo_ctx* ctx, const ebvo_calib* calib, int n_frames, const uint8_t* const* L_imgs,
+                             const uint8_t* const* R_imgs, int w, int h, int stride, ebvo_mate* out, long long cap_records,
+                             int* n_mates, long long* total);
 /* The same batch over several contexts (normally one per GPU of the box): frames are split into contiguous blocks of
  * ceil(n_frames / n_ctx), one host thread per context, no exchange between devices (frames are independent:
  * src/Pipeline.cpp:64-145 reads nothing from other frames); results land in out / n_mates at their global frame index.

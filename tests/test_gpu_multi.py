@@ -65,6 +65,18 @@ def _worker(rank, world, port, F, q):
         assert hg._registered and np.array_equal(hp.numpy(), allp.cpu().numpy()) and np.array_equal(hc.numpy(), allc.cpu().numpy())
     del hp
     hg.close()
+    # the streamed gather: ebvo_stereo_batch_packed writes this rank's records into its region of the shared buffer during the computation
+    per_frame = 12000
+    hs = sharding.HostGather(2 * (-(-F // world)) * per_frame * 64, dist, tag="s")
+    addr, cap, _ = hs.region(F, per_frame)
+    nm2, wrote = ctx.stereo_batch_packed(_calib(cal), Ls[lo:hi], Rs[lo:hi], addr, cap)
+    segs, sc = hs.finish(nm2, F, per_frame, device=dev)
+    if rank == 0:
+        got = np.concatenate([sg.numpy().copy() for sg in segs])
+        assert hs._registered and np.array_equal(got, allp.cpu().numpy()) and np.array_equal(sc.numpy(), allc.cpu().numpy())
+    assert wrote == int(nm.sum()) and np.array_equal(nm2, nm)
+    del segs
+    hs.close()
     if rank == 0:
         one = _lib.Context(0, 480, 200, max_batch=F, max_edges=16384)
         ref, nref = one.stereo_batch(_calib(cal), Ls, Rs, cap=12000)
@@ -92,6 +104,24 @@ def test_sharded_batch_nccl_gather_two_gpus():
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_packed_batch_call_equals_the_padded_one():
+    """ebvo_stereo_batch_packed on one GPU: host images in, the batch's mates back to back in (page-locked) host memory,
+    equal to ebvo_stereo_batch's padded output frame by frame; a buffer that is too small reports EBVO_ERR_CAPACITY."""
+    cal, Ls, Rs = _frames(37)                      # three sub-batches of the 16-frame pipeline, the last one ragged
+    ctx = _lib.Context(0, 480, 200, max_batch=37, max_edges=16384)
+    ref, nref = ctx.stereo_batch(_calib(cal), Ls, Rs, cap=12000)
+    buf = torch.empty((int(nref.sum()) + 5, 64), dtype=torch.uint8).pin_memory()
+    nm, wrote = ctx.stereo_batch_packed(_calib(cal), Ls, Rs, buf.data_ptr(), buf.shape[0])
+    assert wrote == int(nref.sum()) and np.array_equal(nm, nref)
+    rec = buf[:wrote].numpy().reshape(-1).view(_lib.MATE_DTYPE)
+    o = np.concatenate([[0], np.cumsum(nref)])
+    for f in range(37):
+        assert np.array_equal(rec[o[f]:o[f + 1]], ref[f, :nref[f]])
+    with pytest.raises(_lib.EbvoError):
+        ctx.stereo_batch_packed(_calib(cal), Ls, Rs, buf.data_ptr(), int(nref.sum()) - 1)
+    ctx.close()
 
 
 def test_batch_pack_matches_download():
