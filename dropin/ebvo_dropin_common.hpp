@@ -56,7 +56,9 @@ struct Shared {
     ebvo_ctx* ctx = nullptr;
     int w = 0, h = 0, edges = 0;
     FinalizeCache fin;
-    HostBuf mates, l_plus, l_minus, l_desc, r_plus, r_minus, r_desc;
+    HostBuf mates, l_plus, l_minus, l_desc, r_plus, r_minus, r_desc;      // stereo drop-in: results of a frame
+    HostBuf quads, tq_desc[4];                                             // quad-tracking drop-in: result records, descriptor staging
+    size_t tq_last = 0;                                                    // quads of the previous call (sizes the next result buffer)
 };
 inline Shared& shared()
 {

@@ -55,6 +55,7 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
     const int W = current_frame.left_image.cols, H = current_frame.left_image.rows;
     const int n_kf = (int)KF.size(), n_cf = (int)CF.size();
     if (quads.empty() || n_kf == 0) return frame_metrics;
+    ebvo_dropin::Trace tr("get_Temporal_Edge_Pairs_from_Quads");
     ebvo_dropin::Lease lease(W, H, 1);
     ebvo_ctx* ctx = lease.ctx;
     if (!ctx) return frame_metrics;
@@ -79,32 +80,56 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
     const std::vector<unsigned char> kL = pack(keyframe.left_image), kLu = pack(keyframe.left_image_undistorted), kRu = pack(keyframe.right_image_undistorted);
     const std::vector<unsigned char> cL = pack(current_frame.left_image), cLu = pack(current_frame.left_image_undistorted), cRu = pack(current_frame.right_image_undistorted);
     ebvo_quad_params qp{left_spatial_grids.cell_size, 0, 30.0, 10.0, 0.8, 0.8, 200.0};     // thresholds as written at :185-196
-    // descriptor pairs of the mates (filled by the stereo stage's drop-in in its default SIFT-on flow): all present => SIFT-on
-    auto descs = [](const std::vector<final_stereo_edge_pair>& v, bool right, std::vector<float>& out) {
-        out.assign(v.size() * 256, 0.f);
-        for (size_t i = 0; i < v.size(); ++i) {
-            const auto& p = right ? v[i].right_edge_descriptors : v[i].left_edge_descriptors;
-            if (p.first.empty() || p.second.empty() || p.first.cols != 128 || p.second.cols != 128) return false;
-            for (int k = 0; k < 128; ++k) { out[i * 256 + k] = p.first.at<float>(0, k); out[i * 256 + 128 + k] = p.second.at<float>(0, k); }
+    // descriptor pairs of the mates (filled by the stereo stage's drop-in in its default SIFT-on flow): all present => SIFT-on.
+    // They are staged in page-locked buffers the drop-in keeps (4 x 26 MB per KITTI-shape pair; fresh zero-filled vectors and
+    // pageable uploads cost more than the kernels).
+    ebvo_dropin::Shared& S = ebvo_dropin::shared();
+    auto descs = [](const std::vector<final_stereo_edge_pair>& v, bool right, ebvo_dropin::HostBuf& hb, const float*& ptr) {
+        ptr = nullptr;
+        if (v.empty()) return false;
+        float* out = hb.floats(v.size() * 256);
+        if (!out) return false;
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (long long i = 0; i < (long long)v.size(); ++i) {
+            const auto& p = right ? v[(size_t)i].right_edge_descriptors : v[(size_t)i].left_edge_descriptors;
+            if (p.first.empty() || p.second.empty() || p.first.cols != 128 || p.second.cols != 128) { bad |= 1; continue; }
+            std::memcpy(out + (size_t)i * 256, &p.first.at<float>(0, 0), 128 * sizeof(float));
+            std::memcpy(out + (size_t)i * 256 + 128, &p.second.at<float>(0, 0), 128 * sizeof(float));
         }
-        return !v.empty();
+        ptr = out;
+        return bad == 0;
     };
-    std::vector<float> dkl, dkr, dcl, dcr;
-    const bool sift_on = ebvo_dropin::sift_enabled() && descs(KF, false, dkl) && descs(KF, true, dkr) && descs(CF, false, dcl) && descs(CF, true, dcr);
-    std::vector<ebvo_quad> out((size_t)n_kf * 128);
-    int n = 0;
-    const int rc = ebvo_temporal_quads(ctx, kL.data(), kLu.data(), kRu.data(), cL.data(), cLu.data(), cRu.data(), W, H, W, kf.data(), n_kf,
-                                       mask.data(), cf.data(), n_cf, sift_on ? dkl.data() : nullptr, sift_on ? dkr.data() : nullptr,
-                                       sift_on ? dcl.data() : nullptr, sift_on ? dcr.data() : nullptr, &qp, out.data(), (int)out.size(), &n);
+    const float *dkl = nullptr, *dkr = nullptr, *dcl = nullptr, *dcr = nullptr;
+    const bool sift_on = ebvo_dropin::sift_enabled() && descs(KF, false, S.tq_desc[0], dkl) && descs(KF, true, S.tq_desc[1], dkr) &&
+                         descs(CF, false, S.tq_desc[2], dcl) && descs(CF, true, S.tq_desc[3], dcr);
+    tr.mark("inputs");
+    // result records: sized from the previous call (a keyframe mate keeps 4 quads on average, 128 at most); a call that needs
+    // more says how many and is repeated once
+    size_t cap = std::max<size_t>(std::max<size_t>((size_t)n_kf * 8, S.tq_last + S.tq_last / 2), 1024);
+    cap = std::min<size_t>(cap, (size_t)n_kf * 128);
+    int n = 0, rc = EBVO_OK;
+    ebvo_quad* out = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        out = static_cast<ebvo_quad*>(S.quads.ensure(cap * sizeof(ebvo_quad)));
+        if (!out) { std::printf("\033[1;31m[ERROR] out of host memory for the quad records\033[0m\n"); return frame_metrics; }
+        rc = ebvo_temporal_quads(ctx, kL.data(), kLu.data(), kRu.data(), cL.data(), cLu.data(), cRu.data(), W, H, W, kf.data(), n_kf,
+                                 mask.data(), cf.data(), n_cf, sift_on ? dkl : nullptr, sift_on ? dkr : nullptr,
+                                 sift_on ? dcl : nullptr, sift_on ? dcr : nullptr, &qp, out, (int)cap, &n);
+        if (rc == EBVO_ERR_CAPACITY && (size_t)n > cap && attempt == 0) { cap = (size_t)n; continue; }
+        break;
+    }
+    tr.mark("ebvo_temporal_quads");
     if (rc != EBVO_OK) {
         std::printf("\033[1;31m[ERROR] ebvo_temporal_quads failed (%d): %s\033[0m\n", rc, ebvo_last_error(ctx));
         return frame_metrics;
     }
+    S.tq_last = (size_t)n;
     size_t num_quads = 0;
     for (const auto& kvq : quads) num_quads += kvq.veridical_quads.size();
     std::cout << "Veridical quads: " << quads.size() << " KF groups, " << num_quads << " total quads" << std::endl;     // :182
     for (int k = 0; k < n; ++k) {
-        const ebvo_quad& q = out[(size_t)k];
+        const ebvo_quad& q = out[k];
         const int g = group_of[(size_t)q.kf_index];
         if (g < 0) continue;
         Temporal_CF_Edge_Cluster l, r;
@@ -122,5 +147,6 @@ Frame_Evaluation_Metrics Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads(
         quads[g].candidate_quads.clear();
         for (auto& p : candidate_cluster_pairs_[g]) quads[g].candidate_quads.push_back({&p.first, &p.second});
     }
+    tr.mark("containers");
     return frame_metrics;
 }

@@ -1,5 +1,6 @@
-"""Wall-clock of the C++ drop-in members a maintainer links (run on a GPU box): ProcessEdges' detector call and
-get_Stereo_Edge_Pairs + finalize_stereo_edge_mates on one KITTI-shape frame, SIFT-off and SIFT-on.  JSON lines on stdout."""
+"""Wall-clock of the C++ drop-in members a maintainer links (run on a GPU box): ProcessEdges' detector call,
+get_Stereo_Edge_Pairs + finalize_stereo_edge_mates on one KITTI-shape frame, SIFT-off and SIFT-on, and
+get_Temporal_Edge_Pairs_from_Quads on one KITTI-shape keyframe -> current-frame pair.  JSON lines on stdout."""
 import json, os, subprocess, sys, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,3 +31,25 @@ with tempfile.TemporaryDirectory() as d:
             print(json.dumps(j))
         else:
             print(json.dumps({"failed": r.returncode, "sift": sift, "err": (r.stdout + r.stderr)[-300:]}))
+    # quad tracking: mates of two consecutive frames of a synthetic sequence (device stereo), every keyframe mate takes part
+    from edge_based_visual_odometry_b200 import _lib
+    calib = _lib.make_calib(cal.Kl, cal.Kr, cal.R21, cal.T21)
+    ctx = _lib.Context(0, cal.width, cal.height, max_batch=1, max_edges=131072)
+    fr = []
+    for k in (0, 1):
+        Lk, Rk, _ = synth.stereo_sequence_pair(cal, k)
+        fr.append((Lk, Rk, ctx.stereo_frame(calib, Lk, Rk)[0]))
+    ctx.close()
+    (L0, R0, m0), (L1, R1, m1) = fr
+    six = lambda m: np.ascontiguousarray(np.stack([m[k] for k in ("lx", "ly", "ltheta", "rx", "ry", "rtheta")], 1), np.float64)
+    tin, tout = os.path.join(d, "tq.bin"), os.path.join(d, "tq.json")
+    with open(tin, "wb") as f:
+        np.array([L0.shape[1], L0.shape[0], len(m0), len(m1)], np.int32).tofile(f)
+        for im in (L0, R0, L1, R1):
+            np.ascontiguousarray(im, np.uint8).tofile(f)
+        six(m0).tofile(f); six(m1).tofile(f)
+        np.ones(len(m0), np.uint8).tofile(f)
+    r = subprocess.run([os.path.join(B, "test_dropin_temporal"), tin, tout, "time", reps], capture_output=True, text=True, timeout=900)
+    if os.environ.get("EBVO_DROPIN_TRACE"):
+        sys.stderr.write(r.stderr[-3000:])
+    print(open(tout).read().strip() if r.returncode == 0 else json.dumps({"failed": r.returncode, "err": (r.stdout + r.stderr)[-300:]}))

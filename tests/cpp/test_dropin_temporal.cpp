@@ -8,6 +8,7 @@
 //   in : int32 W, H, n_kf, n_cf; u8 kfL[H*W], kfR[H*W], cfL[H*W], cfR[H*W]; double kf[6*n_kf], cf[6*n_cf]; u8 mask[n_kf]
 //   out: int32 n; n x 13 doubles {kf index, cf index, lx, ly, lth, rx, ry, rth, ncc_l, ncc_r, score_l, score_r, valid}
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -85,6 +86,24 @@ int main(int argc, char** argv)
         quads.push_back(k);
     }
     Stereo_Edge_Pairs kfPairs, cfPairs;
+    if (argc > 4 && std::string(argv[3]) == "time") {   // timing mode: wall clock of the GPU-backed member, argv[4] repetitions after one untimed call
+        const int reps = std::atoi(argv[4]);
+        double ms = 0.0;
+        size_t nq = 0;
+        for (int r = -1; r < reps; ++r) {
+            const auto t0 = std::chrono::steady_clock::now();
+            engine.get_Temporal_Edge_Pairs_from_Quads(quads, KF, CF, gl, gr, kfPairs, cfPairs, keyframe, current, 0, 1);
+            if (r >= 0) ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            nq = 0;
+            for (const auto& q : quads) nq += q.candidate_quads.size();
+        }
+        FILE* o = std::fopen(argv[2], "w");
+        if (!o) return 6;
+        std::fprintf(o, "{\"what\": \"Temporal_Matches::get_Temporal_Edge_Pairs_from_Quads (GPU drop-in), one keyframe -> current-frame pair\", \"H\": %d, \"W\": %d, "
+                        "\"kf_mates\": %d, \"cf_mates\": %d, \"quads\": %zu, \"wall_ms\": %.3f}\n", H, W, n_kf, n_cf, nq, ms / reps);
+        std::fclose(o);
+        return 0;
+    }
     engine.get_Temporal_Edge_Pairs_from_Quads(quads, KF, CF, gl, gr, kfPairs, cfPairs, keyframe, current, 0, 1);   // Pipeline.cpp:159-167 (GPU-backed)
 
     std::vector<double> rows;
