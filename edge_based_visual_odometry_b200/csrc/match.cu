@@ -1188,6 +1188,9 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                     reach = fmin(reach, shfl_xor_d(reach, 16));
                     if (reach >= 1.0) { alpha0 = 0.0; Rv = reach - 1e-6; }
                 }
+                // rectified pairs (KITTI): the first row of F is exactly zero, so every epipolar direction is (+-1, 0) and the vertical Sobel
+                // channel enters the Jacobian with the factor 0 (the Sobel values are finite): same bits without its interpolation
+                const bool useGy = diry != 0.0;
                 for (int it = 0; it < p.gn_max_iter; ++it) {
                     const double xs = xc + alpha * dirx, ys = yc + alpha * diry;     // (location +- n*side) + shift (:1203-1204)
                     if (!(fabs(alpha - alpha0) <= Rv)) {
@@ -1226,9 +1229,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) gn_lerp64_kernel(DevBatch b, D
                         VI(m) = vim;
                         top = fma(a, h2d(d0y), h2d(p00.y)); bot = fma(a, h2d(d1y), h2d(p01.y));
                         const double gx = round_to_float(fma(bb, bot - top, top));
-                        top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
-                        const double gy = round_to_float(fma(bb, bot - top, top));
-                        VG(m) = -gx * dirx + gy * diry;                                   // :1240
+                        if (useGy) {
+                            top = fma(a, h2d(d0y >> 16), h2d(p00.y >> 16)); bot = fma(a, h2d(d1y >> 16), h2d(p01.y >> 16));
+                            const double gy = round_to_float(fma(bb, bot - top, top));
+                            VG(m) = -gx * dirx + gy * diry;                               // :1240
+                        } else VG(m) = -gx * dirx;     // horizontal epipolar line: gy * 0 adds an exact zero, its four-corner blend is skipped
                         sR += vim;
                     }
                     // ---- the 49th sample of both patches, one (patch, channel, cell row) per lane ----
