@@ -238,7 +238,7 @@ class Context:
     def _ptr_array(self, imgs):
         arr = (C.c_void_p * len(imgs))()
         for k, im in enumerate(imgs):
-            arr[k] = im.ctypes.data
+            arr[k] = im.__array_interface__["data"][0]      # (im.ctypes.data builds a ctypes object per image: 1 ms per 320 images)
         return arr
 
     def stereo_batch(self, calib, L_imgs, R_imgs, cap, out=None, n_mates=None):
