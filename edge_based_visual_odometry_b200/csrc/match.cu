@@ -1014,7 +1014,7 @@ __device__ __forceinline__ void gn_store(const DevBatch& b, int f, int q, const 
 // What bounds it and what was tried in round 2: profiles/r02_gn_whatif.md, profiles/r02_gn_pair_experiment.md.
 // ------------------------------------------------------------------------------------------------------
 #ifndef GNL_MINB
-#define GNL_MINB 4
+#define GNL_MINB 5
 #endif
 #ifndef GNL_PXV
 #define GNL_PXV 256
