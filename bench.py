@@ -359,6 +359,18 @@ def main():
         packed = torch.empty((cap_rec, 64), dtype=torch.uint8, device=dev)
         offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
         mode = args.strong_gather
+        if world > 1 and mode in ("stream", "host"):
+            # the shared page-locked buffer lives in /dev/shm: fall back to the NCCL gather when the box does not have the room
+            need = world * (-(-FS // world)) * int(per_frame) * 64
+            try:
+                st = os.statvfs("/dev/shm")
+                room = st.f_bavail * st.f_frsize
+            except OSError:
+                room = 0
+            ok = torch.tensor([1 if room > need + (64 << 20) else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                mode = "nccl"
         use_host = world > 1 and mode == "host"
         use_stream = mode == "stream"
         pf_rec = int(per_frame)
