@@ -260,7 +260,7 @@ int ebvo_cluster(ebvo_ctx* ctx, const ebvo_edge* edges, int n, int by_orientatio
  * p +- 8 (sin theta, -cos theta), size 1, angle deg(theta); out = n*2*128 floats (values 0..255).  Needs sift_mode 1. */
 int ebvo_sift_descriptors(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const ebvo_edge* edges, int n, float* out);
 /* cv::undistort(image, out, K, dist) of Pipeline::prepare_Stereo_Images (src/Pipeline.cpp:78-79) for one 8-bit image:
- * K row-major 3x3 (config/*.yaml intrinsics), dist = {k1, k2, p1, p2}; bit-identical to OpenCV 4.x (fixed-point remap). */
+ * K row-major 3x3 (the intrinsics of the config YAML files), dist = {k1, k2, p1, p2}; bit-identical to OpenCV 4.x (fixed-point remap). */
 int ebvo_undistort(ebvo_ctx* ctx, const uint8_t* img, int w, int h, int stride, const double K[9], const double dist[4], uint8_t* out,
                    int out_stride);
 /* util_compute_Img_Gradients (include/utility.h:131-141): Sobel 3x3 * 1/8, reflect-101 border. */

@@ -63,3 +63,15 @@ def test_product_package_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 assert "oracle" not in open(os.path.join(root, f)).read(), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/ebvo_b200.h compiles as C99 (and as C++) on its own, without warnings."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ebvo_b200.h"\nint main(void) { ebvo_params p; ebvo_mate m; ebvo_quad q; ebvo_calib c; (void)p; (void)m; (void)q; (void)c;\n'
+                   '  return (int)sizeof(ebvo_edge) - 32; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"], ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
